@@ -1,0 +1,193 @@
+/*
+ * pvt.h -- C ABI of the B200-native NCC tracking hot path (libpvt.so).
+ *
+ * Drop-in boundary for ONE path of askEric0/Parallel-Video-Object-Tracker: per-frame normalized
+ * cross-correlation search of the object template over the +-R window around the previous box,
+ * peak pick, confidence-gated EMA template update.  Plain pointers and sizes only; no C++ / torch
+ * types; nothing here throws or calls exit().  All compute runs in hand-written sm_100a CUDA
+ * kernels; there is NO CPU fallback: every entry point fails with PVT_ERR_CUDA when no CUDA device
+ * is usable.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   tracker/include/baseline_kernel.hpp:8-17   six baseline::ncc_match_* operators     -> pvt_ncc_match, pvt_ncc_match_batched
+ *   tracker/include/utils.hpp:5-14             toGrayF32                                -> pvt_to_gray_f32 (and the ingest stage of pvt_step)
+ *   tracker/src/main.cpp:6-20                  SEARCH_RADIUS_X/Y, NCC_*_CONFIDENCE, LR  -> pvt_params
+ *   tracker/src/main.cpp:70-71                 template cut from frame 0                -> pvt_track_init
+ *   tracker/src/main.cpp:103-161               NCC -> window clamp -> minMaxLoc -> gates -> addWeighted -> pvt_step / pvt_submit
+ *   tracker/src/main.cpp:115-130               --batch=N hold semantics                 -> pvt_params.mode == PVT_MODE_BATCH
+ *   tracker/src/baseline_kernel.cu:12-18       checkCuda -> exit(1)                     -> negative return code + pvt_last_error()
+ *
+ * Results follow the reference's `--cpu` path (cv::matchTemplate TM_CCOEFF_NORMED, OpenCV 4.13.0):
+ * identical peak per frame (ties -> lowest row-major index), scores within 1e-4, identical bbox
+ * trajectory (tests/ check this against oracle/ and the cv2 golden vectors).
+ *
+ * Threading: one pvt_ctx belongs to one device and is used from one host thread at a time;
+ * separate contexts are independent (that is the multi-GPU model: shard tracks over contexts).
+ */
+#ifndef PVT_H_
+#define PVT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PVT_API __attribute__((visibility("default")))
+#else
+#define PVT_API
+#endif
+
+#define PVT_VERSION 100
+
+/* return codes */
+#define PVT_OK               0
+#define PVT_ERR_INVALID     (-1) /* bad argument; where the reference CV_Asserts (ncc_cpu.cpp:7-10, baseline_kernel.cu:315-325) */
+#define PVT_ERR_CUDA        (-2) /* CUDA failure or no device; where the reference calls std::exit (baseline_kernel.cu:12-18)   */
+#define PVT_ERR_UNSUPPORTED (-3) /* e.g. PVT_MODE_CPU: the library has no CPU path                                             */
+#define PVT_ERR_STATE       (-4) /* call out of order (track not initialised, results pending, ...)                            */
+#define PVT_ERR_NOMEM       (-5)
+
+/* tracker/src/main.cpp:29-41 mode flags.  All GPU modes produce the same (OpenCV-semantics) numbers;
+ * the mode selects hold semantics (BATCH) and, with PVT_KERNEL_AUTO, nothing else. */
+typedef enum pvt_mode {
+    PVT_MODE_NAIVE = 0,       /* default in the reference (NCC_MODE = "naive", main.cpp:8) */
+    PVT_MODE_CPU = 1,         /* --cpu : rejected with PVT_ERR_UNSUPPORTED (oracle/ is the CPU path, test-only) */
+    PVT_MODE_SHARED = 2,      /* --shared */
+    PVT_MODE_CONST = 3,       /* --const */
+    PVT_MODE_CONST_TILED = 4, /* --const_tiled */
+    PVT_MODE_BATCH = 5        /* --batch=N : search every N-th frame, hold the box in between (main.cpp:115-130) */
+} pvt_mode;
+
+typedef enum pvt_kernel {
+    PVT_KERNEL_AUTO = 0,   /* production kernel (TMA-staged tile, register-blocked FP32) */
+    PVT_KERNEL_DIRECT = 1, /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
+    PVT_KERNEL_TILED = 2
+} pvt_kernel;
+
+typedef enum pvt_format { PVT_FMT_BGR8 = 0, PVT_FMT_GRAY8 = 1, PVT_FMT_GRAYF32 = 2 } pvt_format;
+typedef enum pvt_memory { PVT_MEM_HOST = 0, PVT_MEM_DEVICE = 1 } pvt_memory;
+
+/* tracker/src/main.cpp:6-20 */
+typedef struct pvt_params {
+    int search_radius_x;          /* SEARCH_RADIUS_X = 80 */
+    int search_radius_y;          /* SEARCH_RADIUS_Y = 80 */
+    double ncc_min_confidence;    /* NCC_MIN_CONFIDENCE = 0.40   (compared in double, main.cpp:153) */
+    double ncc_strong_confidence; /* NCC_STRONG_CONFIDENCE = 0.70 (main.cpp:157) */
+    double template_update_lr;    /* TEMPLATE_UPDATE_LR = 0.10   (main.cpp:159) */
+    int batch_size;               /* BATCH_SIZE = 4, used when mode == PVT_MODE_BATCH */
+    int mode;                     /* pvt_mode */
+    int kernel;                   /* pvt_kernel */
+    int keep_maps;                /* != 0: keep every track's last window map for pvt_get_window_map (tests) */
+    int reserved[4];
+} pvt_params;
+
+typedef struct pvt_config {
+    int device;       /* CUDA device ordinal */
+    int frame_w;      /* all streams of a context share one frame geometry */
+    int frame_h;
+    int max_streams;  /* independent frame sources (videos) */
+    int max_tracks;   /* tracked objects; each is bound to one stream */
+    int max_templ_w;  /* largest template (= bbox) a track may use */
+    int max_templ_h;
+    int max_radius_x; /* 0: take pvt_params.search_radius_x at creation */
+    int max_radius_y;
+    int reserved[7];
+} pvt_config;
+
+/* one input frame for one stream at one time step */
+typedef struct pvt_frame {
+    int stream;       /* 0 .. max_streams-1 */
+    int format;       /* pvt_format; BGR8 is what cv::VideoCapture hands the reference (main.cpp:95) */
+    int memory;       /* pvt_memory; host buffers are copied with cudaMemcpyAsync (pin them for overlap) */
+    int reserved;
+    const void* data; /* first row */
+    size_t step;      /* bytes per row (cv::Mat::step) */
+} pvt_frame;
+
+/* per-frame output the reference only draws (main.cpp:166); the new API emits it */
+typedef struct pvt_result {
+    int32_t x, y, w, h; /* bbox after this frame */
+    float conf;         /* bestVal of main.cpp:150 (NaN when the frame was held in batch mode) */
+    uint8_t moved;      /* conf >= ncc_min_confidence    (main.cpp:153) */
+    uint8_t updated;    /* conf >= ncc_strong_confidence (main.cpp:157): template EMA applied */
+    uint8_t searched;   /* 0 for frames held by batch mode */
+    uint8_t valid;      /* track was active and its stream had a frame */
+    int32_t track;
+    int32_t step;       /* time-step index since creation */
+} pvt_result;
+
+/* device-time accounting, filled when profiling is enabled (bench.py roofline) */
+typedef struct pvt_profile {
+    double ingest_ms, stats_ms, ncc_ms, update_ms; /* summed CUDA-event time per kernel class */
+    int64_t ingest_launches, stats_launches, ncc_launches, update_launches;
+    int64_t steps;
+    double ncc_macs;       /* algorithmic MACs (n_cand * tw * th) summed over the profiled steps */
+    double ingest_bytes;   /* algorithmic bytes read + written by the ingest kernel */
+} pvt_profile;
+
+typedef struct pvt_ctx pvt_ctx;
+
+PVT_API int pvt_version(void);
+PVT_API const char* pvt_last_error(void); /* thread-local, never NULL */
+PVT_API int pvt_device_count(void);       /* >= 0, or PVT_ERR_CUDA */
+/* sm count, clock (kHz), memory clock (kHz), total memory bytes, cc major*10+minor */
+PVT_API int pvt_device_info(int device, int* sm_count, int* sm_clock_khz, int* mem_clock_khz, size_t* mem_bytes, int* cc);
+
+PVT_API void pvt_default_params(pvt_params* p); /* the constants of main.cpp:6-20 */
+PVT_API int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* config);
+PVT_API int pvt_destroy(pvt_ctx* ctx);
+PVT_API int pvt_set_params(pvt_ctx* ctx, const pvt_params* params); /* radii must stay <= the creation maxima */
+
+/* pinned host memory for frames that are streamed from the host */
+PVT_API int pvt_alloc_pinned(void** out, size_t bytes);
+PVT_API int pvt_free_pinned(void* p);
+
+/* main.cpp:70-71: ingest `frame0` into its stream (NULL: keep the stream's current image) and cut the
+ * template of `track` from it at (x, y, w, h).  Synchronous. */
+PVT_API int pvt_track_init(pvt_ctx* ctx, int track, int stream, const pvt_frame* frame0, int x, int y, int w, int h);
+PVT_API int pvt_track_remove(pvt_ctx* ctx, int track);
+
+/* One time step (main.cpp:98-161 for every active track whose stream got a frame): ingest, window
+ * statistics, NCC search, peak, gates, EMA -- one CUDA-graph launch, no host round trip inside.
+ * pvt_step waits and writes one pvt_result per track slot 0..max_tracks-1 (results may be NULL).
+ * pvt_submit only enqueues; pvt_collect waits for everything submitted and returns the results of
+ * the last `max_steps` steps, oldest first, max_tracks entries per step; returns the step count. */
+PVT_API int pvt_step(pvt_ctx* ctx, int n_frames, const pvt_frame* frames, pvt_result* results);
+PVT_API int pvt_submit(pvt_ctx* ctx, int n_frames, const pvt_frame* frames);
+PVT_API int pvt_collect(pvt_ctx* ctx, pvt_result* results, int max_steps);
+PVT_API int pvt_sync(pvt_ctx* ctx);
+
+/* tracker state = {bbox, template} (the reference keeps it in host variables, main.cpp:63-71) */
+PVT_API int pvt_get_state(pvt_ctx* ctx, int track, int32_t bbox[4], float* templ, size_t templ_step_bytes);
+PVT_API int pvt_set_state(pvt_ctx* ctx, int track, const int32_t bbox[4], const float* templ, size_t templ_step_bytes);
+/* last window map of a track (needs params.keep_maps): win = {minTx, minTy, width, height} (main.cpp:143-147) */
+PVT_API int pvt_get_window_map(pvt_ctx* ctx, int track, float* out, size_t out_step_bytes, int32_t win[4]);
+
+/* utils.hpp:5-14 toGrayF32 on its own: BGR8/GRAY8 -> f32/255 image (host or device destination) */
+PVT_API int pvt_to_gray_f32(pvt_ctx* ctx, const pvt_frame* frame, float* out, size_t out_step_bytes, int out_memory);
+
+/* baseline_kernel.hpp:8-17 map-level operators: full (fh-th+1) x (fw-tw+1) map, host buffers in, host
+ * buffer out, synchronous -- the contract of ncc_match_naive_cuda / _shared_cuda / _const / _const_tiled
+ * (mode picks nothing but is validated; PVT_MODE_CPU -> PVT_ERR_UNSUPPORTED).  Unlike the reference's
+ * GPU modes there is no 4096-pixel template limit (baseline_kernel.cu:500) and no 48 KB limit. */
+PVT_API int pvt_ncc_match(int device, int mode, const float* frame, int fw, int fh, size_t fstep_bytes,
+                          const float* templ, int tw, int th, size_t tstep_bytes, float* out, size_t ostep_bytes);
+/* baseline_kernel.hpp:14 ncc_match_naive_cuda_batched: n frames of one geometry against one template */
+PVT_API int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes,
+                                  const float* templ, int tw, int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes);
+
+/* measurement hooks */
+PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA events, plain stream launches */
+PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);
+PVT_API int64_t pvt_launch_count(pvt_ctx* ctx); /* kernels launched by this context so far (graph nodes counted per launch) */
+/* device time of everything submitted between pvt_timer_start and pvt_timer_stop, CUDA events on the context's stream */
+PVT_API int pvt_timer_start(pvt_ctx* ctx);
+PVT_API int pvt_timer_stop(pvt_ctx* ctx, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVT_H_ */

@@ -1,0 +1,541 @@
+// Hand-written sm_100a kernels of the NCC tracking hot path.  One time step = the launch sequence
+//   k_ingest -> k_colsum -> k_rowsum -> k_ncc_tiled (or k_ncc_direct) -> k_update
+// captured once as a CUDA graph; every kernel finds "which frame / which step" through the
+// device-side step counter and frame table, so the graph is launched unchanged for every frame and
+// nothing returns to the host between frames.
+#pragma once
+#include <float.h>
+
+#include "pvt_device.cuh"
+
+namespace pvt {
+
+// =============================================================================================
+// (1) ingest: BGR u8 -> gray -> f32/255          reference: tracker/include/utils.hpp:5-14
+//     cvtColor(BGR2GRAY) 8u: (3735 B + 19235 G + 9798 R + 16384) >> 15   (bit-exact, tests G6)
+//     convertTo(CV_32F, 1.0f/255.0f): one rounding of g * 0x1.010102p-8
+// HBM-bound: 3 B read + 4 B written per pixel.  Each thread converts 4 pixels: three aligned 32-bit
+// loads (a warp reads 384 contiguous bytes) and one 16-byte store (a warp writes 512 contiguous bytes).
+// =============================================================================================
+__device__ __forceinline__ float gray_to_f32(unsigned int g) { return __fmul_rn((float)g, 1.0f / 255.0f); }
+__device__ __forceinline__ unsigned int bgr_to_gray(unsigned int b, unsigned int g, unsigned int r)
+{
+    return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256) k_ingest(Ctx c)
+{
+    const unsigned long long step = *c.step;
+    const int stream = blockIdx.y;
+    const FrameDesc d = c.table[(step % kRing) * c.max_streams + stream];
+    if (!d.valid) return;
+    const int gpr = (c.W + 3) >> 2;  // 4-pixel groups per row
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * c.H) return;
+    const int y = (int)(gid / gpr), x = ((int)(gid - (long long)y * gpr)) << 2;
+    float* out = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch + x;
+    const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
+    const int n = min(4, c.W - x);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.format == PVT_FMT_BGR8) {
+        const unsigned char* p = row + 3 * x;
+        if (n == 4 && ((((size_t)p) & 3) == 0)) {
+            const unsigned int* p32 = (const unsigned int*)p;
+            unsigned int a = __ldg(p32), b = __ldg(p32 + 1), e = __ldg(p32 + 2);
+            // bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            o.x = gray_to_f32(bgr_to_gray(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u));
+            o.y = gray_to_f32(bgr_to_gray(a >> 24, b & 255u, (b >> 8) & 255u));
+            o.z = gray_to_f32(bgr_to_gray((b >> 16) & 255u, b >> 24, e & 255u));
+            o.w = gray_to_f32(bgr_to_gray((e >> 8) & 255u, (e >> 16) & 255u, e >> 24));
+        } else {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < n; ++i) v[i] = gray_to_f32(bgr_to_gray(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+            o = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else if (d.format == PVT_FMT_GRAY8) {
+        const unsigned char* p = row + x;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < n; ++i) v[i] = gray_to_f32(p[i]);
+        o = make_float4(v[0], v[1], v[2], v[3]);
+    } else {  // PVT_FMT_GRAYF32: already toGrayF32 output, re-pitch into the pool
+        const float* p = (const float*)row + x;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < n; ++i) v[i] = p[i];
+        o = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    *reinterpret_cast<float4*>(out) = o;  // pitch is a multiple of 4 floats: always in bounds, 16-byte aligned
+}
+
+// =============================================================================================
+// (2) window statistics in FP64 -- what cv::matchTemplate gets from cv::integral(..., CV_64F):
+//     wsum = sum of f, wsq = sum of f^2 over every candidate's tw x th window, then OpenCV's
+//     normaliser (common_matchTemplate, TM_CCOEFF_NORMED):
+//       diff2 = max(wsq - wsum^2 * invArea, 0)
+//       t     = diff2 <= min(0.5, 10*FLT_EPSILON*wsq) ? 0 : sqrt(diff2) * sigma_t / sqrt(invArea)
+//     Separable box sums: k_colsum (vertical, sliding) then k_rowsum (row prefix, difference).
+//     For u8-sourced frames every partial sum of f is exactly representable in double, so wsum is
+//     bit-identical to OpenCV's whole-frame integral; wsq agrees to ~1e-16 relative.
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_colsum(Ctx c)
+{
+    const int track = blockIdx.z;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const DevParams P = *c.params;
+    int win[4];
+    search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) t.win[threadIdx.x] = win[threadIdx.x];
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tileW = win[2] + t.w - 1;
+    const int yb = blockIdx.y * kColsumRows;
+    if (X >= tileW || yb >= win[3]) return;
+    const int ye = min(yb + kColsumRows, win[3]);
+    const int th = t.h;
+    const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)(win[1] + yb) * c.pitch + win[0] + X;
+    double s = 0.0, q = 0.0;
+    for (int dy = 0; dy < th; ++dy) {
+        double v = (double)col[(size_t)dy * c.pitch];
+        s += v;
+        q += v * v;
+    }
+    size_t o = ((size_t)track * c.Hmax + yb) * c.VW + X;
+    c.vsum[o] = s;
+    c.vsq[o] = q;
+    for (int y = yb + 1; y < ye; ++y) {
+        double vn = (double)col[(size_t)(y - yb + th - 1) * c.pitch];
+        double vo = (double)col[(size_t)(y - yb - 1) * c.pitch];
+        s = (s + vn) - vo;
+        q = (q + vn * vn) - vo * vo;
+        o += c.VW;
+        c.vsum[o] = s;
+        c.vsq[o] = q;
+    }
+}
+
+// one warp per candidate row: inclusive prefix of the vertical sums along x (8 consecutive values per
+// lane + warp scan, with a carry between 256-wide segments), then box sum = P[x+tw] - P[x].
+__global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per prefix row in smem */)
+{
+    extern __shared__ double sm_d[];
+    const int track = blockIdx.y;
+    const TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * warps + w;
+    const int ww = t.win[2], wh = t.win[3], tw = t.w;
+    if (y >= wh) return;  // warp-uniform
+    const int tileW = ww + tw - 1;
+    double* Ps = sm_d + (size_t)w * 2 * pw;
+    double* Pq = Ps + pw;
+    const double* vs = c.vsum + ((size_t)track * c.Hmax + y) * c.VW;
+    const double* vq = c.vsq + ((size_t)track * c.Hmax + y) * c.VW;
+    double carry_s = 0.0, carry_q = 0.0;
+    for (int base = 0; base < tileW; base += 256) {
+        const int i0 = base + lane * 8;
+        double ls[8], lq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool ok = i0 + k < tileW;
+            ls[k] = ok ? vs[i0 + k] : 0.0;
+            lq[k] = ok ? vq[i0 + k] : 0.0;
+        }
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            ls[k] += ls[k - 1];
+            lq[k] += lq[k - 1];
+        }
+        double is = ls[7], iq = lq[7];  // inclusive warp scan of the lane totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double ns = shfl_up_f64(is, d), nq = shfl_up_f64(iq, d);
+            if (lane >= d) { is += ns; iq += nq; }
+        }
+        const double off_s = carry_s + (is - ls[7]), off_q = carry_q + (iq - lq[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k < tileW) {
+                Ps[i0 + k + 1] = off_s + ls[k];
+                Pq[i0 + k + 1] = off_q + lq[k];
+            }
+        carry_s += shfl_f64(is, 31);
+        carry_q += shfl_f64(iq, 31);
+    }
+    if (lane == 0) { Ps[0] = 0.0; Pq[0] = 0.0; }
+    __syncwarp();
+    const double invArea = 1.0 / ((double)t.h * (double)tw);
+    const double tn = t.templ_norm;
+    double* dn = c.denom + (size_t)track * c.Hmax * c.Wmax + (size_t)y * ww;
+    for (int x = lane; x < ww; x += 32) {
+        const double wsum = Ps[x + tw] - Ps[x];
+        const double wsq = Pq[x + tw] - Pq[x];
+        // exactly OpenCV's operation order, no contraction: wndMean2 = t*t; wndMean2 *= invArea
+        const double wm2 = __dmul_rn(__dmul_rn(wsum, wsum), invArea);
+        double diff2 = __dsub_rn(wsq, wm2);
+        if (diff2 < 0.0) diff2 = 0.0;
+        double lim = __dmul_rn(10.0 * (double)FLT_EPSILON, wsq);
+        if (lim > 0.5) lim = 0.5;
+        dn[x] = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
+    }
+}
+
+// OpenCV's final rule for TM_CCOEFF_NORMED (common_matchTemplate): never NaN, always in [-1, 1]
+__device__ __forceinline__ float ncc_finalize(float num_f32, double t, int flat_templ)
+{
+    if (flat_templ) return 1.0f;
+    double num = (double)num_f32;
+    double r;
+    if (fabs(num) < t) r = num / t;
+    else if (fabs(num) < t * 1.125) r = num > 0 ? 1.0 : -1.0;
+    else r = 0.0;
+    return (float)r;
+}
+
+// =============================================================================================
+// (3a) k_ncc_direct: verification twin of the reference's naive kernel (baseline_kernel.cu:21-64):
+//      one thread per candidate, operands from global/L2 -- but with this library's numerics
+//      (centred template, per-template-row FP32 partials, FP64 normaliser).  PVT_KERNEL_DIRECT.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_ncc_direct(Ctx c)
+{
+    const int track = blockIdx.y;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const int ww = t.win[2], wh = t.win[3];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (idx < ww * wh) {
+        const int y = idx / ww, x = idx - y * ww;
+        const float* f = c.gray + (size_t)t.stream * c.plane + (size_t)(t.win[1] + y) * c.pitch + t.win[0] + x;
+        const float* tc = c.templc + (size_t)track * c.mth * c.mtp;
+        float acc = 0.f;
+        for (int dy = 0; dy < t.h; ++dy) {
+            float r = 0.f;
+            for (int dx = 0; dx < t.w; ++dx) r = fmaf(f[(size_t)dy * c.pitch + dx], tc[dy * t.tp + dx], r);
+            acc += r;
+        }
+        const double dn = c.denom[(size_t)track * c.Hmax * c.Wmax + idx];
+        const float v = ncc_finalize(acc, dn, t.flat);
+        if (c.params->keep_maps) c.maps[(size_t)track * c.Hmax * c.Wmax + idx] = v;
+        key = peak_key(v, (unsigned int)idx);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(key, m);
+        key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+}
+
+// =============================================================================================
+// (3b) k_ncc_tiled: the production cross-term kernel.
+//   CTA = (track, block of NC thread-columns, band of CY*SB candidate rows).
+//   Staging: ONE cp.async.bulk.tensor.3d (TMA) brings the CTA's search sub-tile
+//   [CY*SB + th - 1 rows] x [8*NC + tp + 4 cols] of the stream's gray plane into shared memory, and one
+//   cp.async.bulk brings the track's centred template; both complete on one mbarrier.  Tile origin
+//   (the clamped search window) is read from device state, so no host involvement per frame.
+//   Compute: thread (col, slot) owns 8 consecutive candidates in x times CY candidates in y
+//   (rows slot + SB*cy): 32 FP32 accumulators.  For each template row it sweeps dx in steps of 8 with a
+//   16-float sliding window per candidate row held in registers: per 8 dx it issues CY*2 + 2 LDS.128
+//   for 64*CY FFMA (96 % FMA instructions).  Consecutive lanes are consecutive tile rows and the tile
+//   pitch is == 4 (mod 8) floats, so every quarter-warp LDS.128 hits 8 distinct 16-byte bank groups
+//   (conflict-free); template reads are warp-uniform broadcasts.
+//   Numerics: products with the centred template fl32(t - mean_t); one FP32 partial per template row,
+//   rows then added in FP32 (SURVEY.md §7 scheme (B)); normalisation in FP64 exactly as OpenCV.
+//   Epilogue: finalize, (score desc, index asc) key, warp-shuffle max, one atomicMax per warp.
+// =============================================================================================
+template <int CY>
+__device__ __forceinline__ void fma_sweep8(float (&racc)[CY][8], const float (&lo)[CY][8], const float (&hi)[CY][8], const float (&t)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int cy = 0; cy < CY; ++cy)
+#pragma unroll
+            for (int cx = 0; cx < 8; ++cx) {
+                const int i = k + cx;
+                const float v = i < 8 ? lo[cy][i] : hi[cy][i - 8];
+                racc[cy][cx] = fmaf(v, t[k], racc[cy][cx]);
+            }
+}
+
+template <int CY>
+__device__ __forceinline__ void load8(float (&w)[CY][8], const float* p, int rstride)
+{
+#pragma unroll
+    for (int cy = 0; cy < CY; ++cy) {
+        const float4 a = *reinterpret_cast<const float4*>(p + cy * rstride);
+        const float4 b = *reinterpret_cast<const float4*>(p + cy * rstride + 4);
+        w[cy][0] = a.x; w[cy][1] = a.y; w[cy][2] = a.z; w[cy][3] = a.w;
+        w[cy][4] = b.x; w[cy][5] = b.y; w[cy][6] = b.z; w[cy][7] = b.w;
+    }
+}
+
+struct TileCfg {
+    int NC, SB;        // thread-columns and row-slots per CTA
+    int boxW, boxH;    // TMA box (floats, rows) == shared tile pitch / height
+    int ncb, nbands;   // CTAs per track along x and y
+};
+
+template <int CY>
+__global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    const int track = blockIdx.y;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const int ww = t.win[2], wh = t.win[3];
+    const int cb = blockIdx.x % g.ncb, band = blockIdx.x / g.ncb;
+    const int cx0 = cb * g.NC * 8, cy0 = band * CY * g.SB;  // first candidate of this CTA inside the window
+    if (cx0 >= ww || cy0 >= wh) return;
+
+    float* s_tile = reinterpret_cast<float*>(sm_raw);
+    float* s_templ = s_tile + (size_t)g.boxW * g.boxH;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_templ + (size_t)c.mth * c.mtp);
+    const int tp = t.tp, th = t.h;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        const uint32_t tbytes = (uint32_t)(th * tp) * 4u;
+        mbar_arrive_expect_tx(bar, (uint32_t)(g.boxW * g.boxH) * 4u + tbytes);
+        tma_load_3d(s_tile, &tmap, bar, t.win[0] + cx0, t.win[1] + cy0, t.stream);
+        bulk_load(s_templ, c.templc + (size_t)track * c.mth * c.mtp, tbytes, bar);
+    }
+    __syncthreads();  // barrier initialised before anybody polls it
+    mbar_wait(bar, 0);
+
+    const int q = threadIdx.x;
+    const int col = q / g.SB, slot = q - col * g.SB;
+    unsigned long long key = 0ull;
+    if (col < g.NC && cx0 + col * 8 < ww && cy0 + slot < wh) {
+        const int P = g.boxW;
+        const int rstride = g.SB * P;
+        const float* base = s_tile + (size_t)slot * P + col * 8;
+        float acc[CY][8];
+#pragma unroll
+        for (int cy = 0; cy < CY; ++cy)
+#pragma unroll
+            for (int cx = 0; cx < 8; ++cx) acc[cy][cx] = 0.f;
+
+        for (int dy = 0; dy < th; ++dy) {
+            const float* frow = base + (size_t)dy * P;
+            const float* trow = s_templ + dy * tp;
+            float racc[CY][8];
+#pragma unroll
+            for (int cy = 0; cy < CY; ++cy)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) racc[cy][cx] = 0.f;
+            float wa[CY][8], wb[CY][8], tt[8];
+            load8<CY>(wa, frow, rstride);
+            for (int j = 0; j < tp; j += 16) {
+                load8<CY>(wb, frow + j + 8, rstride);
+                {
+                    const float4 a = *reinterpret_cast<const float4*>(trow + j);
+                    const float4 b = *reinterpret_cast<const float4*>(trow + j + 4);
+                    tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = b.x; tt[5] = b.y; tt[6] = b.z; tt[7] = b.w;
+                }
+                fma_sweep8<CY>(racc, wa, wb, tt);
+                if (j + 8 < tp) {
+                    load8<CY>(wa, frow + j + 16, rstride);
+                    const float4 a = *reinterpret_cast<const float4*>(trow + j + 8);
+                    const float4 b = *reinterpret_cast<const float4*>(trow + j + 12);
+                    tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = b.x; tt[5] = b.y; tt[6] = b.z; tt[7] = b.w;
+                    fma_sweep8<CY>(racc, wb, wa, tt);
+                }
+            }
+#pragma unroll
+            for (int cy = 0; cy < CY; ++cy)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) acc[cy][cx] += racc[cy][cx];
+        }
+
+        const double* dn = c.denom + (size_t)track * c.Hmax * c.Wmax;
+        float* mp = c.params->keep_maps ? c.maps + (size_t)track * c.Hmax * c.Wmax : nullptr;
+        const int flat = t.flat;
+#pragma unroll
+        for (int cy = 0; cy < CY; ++cy) {
+            const int y = cy0 + slot + g.SB * cy;
+            if (y < wh) {
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) {
+                    const int x = cx0 + col * 8 + cx;
+                    if (x < ww) {
+                        const unsigned int idx = (unsigned int)(y * ww + x);
+                        const float v = ncc_finalize(acc[cy][cx], dn[idx], flat);
+                        if (mp) mp[idx] = v;
+                        const unsigned long long k = peak_key(v, idx);
+                        key = k > key ? k : key;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(key, m);
+        key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+}
+
+// =============================================================================================
+// (4) template statistics + centred template (block-cooperative, 256 threads)
+//     cv::meanStdDev in double: mean = s/N, sigma^2 = max(sq/N - mean^2, 0);
+//     matchTemplate: all-ones map if sigma^2 < DBL_EPSILON; templNorm = sqrt(sigma^2)/sqrt(1/N).
+// =============================================================================================
+__device__ void refresh_template(const Ctx& c, int track, TrackState& t, double* red /* 2*256 doubles of smem */)
+{
+    const int tw = t.w, th = t.h, n = tw * th, tid = threadIdx.x;
+    const float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    double s = 0.0, q = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        double v = (double)tp_[i];
+        s += v;
+        q += v * v;
+    }
+    red[tid] = s;
+    red[256 + tid] = q;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (tid < d) {
+            red[tid] += red[tid + d];
+            red[256 + tid] += red[256 + tid + d];
+        }
+        __syncthreads();
+    }
+    const double scale = 1.0 / (double)n;
+    const double mean = __dmul_rn(red[0], scale);
+    double var = __dsub_rn(__dmul_rn(red[256], scale), __dmul_rn(mean, mean));
+    if (var < 0.0) var = 0.0;
+    const double sdv = sqrt(var);
+    const double norm2 = __dmul_rn(sdv, sdv);
+    const int tpad = (tw + 7) & ~7;
+    if (tid == 0) {
+        t.mean = mean;
+        t.flat = norm2 < DBL_EPSILON;
+        t.templ_norm = sqrt(norm2) / sqrt(scale);
+        t.tp = tpad;
+    }
+    float* tc = c.templc + (size_t)track * c.mth * c.mtp;
+    for (int i = tid; i < th * tpad; i += blockDim.x) {
+        const int y = i / tpad, x = i - y * tpad;
+        tc[i] = x < tw ? (float)((double)tp_[y * tw + x] - mean) : 0.f;
+    }
+    __syncthreads();
+}
+
+// main.cpp:70-71: templ = frame_gray_f32(bbox).clone()
+__global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream, int x, int y, int w, int h)
+{
+    __shared__ double red[512];
+    TrackState& t = c.tracks[track];
+    const float* g = c.gray + (size_t)stream * c.plane;
+    float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int r = i / w, col = i - r * w;
+        tp_[i] = g[(size_t)(y + r) * c.pitch + x + col];
+    }
+    if (threadIdx.x == 0) {
+        t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull;
+        t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
+    }
+    __syncthreads();
+    refresh_template(c, track, t, red);
+}
+
+// re-derive statistics after pvt_set_state wrote bbox/template from the host
+__global__ void __launch_bounds__(256) k_track_refresh(Ctx c, int track)
+{
+    __shared__ double red[512];
+    refresh_template(c, track, c.tracks[track], red);
+}
+
+// =============================================================================================
+// (5) k_update: peak -> gates -> bbox -> EMA -> next frame's template statistics, one CTA per track.
+//     main.cpp:150-161.  bestVal is the float peak widened to double and compared in double
+//     (0.7f < 0.7, so a float compare would flip decisions).  cv::addWeighted on CV_32F:
+//     templ' = (float) fma((double)templ, 1-lr, (double)patch * lr)   -- bit-exact (tests G5).
+//     The last CTA to finish advances the device step counter: the next graph launch then picks the
+//     next frame-table entry without any host action.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_update(Ctx c)
+{
+    __shared__ double red[512];
+    const int track = blockIdx.x;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    pvt_result* res = c.results + (step % kRing) * c.max_tracks + track;
+    const bool stepped = track_stepped(c, t, step);
+    if (stepped) {
+        const DevParams P = *c.params;
+        const unsigned long long key = t.peak;
+        const float val = unord_f32((unsigned int)(key >> 32));
+        const unsigned int idx = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+        const int ww = t.win[2];
+        const int bx = t.win[0] + (int)(idx % (unsigned int)ww), by = t.win[1] + (int)(idx / (unsigned int)ww);
+        const double best = (double)val;
+        const bool moved = best >= P.min_conf;
+        const bool updated = moved && best >= P.strong_conf;
+        const int nx = moved ? bx : t.x, ny = moved ? by : t.y;
+        __syncthreads();  // everyone has read t.peak / t.x / t.y
+        if (updated) {
+            const int tw = t.w, n = tw * t.h;
+            const double alpha = 1.0 - P.lr, beta = P.lr;
+            float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+            const float* g = c.gray + (size_t)t.stream * c.plane + (size_t)ny * c.pitch + nx;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int r = i / tw, col = i - r * tw;
+                const double pb = __dmul_rn((double)g[(size_t)r * c.pitch + col], beta);
+                tp_[i] = (float)fma((double)tp_[i], alpha, pb);
+            }
+            __syncthreads();
+            refresh_template(c, track, t, red);
+        }
+        if (threadIdx.x == 0) {
+            t.x = nx; t.y = ny; t.peak = 0ull;
+            atomicAdd(c.macs, (unsigned long long)t.win[2] * t.win[3] * t.w * t.h);
+            res->x = nx; res->y = ny; res->w = t.w; res->h = t.h;
+            res->conf = val; res->moved = moved; res->updated = updated; res->searched = 1; res->valid = 1;
+            res->track = track; res->step = (int32_t)step;
+        }
+    } else if (threadIdx.x == 0) {
+        res->x = t.x; res->y = t.y; res->w = t.w; res->h = t.h;
+        res->conf = __int_as_float(0x7fc00000);
+        res->moved = 0; res->updated = 0; res->searched = 0; res->valid = (uint8_t)(t.active != 0);
+        res->track = track; res->step = (int32_t)step;
+    }
+    // last CTA done -> advance the time step (every CTA has read *c.step before taking a ticket)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int n = atomicAdd(c.ticket, 1u);
+        if (n == gridDim.x - 1) {
+            *c.ticket = 0u;
+            *c.step = step + 1ull;
+            __threadfence();
+        }
+    }
+}
+
+// hold step (batch mode, main.cpp:118-123): no NCC, no update; emit the stale box and advance
+__global__ void k_hold(Ctx c)
+{
+    const unsigned long long step = *c.step;
+    for (int track = threadIdx.x; track < c.max_tracks; track += blockDim.x) {
+        const TrackState& t = c.tracks[track];
+        pvt_result* res = c.results + (step % kRing) * c.max_tracks + track;
+        res->x = t.x; res->y = t.y; res->w = t.w; res->h = t.h;
+        res->conf = __int_as_float(0x7fc00000);
+        res->moved = 0; res->updated = 0; res->searched = 0;
+        res->valid = (uint8_t)(t.active != 0);
+        res->track = track; res->step = (int32_t)step;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *c.step = step + 1ull;
+}
+
+}  // namespace pvt

@@ -1,0 +1,879 @@
+// libpvt.so -- C-ABI entry points (include/pvt.h) over the sm_100a kernels in kernels.cuh.
+// Host code is C++; no torch, no CPU compute path: without a CUDA device every call fails loudly.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace pvt;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(PVT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                                          ":" + std::to_string(__LINE__) + ")");                            \
+    } while (0)
+
+constexpr int kStageDepth = 3;  // host frames in flight per stream (H2D overlaps the previous step's kernels)
+constexpr size_t kSmemBudget = 227u * 1024u;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+}  // namespace
+
+struct pvt_ctx {
+    pvt_params params{};
+    pvt_config cfg{};
+    Ctx d{};  // by-value kernel argument
+    TileCfg tile{};
+    CUtensorMap tmap{};
+    size_t ncc_smem = 0;
+    int rowsum_warps = 8, rowsum_pw = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaGraphExec_t graph = nullptr, graph_hold = nullptr;
+    bool graph_valid = false;
+    std::vector<void*> allocs;
+    FrameDesc* h_table = nullptr;  // pinned, [kRing][max_streams]
+    cudaEvent_t table_ev[kRing]{};
+    bool table_ev_used[kRing]{};
+    std::vector<void*> stage;  // [max_streams * kStageDepth], lazily allocated
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_done[kStageDepth]{}, ev_copied[kStageDepth]{};
+    bool ev_done_used[kStageDepth]{};
+    unsigned long long submitted = 0;  // time steps enqueued
+    int hold_pending = 0;              // batch mode: frames since the last searched one
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<EventPair> ev_pool;
+    size_t ev_next = 0;
+    pvt_profile prof{};
+    unsigned long long* d_macs = nullptr;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    pvt_result* h_results = nullptr;  // pinned, [kRing][max_tracks]
+    std::vector<int> track_stream;    // host mirror: -1 = inactive
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
+{
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256)));
+    if (zero) CK(cudaMemset(q, 0, std::max<size_t>(n * sizeof(T), 256)));
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return PVT_OK;
+}
+
+// Pick the CTA shape of k_ncc_tiled: NC thread-columns x SB row-slots (each thread 8 x kCY candidates).
+// Maximises (useful candidate fraction) x (SM occupancy, capped at 8 warps) x (warps per CTA balanced over
+// the 4 SM sub-partitions), subject to the TMA box limits (<= 256 per dim) and the 227 KB shared memory.
+bool choose_tile(int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
+{
+    double best = -1.0;
+    const int cols = (Wmax + 7) / 8;
+    for (int NC = 1; NC <= 24; ++NC)
+        for (int SB = 1; SB <= 64; ++SB) {
+            const int threads = NC * SB;
+            if (threads > 256) continue;
+            const int boxW = 8 * NC + mtp + 4, boxH = kCY * SB + mth - 1;
+            if (boxW > 256 || boxH > 256) continue;
+            const size_t smem = (size_t)boxW * boxH * 4 + (size_t)mth * mtp * 4 + 16;
+            if (smem > kSmemBudget) continue;
+            const int warps = (threads + 31) / 32;
+            const int ncb = (cols + NC - 1) / NC, nb = (Hmax + kCY * SB - 1) / (kCY * SB);
+            const double useful = (double)Wmax * Hmax / ((double)ncb * nb * warps * 32 * 8 * kCY);
+            const int per_sm = (int)std::min<size_t>(kSmemBudget / smem, 8);
+            const double occ = std::min(1.0, per_sm * warps / 8.0);
+            const int w4 = per_sm * warps;
+            const double bal = (double)w4 / (((w4 + 3) / 4) * 4);
+            const double lanes = (SB >= 8) ? 1.0 : 0.7;  // < 8 consecutive row-slots per column: bank conflicts
+            const double score = useful * occ * bal * lanes;
+            if (score > best) {
+                best = score;
+                *out = TileCfg{NC, SB, boxW, boxH, ncb, nb};
+                *smem_out = smem;
+            }
+        }
+    return best > 0;
+}
+
+int encode_tmap(pvt_ctx* c)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    const Ctx& d = c->d;
+    cuuint64_t dims[3] = {(cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.max_streams};
+    cuuint64_t strides[2] = {(cuuint64_t)d.pitch * 4, (cuuint64_t)d.plane * 4};
+    cuuint32_t box[3] = {(cuuint32_t)c->tile.boxW, (cuuint32_t)c->tile.boxH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.gray, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+    return PVT_OK;
+}
+
+int upload_params(pvt_ctx* c)
+{
+    DevParams p{};
+    p.rx = c->params.search_radius_x;
+    p.ry = c->params.search_radius_y;
+    p.min_conf = c->params.ncc_min_confidence;
+    p.strong_conf = c->params.ncc_strong_confidence;
+    p.lr = c->params.template_update_lr;
+    p.keep_maps = c->params.keep_maps;
+    CK(cudaMemcpyAsync(c->d.params, &p, sizeof(p), cudaMemcpyHostToDevice, c->compute));
+    CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+int validate_params(const pvt_params* p)
+{
+    if (!p) return fail(PVT_ERR_INVALID, "params is NULL");
+    if (p->mode == PVT_MODE_CPU)
+        return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path (the CPU oracle lives in oracle/, test-only)");
+    if (p->mode < PVT_MODE_NAIVE || p->mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
+    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TILED) return fail(PVT_ERR_INVALID, "unknown kernel variant");
+    if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
+    if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
+    if (!(p->template_update_lr >= 0.0 && p->template_update_lr <= 1.0)) return fail(PVT_ERR_INVALID, "template_update_lr outside [0,1]");
+    return PVT_OK;
+}
+
+enum { CLS_INGEST = 0, CLS_STATS = 1, CLS_NCC = 2, CLS_UPDATE = 3 };
+
+int prof_begin(pvt_ctx* c, int cls, EventPair** out)
+{
+    if (c->ev_next == c->ev_pool.size()) {
+        EventPair p{};
+        CK(cudaEventCreate(&p.a));
+        CK(cudaEventCreate(&p.b));
+        c->ev_pool.push_back(p);
+    }
+    EventPair* p = &c->ev_pool[c->ev_next++];
+    p->cls = cls;
+    CK(cudaEventRecord(p->a, c->compute));
+    *out = p;
+    return PVT_OK;
+}
+
+// the kernels of one searched time step, on c->compute (captured into the graph or launched directly)
+int launch_step_kernels(pvt_ctx* c, bool profile)
+{
+    const Ctx& d = c->d;
+    EventPair* ep = nullptr;
+    const int gpr = (d.W + 3) / 4;
+    const long long groups = (long long)gpr * d.H;
+    if (profile) { int r = prof_begin(c, CLS_INGEST, &ep); if (r) return r; }
+    k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+
+    if (profile) { int r = prof_begin(c, CLS_STATS, &ep); if (r) return r; }
+    k_colsum<<<dim3((d.VW + 127) / 128, (d.Hmax + kColsumRows - 1) / kColsumRows, d.max_tracks), 128, 0, c->compute>>>(d);
+    k_rowsum<<<dim3((d.Hmax + c->rowsum_warps - 1) / c->rowsum_warps, d.max_tracks), c->rowsum_warps * 32,
+               (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), c->compute>>>(d, c->rowsum_pw);
+    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+
+    if (profile) { int r = prof_begin(c, CLS_NCC, &ep); if (r) return r; }
+    if (c->params.kernel == PVT_KERNEL_DIRECT) {
+        k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
+    } else {
+        const int threads = ((c->tile.NC * c->tile.SB + 31) / 32) * 32;
+        k_ncc_tiled<kCY><<<dim3(c->tile.ncb * c->tile.nbands, d.max_tracks), threads, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+    }
+    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+
+    if (profile) { int r = prof_begin(c, CLS_UPDATE, &ep); if (r) return r; }
+    k_update<<<d.max_tracks, 256, 0, c->compute>>>(d);
+    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    CK(cudaGetLastError());
+    return PVT_OK;
+}
+
+int build_graphs(pvt_ctx* c)
+{
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+    if (c->graph_hold) { cudaGraphExecDestroy(c->graph_hold); c->graph_hold = nullptr; }
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+    int r = launch_step_kernels(c, false);
+    cudaError_t e = cudaStreamEndCapture(c->compute, &g);
+    if (r) return r;
+    CK(e);
+    CK(cudaGraphInstantiate(&c->graph, g, 0));
+    CK(cudaGraphDestroy(g));
+    CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+    k_hold<<<1, 256, 0, c->compute>>>(c->d);
+    CK(cudaStreamEndCapture(c->compute, &g));
+    CK(cudaGraphInstantiate(&c->graph_hold, g, 0));
+    CK(cudaGraphDestroy(g));
+    c->graph_valid = true;
+    return PVT_OK;
+}
+
+size_t frame_row_bytes(const pvt_ctx* c, int format)
+{
+    return (size_t)c->cfg.frame_w * (format == PVT_FMT_BGR8 ? 3 : format == PVT_FMT_GRAY8 ? 1 : 4);
+}
+
+int check_frame(const pvt_ctx* c, const pvt_frame* f)
+{
+    if (!f->data) return fail(PVT_ERR_INVALID, "frame.data is NULL");
+    if (f->stream < 0 || f->stream >= c->cfg.max_streams) return fail(PVT_ERR_INVALID, "frame.stream out of range");
+    if (f->format < PVT_FMT_BGR8 || f->format > PVT_FMT_GRAYF32) return fail(PVT_ERR_INVALID, "unknown frame format");
+    if (f->memory != PVT_MEM_HOST && f->memory != PVT_MEM_DEVICE) return fail(PVT_ERR_INVALID, "unknown frame memory kind");
+    if (f->step < frame_row_bytes(c, f->format)) return fail(PVT_ERR_INVALID, "frame.step smaller than one row");
+    if (f->format == PVT_FMT_GRAYF32 && (f->step % 4 || ((size_t)f->data) % 4)) return fail(PVT_ERR_INVALID, "f32 frame not 4-byte aligned");
+    return PVT_OK;
+}
+
+// Enqueue one time step.  hold: batch-mode frame that is not searched (main.cpp:118-123).
+int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
+{
+    const int slot = (int)(c->submitted % kRing);
+    const int ms = c->cfg.max_streams;
+    FrameDesc* row = c->h_table + (size_t)slot * ms;
+    if (c->table_ev_used[slot]) CK(cudaEventSynchronize(c->table_ev[slot]));  // previous upload of this pinned row is done
+    for (int s = 0; s < ms; ++s) row[s] = FrameDesc{nullptr, 0, 0, 0};
+    const int sd = (int)(c->submitted % kStageDepth);
+    bool copied = false;
+    if (!hold) {
+        for (int i = 0; i < n_frames; ++i) {
+            const pvt_frame* f = frames + i;
+            int r = check_frame(c, f);
+            if (r) return r;
+            if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
+            FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
+            if (f->memory == PVT_MEM_HOST) {
+                void*& st = c->stage[(size_t)f->stream * kStageDepth + sd];
+                if (!st) {
+                    CK(cudaMalloc(&st, c->stage_bytes));
+                    c->allocs.push_back(st);
+                }
+                if (!copied && c->ev_done_used[sd]) CK(cudaStreamWaitEvent(c->copy, c->ev_done[sd], 0));  // staging slot free again
+                const size_t rb = frame_row_bytes(c, f->format);
+                CK(cudaMemcpy2DAsync(st, rb, f->data, f->step, rb, c->cfg.frame_h, cudaMemcpyHostToDevice, c->copy));
+                copied = true;
+                fd.data = st;
+                fd.step = rb;
+            }
+            row[f->stream] = fd;
+            c->prof.ingest_bytes += c->profiling ? (double)c->cfg.frame_w * c->cfg.frame_h * ((f->format == PVT_FMT_BGR8 ? 3 : f->format == PVT_FMT_GRAY8 ? 1 : 4) + 4) : 0.0;
+        }
+    }
+    if (copied) {
+        CK(cudaEventRecord(c->ev_copied[sd], c->copy));
+        CK(cudaStreamWaitEvent(c->compute, c->ev_copied[sd], 0));
+    }
+    CK(cudaMemcpyAsync(c->d.table + (size_t)slot * ms, row, sizeof(FrameDesc) * ms, cudaMemcpyHostToDevice, c->compute));
+    CK(cudaEventRecord(c->table_ev[slot], c->compute));
+    c->table_ev_used[slot] = true;
+    if (hold) {
+        if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
+        CK(cudaGraphLaunch(c->graph_hold, c->compute));
+        c->launches += 1;
+    } else if (c->profiling) {
+        int r = launch_step_kernels(c, true);
+        if (r) return r;
+        c->launches += 5;
+        c->prof.steps += 1;
+    } else {
+        if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
+        CK(cudaGraphLaunch(c->graph, c->compute));
+        c->launches += 5;
+    }
+    if (copied) {
+        CK(cudaEventRecord(c->ev_done[sd], c->compute));
+        c->ev_done_used[sd] = true;
+    }
+    c->submitted += 1;
+    return PVT_OK;
+}
+
+int resolve_profile(pvt_ctx* c)
+{
+    CK(cudaStreamSynchronize(c->compute));
+    for (size_t i = 0; i < c->ev_next; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b));
+        switch (c->ev_pool[i].cls) {
+            case CLS_INGEST: c->prof.ingest_ms += ms; c->prof.ingest_launches += 1; break;
+            case CLS_STATS: c->prof.stats_ms += ms; c->prof.stats_launches += 2; break;
+            case CLS_NCC: c->prof.ncc_ms += ms; c->prof.ncc_launches += 1; break;
+            default: c->prof.update_ms += ms; c->prof.update_launches += 1; break;
+        }
+    }
+    c->ev_next = 0;
+    return PVT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int pvt_version(void) { return PVT_VERSION; }
+const char* pvt_last_error(void) { return g_err.c_str(); }
+
+int pvt_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(PVT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return n;
+}
+
+int pvt_device_info(int device, int* sm_count, int* sm_clock_khz, int* mem_clock_khz, size_t* mem_bytes, int* cc)
+{
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    int clk = 0, mclk = 0;
+    CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, device));
+    CK(cudaDeviceGetAttribute(&mclk, cudaDevAttrMemoryClockRate, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (sm_clock_khz) *sm_clock_khz = clk;
+    if (mem_clock_khz) *mem_clock_khz = mclk;
+    if (mem_bytes) *mem_bytes = p.totalGlobalMem;
+    if (cc) *cc = p.major * 10 + p.minor;
+    return PVT_OK;
+}
+
+void pvt_default_params(pvt_params* p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->search_radius_x = 80;           // main.cpp:13
+    p->search_radius_y = 80;           // main.cpp:14
+    p->ncc_min_confidence = 0.40;      // main.cpp:17
+    p->ncc_strong_confidence = 0.70;   // main.cpp:18
+    p->template_update_lr = 0.10;      // main.cpp:19
+    p->batch_size = 4;                 // main.cpp:11
+    p->mode = PVT_MODE_NAIVE;          // main.cpp:8
+    p->kernel = PVT_KERNEL_AUTO;
+}
+
+int pvt_alloc_pinned(void** out, size_t bytes)
+{
+    if (!out) return fail(PVT_ERR_INVALID, "out is NULL");
+    CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return PVT_OK;
+}
+int pvt_free_pinned(void* p)
+{
+    CK(cudaFreeHost(p));
+    return PVT_OK;
+}
+
+int pvt_destroy(pvt_ctx* c)
+{
+    if (!c) return PVT_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->compute) cudaStreamSynchronize(c->compute);
+    if (c->copy) cudaStreamSynchronize(c->copy);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_table) cudaFreeHost(c->h_table);
+    if (c->h_results) cudaFreeHost(c->h_results);
+    for (int i = 0; i < kRing; ++i) if (c->table_ev[i]) cudaEventDestroy(c->table_ev[i]);
+    for (int i = 0; i < kStageDepth; ++i) {
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    for (auto& p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (c->timer_a) cudaEventDestroy(c->timer_a);
+    if (c->timer_b) cudaEventDestroy(c->timer_b);
+    if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->copy) cudaStreamDestroy(c->copy);
+    delete c;
+    return PVT_OK;
+}
+
+int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
+{
+    if (!out || !cfg) return fail(PVT_ERR_INVALID, "out/config is NULL");
+    *out = nullptr;
+    int r = validate_params(params);
+    if (r) return r;
+    if (cfg->frame_w <= 0 || cfg->frame_h <= 0 || cfg->max_streams <= 0 || cfg->max_tracks <= 0)
+        return fail(PVT_ERR_INVALID, "frame geometry / stream / track counts must be positive");
+    if (cfg->max_templ_w <= 0 || cfg->max_templ_h <= 0 || cfg->max_templ_w > cfg->frame_w || cfg->max_templ_h > cfg->frame_h)
+        return fail(PVT_ERR_INVALID, "template larger than the frame (ncc_cpu.cpp:9-10)");
+    if (cfg->max_streams > 65535 || cfg->max_tracks > 65535) return fail(PVT_ERR_INVALID, "at most 65535 streams / tracks per context");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PVT_ERR_CUDA, std::string("no usable CUDA device (libpvt has no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PVT_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(PVT_ERR_CUDA, "libpvt is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+
+    pvt_ctx* c = new pvt_ctx();
+    c->params = *params;
+    c->cfg = *cfg;
+    if (c->cfg.max_radius_x <= 0) c->cfg.max_radius_x = params->search_radius_x;
+    if (c->cfg.max_radius_y <= 0) c->cfg.max_radius_y = params->search_radius_y;
+    if (params->search_radius_x > c->cfg.max_radius_x || params->search_radius_y > c->cfg.max_radius_y) {
+        delete c;
+        return fail(PVT_ERR_INVALID, "search radius exceeds config.max_radius");
+    }
+    Ctx& d = c->d;
+    d.W = cfg->frame_w;
+    d.H = cfg->frame_h;
+    d.pitch = (d.W + 3) & ~3;
+    d.plane = ((size_t)d.pitch * d.H + 63) & ~(size_t)63;
+    d.max_streams = cfg->max_streams;
+    d.max_tracks = cfg->max_tracks;
+    d.mtw = cfg->max_templ_w;
+    d.mth = cfg->max_templ_h;
+    d.mtp = (d.mtw + 7) & ~7;
+    // window maxima: main.cpp:143-146 gives at most 2R+1 positions per axis, and never more than the map
+    d.Wmax = std::min(2 * c->cfg.max_radius_x + 1, d.W);
+    d.Hmax = std::min(2 * c->cfg.max_radius_y + 1, d.H);
+    d.VW = (d.Wmax + d.mtw - 1 + 7) & ~7;
+
+#define CR(x)                  \
+    do {                       \
+        int r_ = (x);          \
+        if (r_) {              \
+            pvt_destroy(c);    \
+            return r_;         \
+        }                      \
+    } while (0)
+#define CKD(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            pvt_destroy(c);                                                                           \
+            return fail(PVT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+        }                                                                                             \
+    } while (0)
+
+    CKD(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    const size_t win = (size_t)d.Wmax * d.Hmax;
+    CR(dev_alloc(c, &d.gray, d.plane * d.max_streams));
+    CR(dev_alloc(c, &d.templ, (size_t)d.max_tracks * d.mth * d.mtw));
+    CR(dev_alloc(c, &d.templc, (size_t)d.max_tracks * d.mth * d.mtp));
+    CR(dev_alloc(c, &d.vsum, (size_t)d.max_tracks * d.Hmax * d.VW, false));
+    CR(dev_alloc(c, &d.vsq, (size_t)d.max_tracks * d.Hmax * d.VW, false));
+    CR(dev_alloc(c, &d.denom, (size_t)d.max_tracks * win, false));
+    if (params->keep_maps) CR(dev_alloc(c, &d.maps, (size_t)d.max_tracks * win));
+    CR(dev_alloc(c, &d.tracks, (size_t)d.max_tracks));
+    CR(dev_alloc(c, &d.table, (size_t)kRing * d.max_streams));
+    CR(dev_alloc(c, &d.results, (size_t)kRing * d.max_tracks));
+    CR(dev_alloc(c, &d.params, 1));
+    CR(dev_alloc(c, &d.step, 1));
+    CR(dev_alloc(c, &d.ticket, 1));
+    CR(dev_alloc(c, &d.macs, 1));
+    c->d_macs = d.macs;
+    CKD(cudaHostAlloc((void**)&c->h_table, sizeof(FrameDesc) * kRing * d.max_streams, cudaHostAllocDefault));
+    CKD(cudaHostAlloc((void**)&c->h_results, sizeof(pvt_result) * kRing * d.max_tracks, cudaHostAllocDefault));
+    for (int i = 0; i < kRing; ++i) CKD(cudaEventCreateWithFlags(&c->table_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < kStageDepth; ++i) {
+        CKD(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    CKD(cudaEventCreate(&c->timer_a));
+    CKD(cudaEventCreate(&c->timer_b));
+    c->stage.assign((size_t)d.max_streams * kStageDepth, nullptr);
+    c->stage_bytes = (size_t)d.W * d.H * 4;
+    c->track_stream.assign(d.max_tracks, -1);
+
+    if (!choose_tile(d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
+        pvt_destroy(c);
+        return fail(PVT_ERR_UNSUPPORTED, "template too large for the shared-memory tile of k_ncc_tiled");
+    }
+    CKD(cudaFuncSetAttribute(k_ncc_tiled<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
+    c->rowsum_pw = d.VW + 8;
+    c->rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * c->rowsum_pw * sizeof(double))));
+    CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double))));
+    CR(encode_tmap(c));
+    CR(upload_params(c));
+#undef CR
+#undef CKD
+    *out = c;
+    return PVT_OK;
+}
+
+int pvt_set_params(pvt_ctx* c, const pvt_params* p)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    int r = validate_params(p);
+    if (r) return r;
+    if (p->search_radius_x > c->cfg.max_radius_x || p->search_radius_y > c->cfg.max_radius_y)
+        return fail(PVT_ERR_INVALID, "search radius exceeds the maxima the context was created with");
+    if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->compute));
+    const bool regraph = p->kernel != c->params.kernel;
+    c->params = *p;
+    if (regraph) c->graph_valid = false;
+    return upload_params(c);
+}
+
+int pvt_sync(pvt_ctx* c)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->copy));
+    CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+// ingest one frame into its stream's gray plane right now (used by track_init / to_gray / map API)
+static int ingest_now(pvt_ctx* c, const pvt_frame* f)
+{
+    int r = pvt_sync(c);
+    if (r) return r;
+    r = check_frame(c, f);
+    if (r) return r;
+    const Ctx& d = c->d;
+    // a private table row at the CURRENT device step, then k_ingest alone; the step counter is untouched
+    const int slot = (int)(c->submitted % kRing);
+    std::vector<FrameDesc> row(d.max_streams, FrameDesc{nullptr, 0, 0, 0});
+    FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
+    void* tmp = nullptr;
+    if (f->memory == PVT_MEM_HOST) {
+        const size_t rb = frame_row_bytes(c, f->format);
+        CK(cudaMalloc(&tmp, rb * d.H));
+        cudaError_t e = cudaMemcpy2D(tmp, rb, f->data, f->step, rb, d.H, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(tmp); return fail(PVT_ERR_CUDA, std::string("cudaMemcpy2D: ") + cudaGetErrorString(e)); }
+        fd.data = tmp;
+        fd.step = rb;
+    }
+    row[f->stream] = fd;
+    cudaError_t e = cudaMemcpy(d.table + (size_t)slot * d.max_streams, row.data(), sizeof(FrameDesc) * d.max_streams, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int gpr = (d.W + 3) / 4;
+        const long long groups = (long long)gpr * d.H;
+        k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+        c->launches += 1;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return fail(PVT_ERR_CUDA, std::string("ingest: ") + cudaGetErrorString(e));
+    return PVT_OK;
+}
+
+int pvt_track_init(pvt_ctx* c, int track, int stream, const pvt_frame* frame0, int x, int y, int w, int h)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    if (stream < 0 || stream >= c->cfg.max_streams) return fail(PVT_ERR_INVALID, "stream out of range");
+    if (w <= 0 || h <= 0) return fail(PVT_ERR_INVALID, "empty ROI (main.cpp:66-69)");
+    if (w > c->cfg.max_templ_w || h > c->cfg.max_templ_h) return fail(PVT_ERR_INVALID, "ROI larger than config.max_templ");
+    if (x < 0 || y < 0 || x + w > c->cfg.frame_w || y + h > c->cfg.frame_h) return fail(PVT_ERR_INVALID, "ROI outside the frame");
+    CK(cudaSetDevice(c->cfg.device));
+    if (frame0) {
+        if (frame0->stream != stream) return fail(PVT_ERR_INVALID, "frame0.stream != stream");
+        int r = ingest_now(c, frame0);
+        if (r) return r;
+    } else {
+        int r = pvt_sync(c);
+        if (r) return r;
+    }
+    k_track_init<<<1, 256, 0, c->compute>>>(c->d, track, stream, x, y, w, h);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->compute));
+    c->track_stream[track] = stream;
+    return PVT_OK;
+}
+
+int pvt_track_remove(pvt_ctx* c, int track)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    CK(cudaMemset(&c->d.tracks[track], 0, sizeof(TrackState)));
+    c->track_stream[track] = -1;
+    return PVT_OK;
+}
+
+int pvt_submit(pvt_ctx* c, int n_frames, const pvt_frame* frames)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (n_frames < 0 || (n_frames > 0 && !frames)) return fail(PVT_ERR_INVALID, "frames is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    bool hold = false;
+    if (c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1) {
+        // main.cpp:115-130: frames are collected until the batch is full; only then is one searched
+        if (++c->hold_pending < c->params.batch_size) hold = true;
+        else c->hold_pending = 0;
+    }
+    return enqueue_step(c, n_frames, frames, hold);
+}
+
+int pvt_collect(pvt_ctx* c, pvt_result* results, int max_steps)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    int n = (int)std::min<unsigned long long>(std::min<unsigned long long>(c->submitted, (unsigned long long)std::max(max_steps, 0)), kRing);
+    if (!results || n == 0) return n;
+    const int mt = c->cfg.max_tracks;
+    CK(cudaMemcpy(c->h_results, c->d.results, sizeof(pvt_result) * kRing * mt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long s = c->submitted - n + i;
+        std::memcpy(results + (size_t)i * mt, c->h_results + (size_t)(s % kRing) * mt, sizeof(pvt_result) * mt);
+    }
+    return n;
+}
+
+int pvt_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, pvt_result* results)
+{
+    int r = pvt_submit(c, n_frames, frames);
+    if (r) return r;
+    const int mt = c->cfg.max_tracks;
+    const int slot = (int)((c->submitted - 1) % kRing);
+    if (results) {
+        CK(cudaMemcpyAsync(c->h_results + (size_t)slot * mt, c->d.results + (size_t)slot * mt, sizeof(pvt_result) * mt,
+                           cudaMemcpyDeviceToHost, c->compute));
+        CK(cudaStreamSynchronize(c->compute));
+        std::memcpy(results, c->h_results + (size_t)slot * mt, sizeof(pvt_result) * mt);
+    } else {
+        CK(cudaStreamSynchronize(c->compute));
+    }
+    return PVT_OK;
+}
+
+int pvt_get_state(pvt_ctx* c, int track, int32_t bbox[4], float* templ, size_t templ_step_bytes)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    TrackState t;
+    CK(cudaMemcpy(&t, &c->d.tracks[track], sizeof(t), cudaMemcpyDeviceToHost));
+    if (!t.active) return fail(PVT_ERR_STATE, "track is not initialised");
+    if (bbox) { bbox[0] = t.x; bbox[1] = t.y; bbox[2] = t.w; bbox[3] = t.h; }
+    if (templ) {
+        if (templ_step_bytes < (size_t)t.w * 4) return fail(PVT_ERR_INVALID, "templ_step_bytes too small");
+        CK(cudaMemcpy2D(templ, templ_step_bytes, c->d.templ + (size_t)track * c->d.mth * c->d.mtw, (size_t)t.w * 4, (size_t)t.w * 4, t.h,
+                        cudaMemcpyDeviceToHost));
+    }
+    return PVT_OK;
+}
+
+int pvt_set_state(pvt_ctx* c, int track, const int32_t bbox[4], const float* templ, size_t templ_step_bytes)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    if (!bbox) return fail(PVT_ERR_INVALID, "bbox is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    TrackState t;
+    CK(cudaMemcpy(&t, &c->d.tracks[track], sizeof(t), cudaMemcpyDeviceToHost));
+    if (!t.active && !templ) return fail(PVT_ERR_STATE, "track is not initialised and no template given");
+    const int w = bbox[2], h = bbox[3];
+    if (w <= 0 || h <= 0 || w > c->cfg.max_templ_w || h > c->cfg.max_templ_h) return fail(PVT_ERR_INVALID, "bad template size");
+    if (bbox[0] < 0 || bbox[1] < 0 || bbox[0] + w > c->cfg.frame_w || bbox[1] + h > c->cfg.frame_h) return fail(PVT_ERR_INVALID, "bbox outside the frame");
+    if (!templ && (w != t.w || h != t.h)) return fail(PVT_ERR_INVALID, "template size change needs a template");
+    if (!t.active) { t.stream = std::max(c->track_stream[track], 0); c->track_stream[track] = t.stream; }
+    t.active = 1; t.x = bbox[0]; t.y = bbox[1]; t.w = w; t.h = h; t.peak = 0ull;
+    CK(cudaMemcpy(&c->d.tracks[track], &t, sizeof(t), cudaMemcpyHostToDevice));
+    if (templ) {
+        if (templ_step_bytes < (size_t)w * 4) return fail(PVT_ERR_INVALID, "templ_step_bytes too small");
+        CK(cudaMemcpy2D(c->d.templ + (size_t)track * c->d.mth * c->d.mtw, (size_t)w * 4, templ, templ_step_bytes, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+    }
+    k_track_refresh<<<1, 256, 0, c->compute>>>(c->d, track);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+int pvt_get_window_map(pvt_ctx* c, int track, float* out, size_t out_step_bytes, int32_t win[4])
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    if (!c->d.maps) return fail(PVT_ERR_STATE, "context was created without params.keep_maps");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    TrackState t;
+    CK(cudaMemcpy(&t, &c->d.tracks[track], sizeof(t), cudaMemcpyDeviceToHost));
+    if (!t.active || t.win[2] <= 0) return fail(PVT_ERR_STATE, "track has not been stepped yet");
+    if (win) for (int i = 0; i < 4; ++i) win[i] = t.win[i];
+    if (out) {
+        if (out_step_bytes < (size_t)t.win[2] * 4) return fail(PVT_ERR_INVALID, "out_step_bytes too small");
+        CK(cudaMemcpy2D(out, out_step_bytes, c->d.maps + (size_t)track * c->d.Hmax * c->d.Wmax, (size_t)t.win[2] * 4, (size_t)t.win[2] * 4,
+                        t.win[3], cudaMemcpyDeviceToHost));
+    }
+    return PVT_OK;
+}
+
+int pvt_to_gray_f32(pvt_ctx* c, const pvt_frame* frame, float* out, size_t out_step_bytes, int out_memory)
+{
+    if (!c || !frame || !out) return fail(PVT_ERR_INVALID, "NULL argument");
+    if (out_step_bytes < (size_t)c->cfg.frame_w * 4) return fail(PVT_ERR_INVALID, "out_step_bytes too small");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = ingest_now(c, frame);
+    if (r) return r;
+    CK(cudaMemcpy2D(out, out_step_bytes, c->d.gray + (size_t)frame->stream * c->d.plane, (size_t)c->d.pitch * 4, (size_t)c->d.W * 4, c->d.H,
+                    out_memory == PVT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    return PVT_OK;
+}
+
+// ---- map-level operators (baseline_kernel.hpp:8-17) ---------------------------------------------
+namespace {
+std::mutex g_map_mu;
+std::map<std::tuple<int, int, int, int, int>, pvt_ctx*> g_map_ctx;
+
+int map_ctx(int device, int fw, int fh, int tw, int th, pvt_ctx** out)
+{
+    auto key = std::make_tuple(device, fw, fh, tw, th);
+    auto it = g_map_ctx.find(key);
+    if (it != g_map_ctx.end()) { *out = it->second; return PVT_OK; }
+    pvt_params p;
+    pvt_default_params(&p);
+    p.search_radius_x = fw;  // window == the whole map
+    p.search_radius_y = fh;
+    p.keep_maps = 1;
+    pvt_config cfg{};
+    cfg.device = device; cfg.frame_w = fw; cfg.frame_h = fh; cfg.max_streams = 1; cfg.max_tracks = 1;
+    cfg.max_templ_w = tw; cfg.max_templ_h = th;
+    int r = pvt_create(out, &p, &cfg);
+    if (r) return r;
+    if (g_map_ctx.size() >= 4) {  // small cache: the reference allocates per call (baseline_kernel.cu:340-358)
+        pvt_destroy(g_map_ctx.begin()->second);
+        g_map_ctx.erase(g_map_ctx.begin());
+    }
+    g_map_ctx[key] = *out;
+    return PVT_OK;
+}
+}  // namespace
+
+int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes, const float* templ, int tw,
+                          int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes)
+{
+    if (n <= 0 || !frames || !templ || !outs) return fail(PVT_ERR_INVALID, "empty batch / NULL argument (baseline_kernel.cu:412)");
+    if (tw <= 0 || th <= 0 || fw < tw || fh < th) return fail(PVT_ERR_INVALID, "frame smaller than template (ncc_cpu.cpp:9-10)");
+    const int outW = fw - tw + 1, outH = fh - th + 1;
+    if (fstep_bytes < (size_t)fw * 4 || tstep_bytes < (size_t)tw * 4 || ostep_bytes < (size_t)outW * 4) return fail(PVT_ERR_INVALID, "step too small");
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    pvt_ctx* c = nullptr;
+    int r = map_ctx(device, fw, fh, tw, th, &c);
+    if (r) return r;
+    for (int i = 0; i < n; ++i) {
+        if (!frames[i] || !outs[i]) return fail(PVT_ERR_INVALID, "NULL frame / output in batch");
+        pvt_frame f{0, PVT_FMT_GRAYF32, PVT_MEM_HOST, 0, frames[i], fstep_bytes};
+        const int32_t bbox[4] = {0, 0, tw, th};
+        // every map is taken against the SAME template (baseline_kernel.cu:462-466): reset state per frame
+        if (i == 0) c->track_stream[0] = 0;
+        r = pvt_set_state(c, 0, bbox, templ, tstep_bytes);
+        if (r) return r;
+        r = pvt_step(c, 1, &f, nullptr);
+        if (r) return r;
+        int32_t win[4];
+        r = pvt_get_window_map(c, 0, outs[i], ostep_bytes, win);
+        if (r) return r;
+        if (win[2] != outW || win[3] != outH) return fail(PVT_ERR_STATE, "internal: window is not the full map");
+    }
+    return PVT_OK;
+}
+
+int pvt_ncc_match(int device, int mode, const float* frame, int fw, int fh, size_t fstep_bytes, const float* templ, int tw, int th,
+                  size_t tstep_bytes, float* out, size_t ostep_bytes)
+{
+    if (mode == PVT_MODE_CPU) return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path");
+    if (mode < PVT_MODE_NAIVE || mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
+    return pvt_ncc_match_batched(device, 1, &frame, fw, fh, fstep_bytes, templ, tw, th, tstep_bytes, &out, ostep_bytes);
+}
+
+// ---- measurement hooks ---------------------------------------------------------------------------
+int pvt_profile_enable(pvt_ctx* c, int on)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = resolve_profile(c);
+    if (r) return r;
+    c->profiling = on != 0;
+    return PVT_OK;
+}
+
+int pvt_profile_get(pvt_ctx* c, pvt_profile* out, int reset)
+{
+    if (!c || !out) return fail(PVT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = resolve_profile(c);
+    if (r) return r;
+    unsigned long long macs = 0;
+    CK(cudaMemcpy(&macs, c->d_macs, sizeof(macs), cudaMemcpyDeviceToHost));
+    c->prof.ncc_macs = (double)macs;
+    *out = c->prof;
+    if (reset) {
+        c->prof = pvt_profile{};
+        CK(cudaMemset(c->d_macs, 0, sizeof(unsigned long long)));
+    }
+    return PVT_OK;
+}
+
+int64_t pvt_launch_count(pvt_ctx* c) { return c ? c->launches : 0; }
+
+int pvt_timer_start(pvt_ctx* c)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    CK(cudaEventRecord(c->timer_a, c->compute));
+    return PVT_OK;
+}
+
+int pvt_timer_stop(pvt_ctx* c, double* ms)
+{
+    if (!c || !ms) return fail(PVT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->copy));
+    CK(cudaEventRecord(c->timer_b, c->compute));
+    CK(cudaEventSynchronize(c->timer_b));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->timer_a, c->timer_b));
+    *ms = (double)f;
+    return PVT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Device-side state layout and helpers shared by all kernels of libpvt (sm_100a only).
+//
+// HBM layout per context (allocated once in pvt_create, no per-frame cudaMalloc -- the reference
+// mallocs/frees three buffers per call, tracker/src/baseline_kernel.cu:340-358):
+//   gray     [max_streams][H][pitch]  f32   toGrayF32 image of each stream's current frame (TMA source)
+//   templ    [max_tracks][mth*mtw]    f32   the tracker's template, exactly the reference's templ_gray_f32
+//   templc   [max_tracks][mth*mtp]    f32   fl32(templ - mean_t), rows zero-padded to a multiple of 8
+//   vsum/vsq [max_tracks][Hmax][VW]   f64   vertical box sums of f and f^2 over th rows (scratch)
+//   denom    [max_tracks][Hmax*Wmax]  f64   OpenCV's normaliser t = sqrt(diff2)*sigma_t*sqrt(N), 0 when flat
+//   maps     [max_tracks][Hmax*Wmax]  f32   optional (keep_maps)
+//   tracks   [max_tracks]             TrackState
+//   table    [RING][max_streams]      FrameDesc   what each stream receives at each time step
+//   results  [RING][max_tracks]       pvt_result
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pvt.h"
+
+namespace pvt {
+
+constexpr int kRing = 64;      // time steps that may be in flight
+constexpr int kCX = 8;         // candidates per thread along x (contiguous)
+constexpr int kCY = 4;         // candidates per thread along y (interleaved by the slot count)
+constexpr int kColsumRows = 16;  // candidate rows per thread in the vertical box-sum kernel
+
+struct FrameDesc {
+    const void* data;
+    unsigned long long step;
+    int format;
+    int valid;
+};
+
+struct TrackState {
+    int active, stream;
+    int x, y, w, h;            // bbox; (w, h) is also the template size (main.cpp never changes it)
+    int tp;                    // centred-template row pitch in floats (w rounded up to 8)
+    int flat;                  // sigma_t^2 < DBL_EPSILON -> whole map is 1 (OpenCV common_matchTemplate)
+    double mean, templ_norm;   // mean_t, sigma_t * sqrt(N)
+    unsigned long long peak;   // packed (ordered score << 32 | ~index); 0 = empty
+    int win[4];                // minTx, minTy, width, height of the current search window
+    int pad[2];
+};
+
+struct DevParams {
+    int rx, ry;
+    double min_conf, strong_conf, lr;
+    int keep_maps;
+    int pad;
+};
+
+// geometry + pointers every kernel needs; passed by value (fits in the parameter bank)
+struct Ctx {
+    int W, H, pitch;           // frame geometry, gray-plane pitch in floats
+    size_t plane;              // floats per gray plane
+    int max_streams, max_tracks;
+    int mtw, mth, mtp;         // template maxima: width, height, padded pitch
+    int Wmax, Hmax, VW;        // window maxima (2*rx+1, 2*ry+1) and vsum row pitch
+    float* gray;
+    float* templ;
+    float* templc;
+    double* vsum;
+    double* vsq;
+    double* denom;
+    float* maps;
+    TrackState* tracks;
+    FrameDesc* table;
+    pvt_result* results;
+    DevParams* params;
+    unsigned long long* step;  // device-side time-step counter (advanced by the update kernel)
+    unsigned int* ticket;      // last-block-done counter of the update kernel
+    unsigned long long* macs;  // algorithmic MACs searched so far (n_cand * tw * th per track per step)
+};
+
+// tracker/src/main.cpp:135-146, same int arithmetic (all operands >= 0, so / truncates like C)
+__host__ __device__ inline void search_window(int x, int y, int w, int h, int outW, int outH, int rx, int ry, int* win)
+{
+    int cx = x + w / 2, cy = y + h / 2;
+    int minTx = cx - rx - w / 2; if (minTx < 0) minTx = 0;
+    int maxTx = cx + rx - w / 2; if (maxTx > outW - 1) maxTx = outW - 1;
+    int minTy = cy - ry - h / 2; if (minTy < 0) minTy = 0;
+    int maxTy = cy + ry - h / 2; if (maxTy > outH - 1) maxTy = outH - 1;
+    win[0] = minTx; win[1] = minTy; win[2] = maxTx - minTx + 1; win[3] = maxTy - minTy + 1;
+}
+
+__device__ __forceinline__ bool track_stepped(const Ctx& c, const TrackState& t, unsigned long long step)
+{
+    if (!t.active) return false;
+    return c.table[(step % kRing) * c.max_streams + t.stream].valid != 0;
+}
+
+// monotone float -> uint map (larger float <=> larger uint); -0 is folded into +0 first so that it
+// ties with +0 exactly like a float comparison in cv::minMaxLoc
+__device__ __forceinline__ unsigned int ord_f32(float v)
+{
+    unsigned int u = __float_as_uint(v + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(unsigned int o)
+{
+    unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+// (score desc, row-major index asc): max over keys == first maximum in row-major order
+__device__ __forceinline__ unsigned long long peak_key(float v, unsigned int idx)
+{
+    return ((unsigned long long)ord_f32(v) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// ---- PTX helpers: mbarrier, TMA tensor load, bulk copy -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tile (x, y, plane) of the gray pool -> dense [boxH][boxW] in shared memory; out-of-range
+// elements are zero-filled by the TMA unit
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// contiguous global -> shared, bytes % 16 == 0, both 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+    unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ double shfl_up_f64(double v, int d)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(0xffffffffu, lo, d);
+    hi = __shfl_up_sync(0xffffffffu, hi, d);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+}  // namespace pvt

@@ -1,0 +1,305 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, with the CPU oracle and the
+cv2 4.13.0 golden vectors -- gates G1..G6 of SURVEY.md §8(c).  Nothing here reads /root/reference."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import helpers as Hp
+
+pvt = importlib.import_module("parallel-video-object-tracker_b200")
+pytestmark = pytest.mark.gpu
+
+CLIPS = ["small", "lowtex", "lost", "fade", "border", "flat", "oddsize", "c1_standin", "c2_1080p", "c3_4k"]
+
+
+def records_of(res):
+    """RESULT_DTYPE[n] -> [n, 7] float64 like the golden records (x y w h conf moved updated)."""
+    return np.stack([res["x"], res["y"], res["w"], res["h"], res["conf"].astype(np.float64), res["moved"], res["updated"]], 1).astype(np.float64)
+
+
+def run_clip(frames, roi, **params):
+    recs, templ = pvt.track_clip(frames, roi, **params)
+    return records_of(recs), templ
+
+
+# ---- G6 ingest ---------------------------------------------------------------------------------
+def test_ingest_bit_exact_golden_vectors():
+    g = Hp.golden("ingest.npz")
+    with pvt.Tracker(8192, 1, 1, 1) as tr:
+        out = tr.to_gray_f32(g["bgr"])
+    assert np.array_equal(out, g["lut"][g["gray"]])
+    with pvt.Tracker(256, 1, 1, 1) as tr:
+        assert np.array_equal(tr.to_gray_f32(np.arange(256, dtype=np.uint8).reshape(1, 256))[0], g["lut"])
+
+
+@pytest.mark.parametrize("W,H", [(320, 240), (301, 233), (1920, 1080), (67, 5)])
+def test_ingest_matches_oracle(W, H):
+    rng = np.random.default_rng(W * 7 + H)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    with pvt.Tracker(W, H, 1, 1) as tr:
+        assert np.array_equal(tr.to_gray_f32(bgr), O.to_gray_f32(bgr))
+        # strided rows (cv::Mat::step > cols*3) and the gray / f32 input formats
+        wide = np.zeros((H, W + 5, 3), np.uint8)
+        wide[:, :W] = bgr
+        assert np.array_equal(tr.to_gray_f32(wide[:, :W]), O.to_gray_f32(bgr))
+        g8 = O.bgr2gray(bgr)
+        assert np.array_equal(tr.to_gray_f32(g8), O.gray_to_f32(g8))
+        f32 = O.to_gray_f32(bgr)
+        assert np.array_equal(tr.to_gray_f32(f32), f32)
+
+
+# ---- map-level operators (a3..a8) -----------------------------------------------------------------
+@pytest.mark.parametrize("fn", ["ncc_match_naive_cuda", "ncc_match_shared_cuda", "ncc_match_const", "ncc_match_const_tiled"])
+def test_map_level_operators_vs_cv2_and_oracle(fn):
+    g = Hp.golden("maps.npz")
+    m = getattr(pvt, fn)(g["frame"], g["templ"])
+    assert m.shape == g["full_ipp_off"].shape
+    assert np.abs(m - g["full_ipp_off"]).max() <= Hp.TOL_SCORE
+    assert np.abs(m - g["full_ipp_on"]).max() <= Hp.TOL_SCORE
+    assert np.abs(m - O.ncc_match_cpu(g["frame"], g["templ"])).max() <= 2e-5
+    assert np.argmax(m) == np.argmax(g["full_ipp_on"])
+
+
+def test_map_level_degenerate_cells_identical():
+    g = Hp.golden("maps.npz")
+    f, t = g["frame"], g["templ"]
+    ones = pvt.ncc_match_naive_cuda(f, np.full((13, 17), 0.25, np.float32))
+    assert np.array_equal(ones, g["flat_templ_on"])                       # flat template: all ones
+    z = pvt.ncc_match_naive_cuda(np.full_like(f, 0.5), t)
+    assert np.array_equal(z, g["flat_frame_on"]) and np.all(z == 0)       # flat windows: exactly 0
+    s = pvt.ncc_match_naive_cuda(f, f.copy())                            # template == frame: 1x1 map
+    assert s.shape == (1, 1) and abs(float(s[0, 0]) - 1.0) <= 1e-6
+
+
+def test_map_level_exact_ties_pick_lowest_index():
+    g = Hp.golden("maps.npz")
+    m = pvt.ncc_match_naive_cuda(g["tie_frame"], g["tie_templ"])
+    assert np.abs(m - g["tie_map"]).max() <= Hp.TOL_SCORE
+    # identical windows give bit-identical scores on the GPU too (same operation order for every candidate)
+    ties = np.argwhere(g["tie_map"] == g["tie_map"].max())
+    vals = m[ties[:, 0], ties[:, 1]]
+    assert np.all(vals == vals[0]) and vals[0] == m.max()
+    # ...and the tracker-level peak pick returns the first of them in row-major order
+    with pvt.Tracker(96, 80, 17, 13, search_radius_x=96, search_radius_y=80, ncc_min_confidence=2.0) as tr:
+        tr.init_track(0, g["tie_frame"], (5, 3, 17, 13))
+        tr.set_state(0, (40, 30, 17, 13), g["tie_templ"])
+        r = tr.step([g["tie_frame"]])[0]
+    assert r["moved"] == 0 and (r["x"], r["y"]) == (40, 30)
+    with pvt.Tracker(96, 80, 17, 13, search_radius_x=96, search_radius_y=80) as tr:
+        tr.init_track(0, g["tie_frame"], (5, 3, 17, 13))
+        tr.set_state(0, (40, 30, 17, 13), g["tie_templ"])
+        r = tr.step([g["tie_frame"]])[0]
+    assert (r["x"], r["y"]) == (int(g["tie_best"][1]), int(g["tie_best"][2])) == (5, 3)
+
+
+def test_map_level_batched_and_large_templates():
+    g = Hp.golden("maps.npz")
+    outs = pvt.ncc_match_naive_cuda_batched([g["frame"], g["frame"][::-1].copy(), g["frame"]], g["templ"])
+    assert np.array_equal(outs[0], outs[2])
+    assert np.abs(outs[0] - g["full_ipp_off"]).max() <= Hp.TOL_SCORE
+    assert np.abs(outs[1] - O.ncc_match_cpu(g["frame"][::-1].copy(), g["templ"])).max() <= 2e-5
+    # 72x72 = 5184 px > the reference's 4096-px constant-memory limit (baseline_kernel.cu:499-500)
+    rng = np.random.default_rng(3)
+    f = O.gray_to_f32(rng.integers(0, 256, (150, 170), dtype=np.uint8))
+    t = f[20:92, 31:103].copy()
+    m = pvt.ncc_match_const(f, t)
+    assert np.abs(m - O.ncc_match_cpu(f, t)).max() <= 2e-5 and np.unravel_index(np.argmax(m), m.shape) == (20, 31)
+
+
+# ---- tracker level: G1 / G2 / G5 on every clip -----------------------------------------------------
+@pytest.mark.parametrize("name", CLIPS)
+def test_clip_trajectory_vs_cv2_golden(name):
+    (c, tk) = Hp.clip(name)
+    g = Hp.golden(f"clip_{name}.npz")
+    rec, templ = run_clip(c["frames"], c["roi"], search_radius_x=tk.get("rx", 80), search_radius_y=tk.get("ry", 80))
+    Hp.check_records(rec, g["records"], name)
+    assert np.array_equal(templ, g["templ"]), f"{name}: final template not bit-identical"
+
+
+@pytest.mark.parametrize("name", ["small", "lost", "fade", "oddsize"])
+def test_clip_trajectory_vs_oracle_and_direct_kernel(name):
+    (c, tk) = Hp.clip(name)
+    kw = dict(search_radius_x=tk.get("rx", 80), search_radius_y=tk.get("ry", 80))
+    want, wt = O.track_clip(c["frames"], c["roi"], rx=kw["search_radius_x"], ry=kw["search_radius_y"])
+    rec, templ = run_clip(c["frames"], c["roi"], **kw)
+    d = Hp.check_records(rec, want[:, :7], name)
+    assert d <= 2e-5 and np.array_equal(templ, wt)
+    rec2, templ2 = run_clip(c["frames"], c["roi"], kernel=pvt.KERNEL_DIRECT, **kw)
+    # the verification kernel sums every candidate in the same order: bit-identical results
+    assert np.array_equal(rec, rec2) and np.array_equal(templ, templ2)
+
+
+def test_batch_mode_hold_semantics():
+    (c, tk) = Hp.clip("batch4")
+    g = Hp.golden("clip_batch4.npz")
+    rec, templ = run_clip(c["frames"], c["roi"], mode=pvt.MODE_BATCH, batch_size=4)
+    Hp.check_records(rec, g["records"], "batch4")
+    assert np.array_equal(templ, g["templ"])
+
+
+# ---- G3 / G4 window maps ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,k", [("small", 1), ("small", 7), ("lowtex", 2), ("border", 3), ("flat", 1), ("oddsize", 2), ("c2_1080p", 1)])
+def test_window_map(name, k):
+    (c, tk) = Hp.clip(name)
+    g = Hp.golden(f"clip_{name}.npz")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    templ, bbox = g[f"map{k}_templ"], g[f"map{k}_bbox"]
+    with pvt.Tracker(W, H, roi[2], roi[3], keep_maps=1, search_radius_x=tk.get("rx", 80), search_radius_y=tk.get("ry", 80)) as tr:
+        tr.init_track(0, frames[0], roi)
+        tr.set_state(0, (int(bbox[0]), int(bbox[1]), roi[2], roi[3]), templ)
+        tr.step([frames[k]])
+        m, win = tr.window_map(0)
+        for kern in (pvt.KERNEL_DIRECT,):
+            tr.set_params(kernel=kern)
+            tr.set_state(0, (int(bbox[0]), int(bbox[1]), roi[2], roi[3]), templ)
+            tr.step([frames[k]])
+            m2, _ = tr.window_map(0)
+            assert np.array_equal(m, m2)
+    assert win == tuple(int(v) for v in g[f"map{k}_win"])
+    off, on = g[f"map{k}_ipp_off"], g[f"map{k}_ipp_on"]
+    gray = O.to_gray_f32(frames[k])
+    sig = Hp.window_sigma(gray, roi[2], roi[3], win)
+    d = np.abs(m - off)
+    assert d[sig >= 0.002].max(initial=0) <= Hp.TOL_SCORE            # G3 vs the exact (IPP-off) oracle
+    assert d[sig < 0.002].max(initial=0) <= Hp.TOL_LOWVAR
+    assert np.abs(m - on)[sig >= 0.02].max(initial=0) <= Hp.TOL_SCORE  # G3 vs the default build
+    deg = (off == 0) | (np.abs(off) == 1)
+    assert np.array_equal(m[deg], off[deg])                           # G4
+    assert np.argmax(m) == np.argmax(on)                              # G1
+
+
+# ---- gates are compared in double (main.cpp:153,157) ------------------------------------------------
+def test_thresholds_compare_in_double():
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    conf = run_clip(frames[:2], roi)[0][0, 4]
+    cf = float(np.float32(conf))
+    up = float(np.nextafter(np.float64(cf), 2.0))          # just above the score, rounds to the same float
+    assert np.float32(up) == np.float32(cf)
+    r = run_clip(frames[:2], roi, ncc_strong_confidence=cf)[0][0]
+    assert r[5] == 1 and r[6] == 1                         # conf >= conf
+    r = run_clip(frames[:2], roi, ncc_strong_confidence=up)[0][0]
+    assert r[5] == 1 and r[6] == 0                         # a float compare would still update here
+    r = run_clip(frames[:2], roi, ncc_min_confidence=up, ncc_strong_confidence=up)[0][0]
+    assert r[5] == 0 and r[6] == 0 and (r[0], r[1]) == (roi[0], roi[1])
+
+
+# ---- batching across tracks / streams, async submission ----------------------------------------------
+def test_multi_stream_multi_track_matches_single_runs():
+    names = ["small", "lost", "border"]
+    clips = [Hp.clip(n)[0] for n in names]
+    n = min(len(c["frames"]) for c in clips)
+    H, W = clips[0]["frames"].shape[1:3]
+    singles = [run_clip(c["frames"][:n], c["roi"])[0] for c in clips]
+    with pvt.Tracker(W, H, 32, 32, max_streams=3, max_tracks=5) as tr:
+        # tracks 0..2: one per stream; tracks 3,4: second and third object on stream 0 (multi-ROI, config C4 style)
+        for i, c in enumerate(clips):
+            tr.init_track(i, c["frames"][0], c["roi"], stream=i)
+        x, y, w, h = clips[0]["roi"]
+        tr.init_track(3, None, (x + 9, y - 7, w, h), stream=0)
+        tr.init_track(4, None, (x, y, w, h), stream=0)
+        out = []
+        for k in range(1, n):
+            out.append(tr.step([c["frames"][k] for c in clips]))
+    out = np.array(out)
+    for i in range(3):
+        assert np.array_equal(records_of(out[:, i]), singles[i])
+    assert np.array_equal(records_of(out[:, 4]), singles[0])           # same ROI, same stream -> same trajectory
+    assert np.all(out[:, 3]["valid"] == 1)
+    # a stream that gets no frame in a step is not stepped
+    with pvt.Tracker(W, H, 32, 32, max_streams=2, max_tracks=2) as tr:
+        tr.init_track(0, clips[0]["frames"][0], clips[0]["roi"], stream=0)
+        tr.init_track(1, clips[1]["frames"][0], clips[1]["roi"], stream=1)
+        f = pvt.host_frame(clips[0]["frames"][1], 0)
+        r = tr.step([f])
+    assert r[0]["searched"] == 1 and r[1]["searched"] == 0 and r[1]["valid"] == 1 and np.isnan(r[1]["conf"])
+
+
+def test_async_submit_collect_equals_step():
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi)[0]
+    H, W = frames.shape[1:3]
+    with pvt.Tracker(W, H, 32, 32) as tr:
+        tr.init_track(0, frames[0], roi)
+        keep = [tr.submit([frames[k]]) for k in range(1, len(frames))]
+        got = tr.collect(len(frames) - 1)
+        assert tr.launch_count() >= 5 * (len(frames) - 1)
+    assert np.array_equal(records_of(got[:, 0]), want)
+    assert list(got[:, 0]["step"]) == list(range(len(frames) - 1))
+
+
+def test_device_resident_frames():
+    torch = pytest.importorskip("torch")
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi)[0]
+    H, W = frames.shape[1:3]
+    dev = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
+    with pvt.Tracker(W, H, 32, 32) as tr:
+        tr.init_track(0, pvt.device_frame(dev[0].data_ptr(), W * 3), roi)
+        for k in range(1, len(frames)):
+            tr.submit([pvt.device_frame(dev[k].data_ptr(), W * 3)])
+        got = tr.collect(len(frames) - 1)
+    assert np.array_equal(records_of(got[:, 0]), want)
+
+
+def test_state_roundtrip_and_errors():
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    with pvt.Tracker(W, H, 32, 32, max_tracks=2) as tr:
+        with pytest.raises(pvt.PvtError) as e:
+            tr.get_state(0)
+        assert e.value.code == pvt.ERR_STATE
+        tr.init_track(0, frames[0], roi)
+        bbox, templ = tr.get_state(0)
+        assert bbox == tuple(roi)
+        assert np.array_equal(templ, O.to_gray_f32(frames[0])[roi[1]:roi[1] + roi[3], roi[0]:roi[0] + roi[2]])
+        for bad in [(-1, 0, 32, 32), (0, 0, 33, 32), (W - 31, 0, 32, 32)]:
+            with pytest.raises(pvt.PvtError) as e:
+                tr.init_track(1, None, bad)
+            assert e.value.code == pvt.ERR_INVALID
+        with pytest.raises(pvt.PvtError) as e:
+            tr.step([frames[1][:, : W - 1]])           # wrong geometry is caught as a short row
+        assert e.value.code == pvt.ERR_INVALID
+        with pytest.raises(pvt.PvtError):
+            tr.window_map(0)                            # keep_maps was not requested
+        # checkpoint / resume: state moved to a fresh context continues identically
+        tr.step([frames[1]])
+        bbox, templ = tr.get_state(0)
+        a = tr.step([frames[2]])[0]
+    with pvt.Tracker(W, H, 32, 32) as tr2:
+        tr2.init_track(0, frames[0], roi)
+        tr2.set_state(0, bbox, templ)
+        b = tr2.step([frames[2]])[0]
+    assert records_of(np.array([a])).tolist() == records_of(np.array([b])).tolist()
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ------------------------------------
+@pytest.mark.parametrize("W,H,tw,th,R", [(1920, 1080, 64, 64, 80), (3840, 2160, 128, 128, 160)])
+def test_full_size_properties(W, H, tw, th, R):
+    rng = np.random.default_rng(W)
+    base = rng.integers(0, 256, (H + 64, W + 64), dtype=np.uint8)
+    # smooth a little so the correlation surface has a clear single peak
+    img = ((base[:-1, :-1].astype(np.uint16) + base[1:, :-1] + base[:-1, 1:] + base[1:, 1:]) // 4).astype(np.uint8)
+    f0 = np.ascontiguousarray(img[:H, :W])
+    with pvt.Tracker(W, H, tw, th, keep_maps=1, search_radius_x=R, search_radius_y=R) as tr:
+        for (x, y) in [(W // 2, H // 2), (3, 5), (W - tw - 2, H - th - 1)]:
+            tr.init_track(0, f0, (x, y, tw, th))
+            # self-match: the same frame again -> peak stays put with score 1 (within rounding)
+            r = tr.step([f0])[0]
+            assert (r["x"], r["y"]) == (x, y) and abs(r["conf"] - 1.0) <= 1e-5 and r["updated"] == 1
+            m, win = tr.window_map(0)
+            assert m.shape == (win[3], win[2]) and np.all(np.abs(m) <= 1.0) and not np.isnan(m).any()
+            assert m[y - win[1], x - win[0]] == m.max()
+            # shift property: a translated frame moves the peak by the same vector
+            dx, dy = (17, -11) if 100 < x < W - tw - 100 else ((9, 6) if x < 100 else (-9, -6))
+            f1 = np.zeros_like(f0)
+            f1[max(dy, 0):H + min(dy, 0), max(dx, 0):W + min(dx, 0)] = f0[max(-dy, 0):H - max(dy, 0), max(-dx, 0):W - max(dx, 0)]
+            r = tr.step([f1])[0]
+            assert (r["x"], r["y"]) == (x + dx, y + dy) and r["conf"] > 0.99
