@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- the NCC tracking hot path on B200, BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path on the host cores)
+
+A "step" is one pass of the hot path (ingest -> window statistics -> NCC search -> peak -> gates -> EMA)
+over one time step of the workload.  Default workload = BASELINE.json configs[1]:
+    C2  one 1920x1080 synthetic stream, 64x64 template, SEARCH_RADIUS 80, every frame searched.
+(configs[1] also names --batch=4, the reference's hold mode that searches only every 4th frame
+[main.cpp:115-130]; searching EVERY frame is 4x the work per frame and is what the CPU arm does, so that is the
+headline; the batch=4 figure is reported beside it under "batch4".)
+With N>1 every rank runs its own seeded stream of the same shape (tracks shard by stream, no collective on the
+data path; scaling "weak").  Other workloads: --workload C3 | C4 | C5.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with the frame ring resident in HBM, timed with CUDA events on
+the library's stream (max over ranks).  `e2e` = the same loop through the C ABI with PINNED HOST frames: the H2D
+copy of every frame and the D2H read of every result are inside the timed region.  `roofline` = the NCC search
+kernel (FP32-FMA bound: 2*MACs / t / (SMs*128*2*f_max)), durations from CUDA events around each launch in an
+identical second pass; `ingest` HBM fraction is reported beside it against MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tools import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: W, H, tw, th, R, streams per GPU, ROIs per stream, ring length (frames per stream resident in HBM)
+    "C2": dict(W=1920, H=1080, tw=64, th=64, R=80, streams=1, rois=1, ring=32,
+               desc="single 1920x1080 synthetic stream, 64x64 template, radius 80, every frame searched"),
+    "C3": dict(W=3840, H=2160, tw=128, th=128, R=160, streams=1, rois=1, ring=16,
+               desc="single 3840x2160 synthetic stream, 128x128 template, radius 160"),
+    "C4": dict(W=1920, H=1080, tw=64, th=64, R=80, streams=1, rois=256, ring=32,
+               desc="256 independent ROIs per frame on one 1920x1080 stream, 64x64 templates, radius 80"),
+    "C5": dict(W=1920, H=1080, tw=64, th=64, R=80, streams=64, rois=1, ring=4,
+               desc="64 independent 1920x1080 streams per GPU (512 over 8 GPUs), 64x64 template, radius 80"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_rings(wl, rank, torch):
+    """Per stream: a periodic clip of `ring` frames (frame `ring` == frame 0), resident in HBM and in pinned host memory."""
+    W, H, tw, th, R = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"]
+    L = wl["ring"]
+    n_distinct = min(wl["streams"], 8)  # distinct contents; further streams reuse them in their OWN buffers
+    scenes = [synth.Scene(synth.ClipSpec(seed=100 + 17 * rank + i, W=W, H=H, tw=tw, th=th, n_frames=L, R=R, period=L)) for i in range(n_distinct)]
+    host = torch.empty((wl["streams"], L, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    hn = host.numpy()
+    for i, sc in enumerate(scenes):
+        for k in range(L):
+            hn[i, k] = sc.frame(k)
+    for s in range(n_distinct, wl["streams"]):
+        hn[s] = hn[s % n_distinct]
+    dev = host.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+    return scenes, host, dev
+
+
+def rois_for(wl, scene):
+    """ROI list for one stream: the moving object first, then a grid of static background patches (C4)."""
+    x, y = scene.obj_pos(0)
+    rois = [(x, y, wl["tw"], wl["th"])]
+    g = 0
+    while len(rois) < wl["rois"]:
+        gx, gy = g % 17, g // 17          # 17 x 16 grid: spares for the cells the object starts in
+        g += 1
+        rx = 40 + gx * ((wl["W"] - 80 - wl["tw"]) // 16)
+        ry = 40 + gy * ((wl["H"] - 80 - wl["th"]) // 16)
+        if abs(rx - x) < wl["tw"] and abs(ry - y) < wl["th"]:
+            continue
+        rois.append((rx, ry, wl["tw"], wl["th"]))
+    return rois
+
+
+def ring_descs(pvt, wl, buf, device_mem):
+    """ring[k] = list of pvt_frame (one per stream) for ring position k."""
+    L, S, W = wl["ring"], wl["streams"], wl["W"]
+    ring = []
+    for k in range(L):
+        fr = []
+        for s in range(S):
+            ptr = buf[s, k].data_ptr()
+            fr.append(pvt.Frame(s, pvt.FMT_BGR8, pvt.MEM_DEVICE if device_mem else pvt.MEM_HOST, 0, ptr, W * 3))
+        ring.append(fr)
+    return ring
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev_index = local if world > 1 else 0
+    pvt = importlib.import_module("parallel-video-object-tracker_b200")
+    pvt.lib()  # fails loudly if libpvt.so is missing: there is no fallback path
+
+    wl = dict(WORKLOADS[args.workload])
+    W, H, tw, th, R, L, S = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], wl["ring"], wl["streams"]
+    n_tracks = S * wl["rois"]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    scenes, host, dev = build_rings(wl, rank, torch)
+    info = pvt.device_info(dev_index)
+
+    def make_tracker(**kw):
+        tr = pvt.Tracker(W, H, tw, th, max_streams=S, max_tracks=n_tracks, device=dev_index,
+                         search_radius_x=R, search_radius_y=R, **kw)
+        t = 0
+        for s in range(S):
+            for j, roi in enumerate(rois_for(wl, scenes[s % len(scenes)])):
+                tr.init_track(t, pvt.device_frame(dev[s, 0].data_ptr(), W * 3, stream=s) if j == 0 else None, roi, stream=s)
+                t += 1
+        return tr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def shifted(ring, start):  # step s uses ring position (start + s) % L; frame 0 was the init frame
+        return ring[start % L:] + ring[:start % L]
+
+    # ---- leg 1: frames resident in HBM (value) -----------------------------------------------------
+    ring_dev = ring_descs(pvt, wl, dev, True)
+    tr = make_tracker()
+    tr.submit_sequence(Wm, shifted(ring_dev, 1))
+    tr.sync()
+    sampler = ClockSampler(dev_index)
+    barrier()
+    sampler.start()
+    l0 = tr.launch_count()
+    tr.timer_start()
+    tr.submit_sequence(K, shifted(ring_dev, 1 + Wm))
+    ms = tr.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = tr.launch_count() - l0
+    ms = maxr(ms)
+    # correctness guard: the last steps must sit exactly on the synthetic ground truth
+    last = tr.collect(min(64, K))
+    ok = True
+    for i in range(len(last)):
+        stp = Wm + K - len(last) + i + 1
+        for s in range(S):
+            tx, ty = scenes[s % len(scenes)].obj_pos(stp % L)
+            r = last[i][s * wl["rois"]]
+            ok &= bool(r["x"] == tx and r["y"] == ty and r["searched"] == 1)
+    if not ok:
+        raise SystemExit("bench: tracked boxes left the synthetic ground truth -- refusing to report a number")
+    conf_min = float(last["conf"][:, ::wl["rois"]].min())
+    frames_per_step = S                      # frames consumed per time step on this rank
+    value = world * frames_per_step * K / (ms * 1e-3)
+
+    # ---- leg 2: identical pass with CUDA events around every kernel (roofline) -----------------------
+    Kp = min(K, 200)
+    tr.profile_enable(True)
+    tr.profile_get(reset=True)
+    tr.submit_sequence(Kp, shifted(ring_dev, 1 + Wm + K))
+    prof = tr.profile_get(reset=True)
+    tr.profile_enable(False)
+    fmax_ghz = info["sm_clock_khz"] * 1e-6
+    fp32_peak = info["sm_count"] * 128 * 2 * fmax_ghz * 1e-3  # TFLOP/s at the max SM clock
+    ncc_s = prof["ncc_ms"] * 1e-3 / max(prof["ncc_launches"], 1)
+    macs_per_launch = prof["ncc_macs"] / max(prof["ncc_launches"], 1)
+    ncc_tf = 2.0 * macs_per_launch / ncc_s / 1e12
+    hbm_peak, hbm_src = peaks()
+    ing_s = prof["ingest_ms"] * 1e-3 / max(prof["ingest_launches"], 1)
+    ing_gbs = prof["ingest_bytes"] / max(prof["ingest_launches"], 1) / ing_s / 1e9
+    step_ms_prof = (prof["ingest_ms"] + prof["stats_ms"] + prof["ncc_ms"] + prof["update_ms"]) / max(prof["steps"], 1)
+    tr.close()
+
+    # ---- leg 3: batch=4 hold semantics (reported beside the headline) ---------------------------------
+    batch4 = None
+    if args.workload == "C2":
+        trb = make_tracker(mode=pvt.MODE_BATCH, batch_size=4)
+        trb.submit_sequence(Wm, shifted(ring_dev, 1))
+        trb.sync()
+        barrier()
+        trb.timer_start()
+        trb.submit_sequence(K, shifted(ring_dev, 1 + Wm))
+        msb = maxr(trb.timer_stop())
+        trb.close()
+        batch4 = {"frames_per_s": world * K / (msb * 1e-3), "searched_frames_per_s": world * (K // 4) / (msb * 1e-3), "ms_per_frame": msb / K}
+
+    # ---- leg 4: end to end through the C ABI with pinned HOST frames ------------------------------------
+    ring_host = ring_descs(pvt, wl, host, False)
+    tre = make_tracker()
+    ce = 32 if K >= 32 else K
+    Ke = (K // ce) * ce
+    tre.submit_sequence(min(Wm, 8), shifted(ring_host, 1), collect_every=0)
+    tre.sync()
+    barrier()
+    t0 = time.perf_counter()
+    res = tre.submit_sequence(Ke, shifted(ring_host, 1 + min(Wm, 8)), collect_every=ce, want_results=True)
+    tre.sync()
+    e2e_s = maxr(time.perf_counter() - t0)
+    for i in range(max(0, Ke - 8), Ke):
+        stp = min(Wm, 8) + i + 1
+        tx, ty = scenes[0].obj_pos(stp % L)
+        if not (res[i][0]["x"] == tx and res[i][0]["y"] == ty):
+            raise SystemExit("bench: e2e leg lost the object")
+    tre.close()
+    e2e = {"value": world * frames_per_step * Ke / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(S * W * H * 3),
+           "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke, "how": "pvt_submit_sequence over pinned host BGR frames; results read back every %d steps" % ce}
+
+    out = {
+        "metric": "tracked_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [W, H], "template": [tw, th], "radius": R,
+                   "streams_per_gpu": S, "tracks_per_gpu": n_tracks, "ring_frames_per_stream": L,
+                   "l2_policy": "frame ring %.0f MB per GPU > 126 MB L2; no explicit flush" % (S * L * W * H * 3 / 1e6),
+                   "parallelism": "1 process per GPU, tracks sharded by stream, no data-path collective"},
+        "ncc_gmacs_per_s": world * macs_per_launch * K / (ms * 1e-3) / 1e9,
+        "roofline": {"kernel": "k_ncc_tiled", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": ncc_tf / fp32_peak, "traffic": None,
+                     "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
+                     "us_per_launch": ncc_s * 1e6, "macs_per_launch": macs_per_launch,
+                     "how": "CUDA events around each launch on the library's stream, identical second pass of %d steps" % Kp},
+        "ingest": {"kernel": "k_ingest", "bound": "hbm", "achieved": ing_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ing_gbs / hbm_peak,
+                   "peak_source": hbm_src, "us_per_launch": ing_s * 1e6},
+        "kernel_ms_per_step": {"ingest": prof["ingest_ms"] / max(prof["steps"], 1), "stats": prof["stats_ms"] / max(prof["steps"], 1),
+                               "ncc": prof["ncc_ms"] / max(prof["steps"], 1), "update": prof["update_ms"] / max(prof["steps"], 1),
+                               "sum": step_ms_prof},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "conf_min": conf_min, "batch4": batch4,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(wl, scenes[0], host[0].numpy(), budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl, scene, frames, budget_s=15.0, max_frames=100000):
+    """The reference's --cpu loop (cv2 4.13.0 harness restating main.cpp:93-169; C oracle if cv2 is missing) on the
+    host cores, on a bounded prefix of the same stream.  value = frames / (toGrayF32 + NCC + peak + update)."""
+    from oracle import cv2_harness as H
+
+    L = frames.shape[0]
+    roi = (*scene.obj_pos(0), wl["tw"], wl["th"])
+    per_frame = 0.07 * (wl["W"] * wl["H"]) / (1920 * 1080)
+    n = int(max(4, min(max_frames, budget_s / per_frame)))
+    seq = np.stack([frames[k % L] for k in range(n + 1)])
+    if H.available():
+        import cv2
+        timing = {}
+        r = H.track_clip(seq, roi, rx=wl["R"], ry=wl["R"], timing=timing)
+        kind, cores = "port", int(cv2.getNumThreads())
+        impl = "cv2 %s matchTemplate(TM_CCOEFF_NORMED) full-frame, IPP %s" % (cv2.__version__, cv2.ipp.useIPP())
+        t_tot, t_gray = timing["t_tot"], timing["t_gray"]
+        rec = r["records"]
+    else:
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        rec, _ = O.track_clip(seq, roi, rx=wl["R"], ry=wl["R"])
+        t_tot, t_gray = time.perf_counter() - t0, 0.0
+        kind, cores, impl = "port", O.num_threads(), "oracle/ncc_oracle.c (window-only, double accumulation)"
+    truth = np.array([scene.obj_pos(k % L) for k in range(1, n + 1)])
+    assert np.array_equal(rec[:, :2].astype(int), truth), "cpu baseline lost the object"
+    macs = n * (2 * wl["R"] + 1) ** 2 * wl["tw"] * wl["th"]
+    return {"value": n / (t_tot + t_gray) / wl["rois"], "unit": "frames/s", "cores": cores, "kind": kind, "host_cpus": os.cpu_count(),
+            "sample": "%d frames of the same stream (%s); reference timing convention t_tot (NCC+peak+update) = %.1f ms/frame, "
+                      "toGrayF32 = %.1f ms/frame" % (n, impl, 1e3 * t_tot / n, 1e3 * t_gray / n),
+            "frames_per_s_compute_only": n / t_tot, "window_gmacs_per_s": macs / (t_tot + t_gray) / 1e9}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its --cpu mode), on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    wl = dict(WORKLOADS[args.workload])
+    L = wl["ring"]
+    scene = synth.Scene(synth.ClipSpec(seed=100, W=wl["W"], H=wl["H"], tw=wl["tw"], th=wl["th"], n_frames=L, R=wl["R"], period=L))
+    frames = np.stack([scene.frame(k) for k in range(L)])
+    K, Wm = args.steps, max(args.warmup, 1)
+    per_frame = 0.07 * (wl["W"] * wl["H"]) / (1920 * 1080) * wl["streams"] * wl["rois"]
+    n = int(max(2, min(K, 150.0 / per_frame)))  # bounded sample: the whole run ends within a few minutes
+    cpu_baseline(wl, scene, frames, budget_s=1e9, max_frames=min(Wm, 3))  # warm-up
+    cb = cpu_baseline(wl, scene, frames, budget_s=1e9, max_frames=n)
+    # one stream is timed; a workload with S streams x R rois per step costs S*R such searches per step on the CPU
+    scale = wl["streams"] * wl["rois"]
+    fps = cb["value"]  # frames/s of the whole workload: a frame costs `rois` searches (already divided); streams run one after another
+    out = {"impl": "reference", "metric": "tracked_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
+           "warmup": Wm, "ms_per_step": 1e3 * wl["streams"] / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [wl["W"], wl["H"]], "template": [wl["tw"], wl["th"]],
+                      "radius": wl["R"], "searches_per_step": scale, "world_size_ignored": world},
+           "cpu_baseline": dict(cb, value=fps),
+           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,12 @@ PVT_API int pvt_track_remove(pvt_ctx* ctx, int track);
 PVT_API int pvt_step(pvt_ctx* ctx, int n_frames, const pvt_frame* frames, pvt_result* results);
 PVT_API int pvt_submit(pvt_ctx* ctx, int n_frames, const pvt_frame* frames);
 PVT_API int pvt_collect(pvt_ctx* ctx, pvt_result* results, int max_steps);
+/* The frame loop of main.cpp:93-169 in one call: n_steps time steps, step s uses the n_frames descriptors
+ * frames[(s % ring_len) * n_frames ...] (a ring of resident or pinned-host frames).  Enqueues only; at most
+ * the last 64 steps' results are kept (pvt_collect).  collect_every > 0: every that many steps the results
+ * ring is read back to the host inside the loop (results_out may be NULL to discard after reading). */
+PVT_API int pvt_submit_sequence(pvt_ctx* ctx, int n_steps, int n_frames, const pvt_frame* frames, int ring_len,
+                                int collect_every, pvt_result* results_out);
 PVT_API int pvt_sync(pvt_ctx* ctx);
 
 /* tracker state = {bbox, template} (the reference keeps it in host variables, main.cpp:63-71) */

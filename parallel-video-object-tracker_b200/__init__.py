@@ -33,7 +33,7 @@ MEM_HOST, MEM_DEVICE = range(2)
 SYMBOLS = [
     "pvt_version", "pvt_last_error", "pvt_device_count", "pvt_device_info", "pvt_default_params", "pvt_create",
     "pvt_destroy", "pvt_set_params", "pvt_alloc_pinned", "pvt_free_pinned", "pvt_track_init", "pvt_track_remove",
-    "pvt_step", "pvt_submit", "pvt_collect", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
+    "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop",
 ]
@@ -107,6 +107,7 @@ def lib():
     L.pvt_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(Frame)]
     L.pvt_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.pvt_sync.argtypes = [C.c_void_p]
+    L.pvt_submit_sequence.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Frame), C.c_int, C.c_int, C.c_void_p]
     L.pvt_get_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t]
     L.pvt_set_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t]
     L.pvt_get_window_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
@@ -240,10 +241,14 @@ class Tracker:
     def remove_track(self, track):
         _ck(lib().pvt_track_remove(self._h, track))
 
-    @staticmethod
-    def _frames(frames):
+    def _frames(self, frames):
         if isinstance(frames, np.ndarray):
             frames = [frames]
+        for f in frames:
+            # pvt_frame carries no width/height (the geometry is the context's, like the reference's fixed-size
+            # Mats); numpy inputs are checked here the way the reference CV_Asserts them (baseline_kernel.cu:419-422)
+            if not isinstance(f, Frame) and tuple(f.shape[:2]) != (self.cfg.frame_h, self.cfg.frame_w):
+                raise PvtError(ERR_INVALID, f"frame is {f.shape[1]}x{f.shape[0]}, context expects {self.cfg.frame_w}x{self.cfg.frame_h}")
         fl = [f if isinstance(f, Frame) else host_frame(f, i) for i, f in enumerate(frames)]
         arr = (Frame * len(fl))(*fl)
         arr._keep = fl
@@ -260,6 +265,16 @@ class Tracker:
         arr = self._frames(frames)
         _ck(lib().pvt_submit(self._h, len(arr), arr))
         return arr  # keep host buffers alive until collect()
+
+    def submit_sequence(self, n_steps, ring, collect_every=0, want_results=False):
+        """main.cpp:93-169 as one call: n_steps steps cycling over `ring`, a list of per-step frame lists."""
+        n_frames = len(ring[0])
+        flat = [f for st in ring for f in st]
+        arr = (Frame * len(flat))(*flat)
+        out = np.zeros((n_steps, self.max_tracks), RESULT_DTYPE) if (want_results and collect_every > 0) else None
+        _ck(lib().pvt_submit_sequence(self._h, n_steps, n_frames, arr, len(ring), collect_every,
+                                      out.ctypes.data if out is not None else None))
+        return out
 
     def collect(self, max_steps=64) -> np.ndarray:
         out = np.zeros((max_steps, self.max_tracks), RESULT_DTYPE)

@@ -289,8 +289,12 @@ __global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __
     if (!track_stepped(c, t, step)) return;
     const int ww = t.win[2], wh = t.win[3];
     const int cb = blockIdx.x % g.ncb, band = blockIdx.x / g.ncb;
-    const int cx0 = cb * g.NC * 8, cy0 = band * CY * g.SB;  // first candidate of this CTA inside the window
-    if (cx0 >= ww || cy0 >= wh) return;
+    // The TMA tile must start on a 16-byte boundary in the innermost dimension (an unaligned start
+    // coordinate faults on sm_100a), so the column grid starts at the window origin rounded DOWN to a
+    // multiple of 4 pixels; the xs (0..3) columns in front of the window are masked out below.
+    const int xs = t.win[0] & 3;
+    const int cx0 = cb * g.NC * 8, cy0 = band * CY * g.SB;  // first grid column / candidate row of this CTA
+    if (cx0 >= xs + ww || cy0 >= wh) return;
 
     float* s_tile = reinterpret_cast<float*>(sm_raw);
     float* s_templ = s_tile + (size_t)g.boxW * g.boxH;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __
         fence_mbar_init();
         const uint32_t tbytes = (uint32_t)(th * tp) * 4u;
         mbar_arrive_expect_tx(bar, (uint32_t)(g.boxW * g.boxH) * 4u + tbytes);
-        tma_load_3d(s_tile, &tmap, bar, t.win[0] + cx0, t.win[1] + cy0, t.stream);
+        tma_load_3d(s_tile, &tmap, bar, t.win[0] - xs + cx0, t.win[1] + cy0, t.stream);
         bulk_load(s_templ, c.templc + (size_t)track * c.mth * c.mtp, tbytes, bar);
     }
     __syncthreads();  // barrier initialised before anybody polls it
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __
     const int q = threadIdx.x;
     const int col = q / g.SB, slot = q - col * g.SB;
     unsigned long long key = 0ull;
-    if (col < g.NC && cx0 + col * 8 < ww && cy0 + slot < wh) {
+    if (col < g.NC && cx0 + col * 8 < xs + ww && cy0 + slot < wh) {
         const int P = g.boxW;
         const int rstride = g.SB * P;
         const float* base = s_tile + (size_t)slot * P + col * 8;
@@ -362,8 +366,8 @@ __global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __
             if (y < wh) {
 #pragma unroll
                 for (int cx = 0; cx < 8; ++cx) {
-                    const int x = cx0 + col * 8 + cx;
-                    if (x < ww) {
+                    const int x = cx0 + col * 8 + cx - xs;
+                    if (x >= 0 && x < ww) {
                         const unsigned int idx = (unsigned int)(y * ww + x);
                         const float v = ncc_finalize(acc[cy][cx], dn[idx], flat);
                         if (mp) mp[idx] = v;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -100,7 +101,7 @@ int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
 bool choose_tile(int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
 {
     double best = -1.0;
-    const int cols = (Wmax + 7) / 8;
+    const int cols = (Wmax + 3 + 7) / 8;  // + up to 3 masked columns: the tile origin is aligned down to 4 pixels
     for (int NC = 1; NC <= 24; ++NC)
         for (int SB = 1; SB <= 64; ++SB) {
             const int threads = NC * SB;
@@ -174,6 +175,21 @@ int validate_params(const pvt_params* p)
 
 enum { CLS_INGEST = 0, CLS_STATS = 1, CLS_NCC = 2, CLS_UPDATE = 3 };
 
+// PVT_DEBUG_SYNC=1: launch kernels directly (no graph), synchronise after each and name the one that faulted
+bool debug_sync()
+{
+    static const bool on = [] { const char* e = getenv("PVT_DEBUG_SYNC"); return e && *e && *e != '0'; }();
+    return on;
+}
+int dbg(pvt_ctx* c, const char* what)
+{
+    if (!debug_sync()) return PVT_OK;
+    cudaError_t e = cudaStreamSynchronize(c->compute);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PVT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return PVT_OK;
+}
+
 int prof_begin(pvt_ctx* c, int cls, EventPair** out)
 {
     if (c->ev_next == c->ev_pool.size()) {
@@ -199,12 +215,15 @@ int launch_step_kernels(pvt_ctx* c, bool profile)
     if (profile) { int r = prof_begin(c, CLS_INGEST, &ep); if (r) return r; }
     k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    { int r = dbg(c, "k_ingest"); if (r) return r; }
 
     if (profile) { int r = prof_begin(c, CLS_STATS, &ep); if (r) return r; }
     k_colsum<<<dim3((d.VW + 127) / 128, (d.Hmax + kColsumRows - 1) / kColsumRows, d.max_tracks), 128, 0, c->compute>>>(d);
+    { int r = dbg(c, "k_colsum"); if (r) return r; }
     k_rowsum<<<dim3((d.Hmax + c->rowsum_warps - 1) / c->rowsum_warps, d.max_tracks), c->rowsum_warps * 32,
                (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), c->compute>>>(d, c->rowsum_pw);
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    { int r = dbg(c, "k_rowsum"); if (r) return r; }
 
     if (profile) { int r = prof_begin(c, CLS_NCC, &ep); if (r) return r; }
     if (c->params.kernel == PVT_KERNEL_DIRECT) {
@@ -214,10 +233,12 @@ int launch_step_kernels(pvt_ctx* c, bool profile)
         k_ncc_tiled<kCY><<<dim3(c->tile.ncb * c->tile.nbands, d.max_tracks), threads, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
     }
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    { int r = dbg(c, "k_ncc"); if (r) return r; }
 
     if (profile) { int r = prof_begin(c, CLS_UPDATE, &ep); if (r) return r; }
     k_update<<<d.max_tracks, 256, 0, c->compute>>>(d);
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    { int r = dbg(c, "k_update"); if (r) return r; }
     CK(cudaGetLastError());
     return PVT_OK;
 }
@@ -304,11 +325,11 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph_hold, c->compute));
         c->launches += 1;
-    } else if (c->profiling) {
-        int r = launch_step_kernels(c, true);
+    } else if (c->profiling || debug_sync()) {
+        int r = launch_step_kernels(c, c->profiling);
         if (r) return r;
         c->launches += 5;
-        c->prof.steps += 1;
+        if (c->profiling) c->prof.steps += 1;
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
@@ -525,6 +546,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
                              (int)((size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double))));
     CR(encode_tmap(c));
     CR(upload_params(c));
+    CKD(cudaDeviceSynchronize());  // the zero-fills above ran on the default stream; kernels use non-blocking streams
 #undef CR
 #undef CKD
     *out = c;
@@ -572,13 +594,16 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
     if (f->memory == PVT_MEM_HOST) {
         const size_t rb = frame_row_bytes(c, f->format);
         CK(cudaMalloc(&tmp, rb * d.H));
-        cudaError_t e = cudaMemcpy2D(tmp, rb, f->data, f->step, rb, d.H, cudaMemcpyHostToDevice);
+        // stream-ordered on the compute stream: a synchronous cudaMemcpy from pageable memory may return
+        // while its DMA is still in flight, and the non-blocking compute stream would not wait for it
+        cudaError_t e = cudaMemcpy2DAsync(tmp, rb, f->data, f->step, rb, d.H, cudaMemcpyHostToDevice, c->compute);
         if (e != cudaSuccess) { cudaFree(tmp); return fail(PVT_ERR_CUDA, std::string("cudaMemcpy2D: ") + cudaGetErrorString(e)); }
         fd.data = tmp;
         fd.step = rb;
     }
     row[f->stream] = fd;
-    cudaError_t e = cudaMemcpy(d.table + (size_t)slot * d.max_streams, row.data(), sizeof(FrameDesc) * d.max_streams, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyAsync(d.table + (size_t)slot * d.max_streams, row.data(), sizeof(FrameDesc) * d.max_streams,
+                                    cudaMemcpyHostToDevice, c->compute);
     if (e == cudaSuccess) {
         const int gpr = (d.W + 3) / 4;
         const long long groups = (long long)gpr * d.H;
@@ -624,7 +649,8 @@ int pvt_track_remove(pvt_ctx* c, int track)
     CK(cudaSetDevice(c->cfg.device));
     int r = pvt_sync(c);
     if (r) return r;
-    CK(cudaMemset(&c->d.tracks[track], 0, sizeof(TrackState)));
+    CK(cudaMemsetAsync(&c->d.tracks[track], 0, sizeof(TrackState), c->compute));
+    CK(cudaStreamSynchronize(c->compute));
     c->track_stream[track] = -1;
     return PVT_OK;
 }
@@ -658,6 +684,34 @@ int pvt_collect(pvt_ctx* c, pvt_result* results, int max_steps)
         std::memcpy(results + (size_t)i * mt, c->h_results + (size_t)(s % kRing) * mt, sizeof(pvt_result) * mt);
     }
     return n;
+}
+
+int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* frames, int ring_len, int collect_every,
+                        pvt_result* results_out)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (n_steps < 0 || n_frames <= 0 || ring_len <= 0 || !frames) return fail(PVT_ERR_INVALID, "bad sequence arguments");
+    if (collect_every > kRing) return fail(PVT_ERR_INVALID, "collect_every exceeds the 64-step results ring");
+    const int mt = c->cfg.max_tracks;
+    for (int s = 0; s < n_steps; ++s) {
+        int r = pvt_submit(c, n_frames, frames + (size_t)(s % ring_len) * n_frames);
+        if (r) return r;
+        if (collect_every > 0 && (s + 1) % collect_every == 0) {
+            // device -> host read of these steps' results (async copy, then wait for it: the e2e contract)
+            const unsigned long long first = c->submitted - collect_every;
+            for (int k = 0; k < collect_every; ++k) {
+                const int slot = (int)((first + k) % kRing);
+                CK(cudaMemcpyAsync(c->h_results + (size_t)slot * mt, c->d.results + (size_t)slot * mt, sizeof(pvt_result) * mt,
+                                   cudaMemcpyDeviceToHost, c->compute));
+            }
+            CK(cudaStreamSynchronize(c->compute));
+            if (results_out)
+                for (int k = 0; k < collect_every; ++k)
+                    std::memcpy(results_out + (size_t)(s + 1 - collect_every + k) * mt, c->h_results + (size_t)((first + k) % kRing) * mt,
+                                sizeof(pvt_result) * mt);
+        }
+    }
+    return PVT_OK;
 }
 
 int pvt_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, pvt_result* results)
@@ -713,10 +767,11 @@ int pvt_set_state(pvt_ctx* c, int track, const int32_t bbox[4], const float* tem
     if (!templ && (w != t.w || h != t.h)) return fail(PVT_ERR_INVALID, "template size change needs a template");
     if (!t.active) { t.stream = std::max(c->track_stream[track], 0); c->track_stream[track] = t.stream; }
     t.active = 1; t.x = bbox[0]; t.y = bbox[1]; t.w = w; t.h = h; t.peak = 0ull;
-    CK(cudaMemcpy(&c->d.tracks[track], &t, sizeof(t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(&c->d.tracks[track], &t, sizeof(t), cudaMemcpyHostToDevice, c->compute));
     if (templ) {
         if (templ_step_bytes < (size_t)w * 4) return fail(PVT_ERR_INVALID, "templ_step_bytes too small");
-        CK(cudaMemcpy2D(c->d.templ + (size_t)track * c->d.mth * c->d.mtw, (size_t)w * 4, templ, templ_step_bytes, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy2DAsync(c->d.templ + (size_t)track * c->d.mth * c->d.mtw, (size_t)w * 4, templ, templ_step_bytes, (size_t)w * 4, h,
+                             cudaMemcpyHostToDevice, c->compute));
     }
     k_track_refresh<<<1, 256, 0, c->compute>>>(c->d, track);
     c->launches += 1;
@@ -846,7 +901,8 @@ int pvt_profile_get(pvt_ctx* c, pvt_profile* out, int reset)
     *out = c->prof;
     if (reset) {
         c->prof = pvt_profile{};
-        CK(cudaMemset(c->d_macs, 0, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->d_macs, 0, sizeof(unsigned long long), c->compute));
+        CK(cudaStreamSynchronize(c->compute));
     }
     return PVT_OK;
 }

@@ -22,7 +22,7 @@ template <int MODE, int CY>
 __global__ void __launch_bounds__(256, 1) k_fma(float* out, int iters, int pitch)
 {
     extern __shared__ __align__(16) float sm[];
-    for (int i = threadIdx.x; i < 40 * pitch; i += blockDim.x) sm[i] = 1.0f + 1e-6f * (float)i;
+    for (int i = threadIdx.x; i < 64 * pitch; i += blockDim.x) sm[i] = 1.0f + 1e-6f * (float)i;
     __syncthreads();
     const float* base = sm + (threadIdx.x & 31) * pitch + (threadIdx.x >> 5) * 8;
     float sum = 0.f;
@@ -118,11 +118,63 @@ __global__ void __launch_bounds__(256, 1) k_fma(float* out, int iters, int pitch
     out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
+
+// PAT 0: acc[i] += a*b (a, b loop invariant)   PAT 1: acc[i] += w[i]*b (fixed pairing, b invariant)
+// PAT 2: acc[i] += w[i]*t[i] (fixed pairing, three fresh operands)
+template <int PAT>
+__global__ void __launch_bounds__(256, 1) k_pat(float* out, int iters, float a0, float b0, long long* clk)
+{
+    float acc[32], w[32], t[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { acc[i] = 0.f; w[i] = a0 + i * 1e-3f + threadIdx.x * 1e-5f; t[i] = b0 + i * 1e-4f; }
+    long long c0 = clock64();
+    unsigned long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                acc[i] = PAT == 0 ? fmaf(a0, b0, acc[i]) : PAT == 1 ? fmaf(w[i], b0, acc[i]) : fmaf(w[i], t[i], acc[i]);
+    }
+    long long c1 = clock64();
+    unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = c1 - c0; clk[1] = (long long)(g1 - g0); }
+}
+
+template <int PAT>
+void run_pat(const char* name, int sms, double clk_ghz, int threads)
+{
+    const int iters = 8192;
+    float* out; CK(cudaMalloc(&out, (size_t)sms * threads * 4));
+    long long* clk; CK(cudaMalloc(&clk, 16));
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    for (int w = 0; w < 2; ++w) k_pat<PAT><<<sms, threads>>>(out, iters, 1.0f, 1e-3f, clk);
+    CK(cudaDeviceSynchronize());
+    float best = 1e9f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(a));
+        k_pat<PAT><<<sms, threads>>>(out, iters, 1.0f, 1e-3f, clk);
+        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+    }
+    long long h[2]; CK(cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost));
+    const double fma = (double)sms * threads * iters * 256.0;
+    const double tf = 2.0 * fma / (best * 1e-3) / 1e12;
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("%-34s thr=%4d  %8.3f ms  %7.2f TFLOP/s  %5.1f%% of nominal | in-kernel %.0f MHz, %.3f cyc per FFMA per SMSP\n", name, threads, best, tf,
+           100.0 * tf / (sms * 128 * 2 * clk_ghz * 1e-3), 1e3 * (double)h[0] / (double)h[1], (double)h[0] / (iters * 256.0 * warps_per_smsp));
+    CK(cudaFree(out)); CK(cudaFree(clk));
+}
+
 template <int MODE, int CY>
 void run(const char* name, int sms, double clk_ghz, int threads, int ctas_per_sm)
 {
     const int pitch = 100, iters = 4096;
-    const size_t smem = 40 * pitch * 4;
+    const size_t smem = 64 * pitch * 4;
     float* out; CK(cudaMalloc(&out, (size_t)sms * ctas_per_sm * threads * 4));
     CK(cudaFuncSetAttribute(k_fma<MODE, CY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -149,6 +201,11 @@ int main()
     const double ghz = clk * 1e-6;
     printf("device %s, %d SMs, max clock %.3f GHz\n", p.name, p.multiProcessorCount, ghz);
     const int sms = p.multiProcessorCount;
+    run_pat<0>("FFMA acc+=a*b (invariant a,b)", sms, ghz, 256);
+    run_pat<0>("FFMA acc+=a*b (invariant a,b)", sms, ghz, 512);
+    run_pat<1>("FFMA acc+=w[i]*b (fixed pairing)", sms, ghz, 256);
+    run_pat<1>("FFMA acc+=w[i]*b (fixed pairing)", sms, ghz, 512);
+    run_pat<2>("FFMA acc+=w[i]*t[i] (3 fresh)", sms, ghz, 256);
     run<0, 4>("FFMA  regs only", sms, ghz, 256, 1);
     run<0, 4>("FFMA  regs only", sms, ghz, 128, 1);
     run<0, 4>("FFMA  regs only", sms, ghz, 128, 3);
