@@ -1,5 +1,5 @@
 // Hand-written sm_100a kernels of the NCC tracking hot path.  One time step = the launch sequence
-//   k_ingest -> k_colsum -> k_rowsum -> k_ncc_tiled (or k_ncc_direct) -> k_update
+//   k_ingest -> k_colsum -> k_rowsum -> k_ncc_search [-> k_ncc_finalize] (or k_ncc_direct) -> k_update
 // captured once as a CUDA graph; every kernel finds "which frame / which step" through the
 // device-side step counter and frame table, so the graph is launched unchanged for every frame and
 // nothing returns to the host between frames.
@@ -193,10 +193,17 @@ __device__ __forceinline__ float ncc_finalize(float num_f32, double t, int flat_
 }
 
 // =============================================================================================
-// (3a) k_ncc_direct: verification twin of the reference's naive kernel (baseline_kernel.cu:21-64):
-//      one thread per candidate, operands from global/L2 -- but with this library's numerics
-//      (centred template, per-template-row FP32 partials, FP64 normaliser).  PVT_KERNEL_DIRECT.
+// Cross-term accumulation order (shared by both NCC kernels, so their results are bit-identical):
+//   for every 8-column chunk j of the (zero-padded) centred template:
+//       r = 0;  for dy = 0..th-1: for k = 0..7:  r = fma(f[y+dy][x+j+k], tc[dy][j+k], r)      (512 products at 64 rows)
+//       acc += r
+//   i.e. one FP32 partial per template chunk, chunks then added in FP32 (blocked summation in the sense
+//   of SURVEY.md §7 scheme (B); products use the centred template fl32(t - mean_t)).
+//   The centred template is stored CHUNK-MAJOR: templc[chunk][dy][8], so a chunk is one contiguous slice.
 // =============================================================================================
+
+// (3a) k_ncc_direct: verification twin of the reference's naive kernel (baseline_kernel.cu:21-64):
+//      one thread per candidate, operands from global/L2.  PVT_KERNEL_DIRECT.
 __global__ void __launch_bounds__(256) k_ncc_direct(Ctx c)
 {
     const int track = blockIdx.y;
@@ -210,10 +217,14 @@ __global__ void __launch_bounds__(256) k_ncc_direct(Ctx c)
         const int y = idx / ww, x = idx - y * ww;
         const float* f = c.gray + (size_t)t.stream * c.plane + (size_t)(t.win[1] + y) * c.pitch + t.win[0] + x;
         const float* tc = c.templc + (size_t)track * c.mth * c.mtp;
+        const int th = t.h, tw = t.w;
         float acc = 0.f;
-        for (int dy = 0; dy < t.h; ++dy) {
+        for (int j = 0; j < tw; j += 8) {
+            const float* tj = tc + (size_t)(j >> 3) * th * 8;
+            const int kn = min(8, tw - j);
             float r = 0.f;
-            for (int dx = 0; dx < t.w; ++dx) r = fmaf(f[(size_t)dy * c.pitch + dx], tc[dy * t.tp + dx], r);
+            for (int dy = 0; dy < th; ++dy)
+                for (int k = 0; k < kn; ++k) r = fmaf(f[(size_t)dy * c.pitch + j + k], tj[dy * 8 + k], r);
             acc += r;
         }
         const double dn = c.denom[(size_t)track * c.Hmax * c.Wmax + idx];
@@ -230,57 +241,37 @@ __global__ void __launch_bounds__(256) k_ncc_direct(Ctx c)
 }
 
 // =============================================================================================
-// (3b) k_ncc_tiled: the production cross-term kernel.
-//   CTA = (track, block of NC thread-columns, band of CY*SB candidate rows).
-//   Staging: ONE cp.async.bulk.tensor.3d (TMA) brings the CTA's search sub-tile
-//   [CY*SB + th - 1 rows] x [8*NC + tp + 4 cols] of the stream's gray plane into shared memory, and one
-//   cp.async.bulk brings the track's centred template; both complete on one mbarrier.  Tile origin
-//   (the clamped search window) is read from device state, so no host involvement per frame.
-//   Compute: thread (col, slot) owns 8 consecutive candidates in x times CY candidates in y
-//   (rows slot + SB*cy): 32 FP32 accumulators.  For each template row it sweeps dx in steps of 8 with a
-//   16-float sliding window per candidate row held in registers: per 8 dx it issues CY*2 + 2 LDS.128
-//   for 64*CY FFMA (96 % FMA instructions).  Consecutive lanes are consecutive tile rows and the tile
-//   pitch is == 4 (mod 8) floats, so every quarter-warp LDS.128 hits 8 distinct 16-byte bank groups
-//   (conflict-free); template reads are warp-uniform broadcasts.
-//   Numerics: products with the centred template fl32(t - mean_t); one FP32 partial per template row,
-//   rows then added in FP32 (SURVEY.md §7 scheme (B)); normalisation in FP64 exactly as OpenCV.
-//   Epilogue: finalize, (score desc, index asc) key, warp-shuffle max, one atomicMax per warp.
+// (3b) k_ncc_search: the production cross-term kernel ("y-sliding" register blocking).
+//   Thread tile = 8 consecutive candidates in x  x  CY = 5 ADJACENT candidate rows (40 FP32 accumulators).
+//   Loop order: template chunk j (8 columns) outermost, template row dy innermost.  At step dy the thread holds the
+//   CY frame-row windows (16 floats each) its candidate rows need; going to dy+1 drops the oldest window and loads
+//   ONE new one (4 LDS.128) plus the 8 template values of that row (2 LDS.128, warp-uniform broadcast): 6 shared
+//   loads feed 64*CY = 320 FFMA (1.9 % of the instruction stream; the x-sliding predecessor needed 3.9 % and ran at
+//   75 % of the FP32 peak where this loop sustains 87 % -- tools/microbench2.cu, profiles/).  The window registers
+//   rotate through static names by unrolling dy CY times.
+//   Thread tiles of a track are numbered column-major, q = col * G + g (G = row groups per column); a CTA takes
+//   128 consecutive tiles.  Consecutive lanes are consecutive row groups, i.e. frame rows CY apart, and the tile
+//   pitch is == 4 (mod 8) floats, so with CY odd every quarter-warp LDS.128 hits 8 distinct 16-byte bank groups.
+//   Staging: ONE cp.async.bulk.tensor.3d (TMA) brings the CTA's sub-tile (<= span columns x all rows) of the
+//   stream's gray plane; the centred template streams through a 4-deep ring of 8-column slices (cp.async.bulk with
+//   full/empty mbarriers, no CTA-wide sync in the loop), so a CTA needs ~107 KB and two CTAs share an SM.  Window origin comes from device state.
+//   K-split (single-stream latency mode): grid.z parts, part p handles template rows [d0, d1) of chunk range
+//   [j0, j1); partial sums go to a scratch plane per part and k_ncc_finalize adds them in a fixed order.
+//   Epilogue (no K-split): OpenCV normalisation in FP64, (score desc, index asc) key, warp-shuffle max, atomicMax.
 // =============================================================================================
-template <int CY>
-__device__ __forceinline__ void fma_sweep8(float (&racc)[CY][8], const float (&lo)[CY][8], const float (&hi)[CY][8], const float (&t)[8])
-{
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int cy = 0; cy < CY; ++cy)
-#pragma unroll
-            for (int cx = 0; cx < 8; ++cx) {
-                const int i = k + cx;
-                const float v = i < 8 ? lo[cy][i] : hi[cy][i - 8];
-                racc[cy][cx] = fmaf(v, t[k], racc[cy][cx]);
-            }
-}
-
-template <int CY>
-__device__ __forceinline__ void load8(float (&w)[CY][8], const float* p, int rstride)
-{
-#pragma unroll
-    for (int cy = 0; cy < CY; ++cy) {
-        const float4 a = *reinterpret_cast<const float4*>(p + cy * rstride);
-        const float4 b = *reinterpret_cast<const float4*>(p + cy * rstride + 4);
-        w[cy][0] = a.x; w[cy][1] = a.y; w[cy][2] = a.z; w[cy][3] = a.w;
-        w[cy][4] = b.x; w[cy][5] = b.y; w[cy][6] = b.z; w[cy][7] = b.w;
-    }
-}
+constexpr int kTilesPerCta = 128;
 
 struct TileCfg {
-    int NC, SB;        // thread-columns and row-slots per CTA
-    int boxW, boxH;    // TMA box (floats, rows) == shared tile pitch / height
-    int ncb, nbands;   // CTAs per track along x and y
+    int G, C;            // row groups per column (ceil(Hmax / CY)), columns (ceil((Wmax + 3) / 8))
+    int GB, bands;       // row groups per band (a CTA's tiles live in one band), bands = ceil(G / GB)
+    int ctas_band;       // CTAs per band (ceil(GB * C / 128))
+    int span;            // columns one CTA's 128 tiles can touch
+    int boxW, boxH;      // TMA box == shared tile [boxH][boxW]
+    int pj, pd;          // K-split: parts along template chunks and along template rows (pj * pd = grid.z)
 };
 
 template <int CY>
-__global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char sm_raw[];
     const int track = blockIdx.y;
@@ -288,95 +279,203 @@ __global__ void __launch_bounds__(256, 1) k_ncc_tiled(Ctx c, TileCfg g, const __
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
     const int ww = t.win[2], wh = t.win[3];
-    const int cb = blockIdx.x % g.ncb, band = blockIdx.x / g.ncb;
-    // The TMA tile must start on a 16-byte boundary in the innermost dimension (an unaligned start
-    // coordinate faults on sm_100a), so the column grid starts at the window origin rounded DOWN to a
-    // multiple of 4 pixels; the xs (0..3) columns in front of the window are masked out below.
+    const int th = t.h, nchunk = t.tp >> 3;
+    // the TMA tile must start on a 16-byte boundary in x: the column grid starts at the window origin rounded
+    // DOWN to a multiple of 4 pixels; the xs (0..3) grid columns in front of the window are masked
     const int xs = t.win[0] & 3;
-    const int cx0 = cb * g.NC * 8, cy0 = band * CY * g.SB;  // first grid column / candidate row of this CTA
-    if (cx0 >= xs + ww || cy0 >= wh) return;
+    const int band = blockIdx.x / g.ctas_band, q0 = (blockIdx.x - band * g.ctas_band) * kTilesPerCta;
+    const int c_lo = q0 / g.GB;
+    const int row0 = band * g.GB * CY;  // first candidate row of this band
+    if (c_lo * 8 >= xs + ww || row0 >= wh) return;
 
+    // K-split part -> template chunk range [j0, j1) and row range [d0, d1)
+    const int part = blockIdx.z, pjx = part % g.pj, pdx = part / g.pj;
+    const int j0 = (nchunk * pjx) / g.pj;
+    const int d0 = (th * pdx) / g.pd, d1 = (th * (pdx + 1)) / g.pd;
+    const int nd = d1 - d0;
+    const int j1 = nd > 0 ? (nchunk * (pjx + 1)) / g.pj : j0;
+
+    constexpr int kRingT = 4;  // template slices in flight (full/empty mbarrier ring; no CTA-wide sync in the loop)
     float* s_tile = reinterpret_cast<float*>(sm_raw);
-    float* s_templ = s_tile + (size_t)g.boxW * g.boxH;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_templ + (size_t)c.mth * c.mtp);
-    const int tp = t.tp, th = t.h;
+    float* s_templ = s_tile + (size_t)g.boxW * g.boxH;             // kRingT slices of [mth][8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_templ + kRingT * (size_t)c.mth * 8);  // [0] tile, [1..4] full, [5..8] empty
+    uint64_t* full = bars + 1;
+    uint64_t* empty = bars + 1 + kRingT;
+    const float* gtempl = c.templc + (size_t)track * c.mth * c.mtp;
+    const uint32_t slice_bytes = (uint32_t)nd * 32u;
+    const int nj = j1 - j0;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        mbar_init(&bars[0], 1);
+#pragma unroll
+        for (int s = 0; s < kRingT; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], blockDim.x >> 5);
+        }
         fence_mbar_init();
-        const uint32_t tbytes = (uint32_t)(th * tp) * 4u;
-        mbar_arrive_expect_tx(bar, (uint32_t)(g.boxW * g.boxH) * 4u + tbytes);
-        tma_load_3d(s_tile, &tmap, bar, t.win[0] - xs + cx0, t.win[1] + cy0, t.stream);
-        bulk_load(s_templ, c.templc + (size_t)track * c.mth * c.mtp, tbytes, bar);
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
+        tma_load_3d(s_tile, &tmap, &bars[0], t.win[0] - xs + (c_lo + j0) * 8, t.win[1] + row0 + d0, t.stream);
+        for (int s = 0; s < 2 && s < nj; ++s) {
+            mbar_arrive_expect_tx(&full[s], slice_bytes);
+            bulk_load(s_templ + (size_t)s * c.mth * 8, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
+        }
     }
-    __syncthreads();  // barrier initialised before anybody polls it
-    mbar_wait(bar, 0);
+    __syncthreads();  // barriers initialised before anybody polls them
+    mbar_wait(&bars[0], 0);
 
-    const int q = threadIdx.x;
-    const int col = q / g.SB, slot = q - col * g.SB;
-    unsigned long long key = 0ull;
-    if (col < g.NC && cx0 + col * 8 < xs + ww && cy0 + slot < wh) {
-        const int P = g.boxW;
-        const int rstride = g.SB * P;
-        const float* base = s_tile + (size_t)slot * P + col * 8;
-        float acc[CY][8];
-#pragma unroll
-        for (int cy = 0; cy < CY; ++cy)
-#pragma unroll
-            for (int cx = 0; cx < 8; ++cx) acc[cy][cx] = 0.f;
+    const int q = q0 + threadIdx.x;
+    const int col = q / g.GB, gl = q - col * g.GB;
+    const int grp = band * g.GB + gl;
+    const bool active = col < g.C && col * 8 < xs + ww && grp * CY < wh;
+    const int P = g.boxW;
+    const float* base = s_tile + (size_t)(gl * CY) * P + (col - c_lo) * 8;
 
-        for (int dy = 0; dy < th; ++dy) {
-            const float* frow = base + (size_t)dy * P;
-            const float* trow = s_templ + dy * tp;
-            float racc[CY][8];
+    float acc[CY][8];
 #pragma unroll
-            for (int cy = 0; cy < CY; ++cy)
+    for (int i = 0; i < CY; ++i)
 #pragma unroll
-                for (int cx = 0; cx < 8; ++cx) racc[cy][cx] = 0.f;
-            float wa[CY][8], wb[CY][8], tt[8];
-            load8<CY>(wa, frow, rstride);
-            for (int j = 0; j < tp; j += 16) {
-                load8<CY>(wb, frow + j + 8, rstride);
-                {
-                    const float4 a = *reinterpret_cast<const float4*>(trow + j);
-                    const float4 b = *reinterpret_cast<const float4*>(trow + j + 4);
-                    tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = b.x; tt[5] = b.y; tt[6] = b.z; tt[7] = b.w;
+        for (int cx = 0; cx < 8; ++cx) acc[i][cx] = 0.f;
+
+    for (int it = 0; it < nj; ++it) {
+        const int j = j0 + it, slot = it & (kRingT - 1);
+        if (threadIdx.x == 0 && it + 2 < nj) {
+            // producer: slice it+2 goes to the slot slice it-2 used; wait until every warp released that slot
+            const int c2 = it + 2, s2 = c2 & (kRingT - 1);
+            if (c2 >= kRingT) mbar_wait(&empty[s2], (uint32_t)((c2 / kRingT) - 1) & 1u);
+            mbar_arrive_expect_tx(&full[s2], slice_bytes);
+            bulk_load(s_templ + (size_t)s2 * c.mth * 8, gtempl + ((size_t)(j0 + c2) * th + d0) * 8, slice_bytes, &full[s2]);
+        }
+        mbar_wait(&full[slot], (uint32_t)(it / kRingT) & 1u);
+        if (active) {
+            const float* st = s_templ + (size_t)slot * c.mth * 8;
+            const float* fb = base + (j - j0) * 8;
+            float racc[CY][8], w[CY][16];
+#pragma unroll
+            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = 0.f;
+#pragma unroll
+            for (int r = 0; r < CY - 1; ++r) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 a = *reinterpret_cast<const float4*>(fb + r * P + 4 * v);
+                    w[r][4 * v] = a.x; w[r][4 * v + 1] = a.y; w[r][4 * v + 2] = a.z; w[r][4 * v + 3] = a.w;
                 }
-                fma_sweep8<CY>(racc, wa, wb, tt);
-                if (j + 8 < tp) {
-                    load8<CY>(wa, frow + j + 16, rstride);
-                    const float4 a = *reinterpret_cast<const float4*>(trow + j + 8);
-                    const float4 b = *reinterpret_cast<const float4*>(trow + j + 12);
-                    tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = b.x; tt[5] = b.y; tt[6] = b.z; tt[7] = b.w;
-                    fma_sweep8<CY>(racc, wb, wa, tt);
+            }
+#pragma unroll 1
+            for (int e0 = 0; e0 < nd; e0 += CY) {
+#pragma unroll
+                for (int u = 0; u < CY; ++u) {
+                    const int e = e0 + u;  // template row d0 + e; tile rows are relative to d0
+                    if (e < nd) {
+                        float(&wn)[16] = w[(u + CY - 1) % CY];
+                        const float* pr = fb + (size_t)(e + CY - 1) * P;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 a = *reinterpret_cast<const float4*>(pr + 4 * v);
+                            wn[4 * v] = a.x; wn[4 * v + 1] = a.y; wn[4 * v + 2] = a.z; wn[4 * v + 3] = a.w;
+                        }
+                        float tt[8];
+                        {
+                            const float4 a = *reinterpret_cast<const float4*>(st + e * 8);
+                            const float4 b = *reinterpret_cast<const float4*>(st + e * 8 + 4);
+                            tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = b.x; tt[5] = b.y; tt[6] = b.z; tt[7] = b.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+#pragma unroll
+                            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = fmaf(w[(u + i) % CY][k + cx], tt[k], racc[i][cx]);
+                    }
                 }
             }
 #pragma unroll
-            for (int cy = 0; cy < CY; ++cy)
+            for (int i = 0; i < CY; ++i)
 #pragma unroll
-                for (int cx = 0; cx < 8; ++cx) acc[cy][cx] += racc[cy][cx];
+                for (int cx = 0; cx < 8; ++cx) acc[i][cx] += racc[i][cx];
         }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done with the slice
+    }
 
-        const double* dn = c.denom + (size_t)track * c.Hmax * c.Wmax;
-        float* mp = c.params->keep_maps ? c.maps + (size_t)track * c.Hmax * c.Wmax : nullptr;
-        const int flat = t.flat;
+    unsigned long long key = 0ull;
+    if (active) {
+        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+        if (g.pj * g.pd > 1) {
+            // K-split: store the partial sums; k_ncc_finalize adds the parts in order and normalises
+            float* part_out = c.partial + ((size_t)part * c.max_tracks) * c.Hmax * c.Wmax + woff;
 #pragma unroll
-        for (int cy = 0; cy < CY; ++cy) {
-            const int y = cy0 + slot + g.SB * cy;
-            if (y < wh) {
+            for (int i = 0; i < CY; ++i) {
+                const int y = grp * CY + i;
+                if (y < wh) {
 #pragma unroll
-                for (int cx = 0; cx < 8; ++cx) {
-                    const int x = cx0 + col * 8 + cx - xs;
-                    if (x >= 0 && x < ww) {
-                        const unsigned int idx = (unsigned int)(y * ww + x);
-                        const float v = ncc_finalize(acc[cy][cx], dn[idx], flat);
-                        if (mp) mp[idx] = v;
-                        const unsigned long long k = peak_key(v, idx);
-                        key = k > key ? k : key;
+                    for (int cx = 0; cx < 8; ++cx) {
+                        const int x = col * 8 + cx - xs;
+                        if (x >= 0 && x < ww) part_out[y * ww + x] = acc[i][cx];
+                    }
+                }
+            }
+        } else {
+            const double* dn = c.denom + woff;
+            float* mp = c.params->keep_maps ? c.maps + woff : nullptr;
+            const int flat = t.flat;
+#pragma unroll
+            for (int i = 0; i < CY; ++i) {
+                const int y = grp * CY + i;
+                if (y < wh) {
+                    // issue the row's 8 normaliser loads back to back (the window registers are dead by now), then finalise
+                    double d8[8];
+#pragma unroll
+                    for (int cx = 0; cx < 8; ++cx) {
+                        const int x = col * 8 + cx - xs;
+                        d8[cx] = (x >= 0 && x < ww) ? __ldg(dn + y * ww + x) : 0.0;
+                    }
+#pragma unroll
+                    for (int cx = 0; cx < 8; ++cx) {
+                        const int x = col * 8 + cx - xs;
+                        if (x >= 0 && x < ww) {
+                            const unsigned int idx = (unsigned int)(y * ww + x);
+                            const float v = ncc_finalize(acc[i][cx], d8[cx], flat);
+                            if (mp) mp[idx] = v;
+                            const unsigned long long k = peak_key(v, idx);
+                            key = k > key ? k : key;
+                        }
                     }
                 }
             }
         }
+    }
+    if (g.pj * g.pd == 1) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            unsigned long long o = shfl_xor_u64(key, m);
+            key = o > key ? o : key;
+        }
+        if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+    }
+}
+
+// K-split second stage: add the parts' partial sums in part order, normalise, pick the peak.
+// NOTE the summation order differs from the unsplit kernel (parts regroup template rows), so scores may differ
+// from it in the last bits; within one configuration every candidate is summed identically (exact ties stay exact).
+__global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, int parts)
+{
+    const int track = blockIdx.y;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const int n = t.win[2] * t.win[3];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (idx < n) {
+        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+        const size_t pstride = (size_t)c.max_tracks * c.Hmax * c.Wmax;
+        float acc = 0.f;
+        for (int p = 0; p < parts; ++p) acc += c.partial[p * pstride + woff + idx];
+        const float v = ncc_finalize(acc, c.denom[woff + idx], t.flat);
+        if (c.params->keep_maps) c.maps[woff + idx] = v;
+        key = peak_key(v, (unsigned int)idx);
     }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
@@ -424,9 +523,10 @@ __device__ void refresh_template(const Ctx& c, int track, TrackState& t, double*
         t.templ_norm = sqrt(norm2) / sqrt(scale);
         t.tp = tpad;
     }
+    // centred template, CHUNK-MAJOR: tc[(x / 8) * th * 8 + y * 8 + (x % 8)], columns >= tw are zero
     float* tc = c.templc + (size_t)track * c.mth * c.mtp;
     for (int i = tid; i < th * tpad; i += blockDim.x) {
-        const int y = i / tpad, x = i - y * tpad;
+        const int ch = i / (th * 8), r = i - ch * th * 8, y = r >> 3, x = ch * 8 + (r & 7);
         tc[i] = x < tw ? (float)((double)tp_[y * tw + x] - mean) : 0.f;
     }
     __syncthreads();

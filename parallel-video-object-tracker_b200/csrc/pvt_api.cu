@@ -95,37 +95,47 @@ int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
     return PVT_OK;
 }
 
-// Pick the CTA shape of k_ncc_tiled: NC thread-columns x SB row-slots (each thread 8 x kCY candidates).
-// Maximises (useful candidate fraction) x (SM occupancy, capped at 8 warps) x (warps per CTA balanced over
-// the 4 SM sub-partitions), subject to the TMA box limits (<= 256 per dim) and the 227 KB shared memory.
-bool choose_tile(int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
+// Plan k_ncc_search for a context: row-band height (GB groups of kCY rows), and the K-split (pj parts along the
+// template's 8-column chunks x pd parts along its rows).  K-split serves two purposes: (1) large templates / windows
+// (4K, 128x128, R=160) only fit the 256-row TMA box and the shared memory when a CTA sees part of the template;
+// (2) with few tracks (a single 1080p stream is 106 MMAC = 2.9 us of FP32 peak) the work must be cut finely enough
+// to occupy all SMs.  The model: CTAs run in waves of sm_count * per_sm; a CTA costs its per-thread FMA count over
+// the measured loop rate (tools/microbench2.cu: 0.87 FMA/clk/SMSP with 2 warps per sub-partition, ~0.6 with one)
+// plus a fixed prologue; a second-stage reduction is charged when parts > 1.  Smallest estimated time wins.
+bool choose_plan(int sm_count, int n_tracks, int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
 {
-    double best = -1.0;
-    const int cols = (Wmax + 3 + 7) / 8;  // + up to 3 masked columns: the tile origin is aligned down to 4 pixels
-    for (int NC = 1; NC <= 24; ++NC)
-        for (int SB = 1; SB <= 64; ++SB) {
-            const int threads = NC * SB;
-            if (threads > 256) continue;
-            const int boxW = 8 * NC + mtp + 4, boxH = kCY * SB + mth - 1;
-            if (boxW > 256 || boxH > 256) continue;
-            const size_t smem = (size_t)boxW * boxH * 4 + (size_t)mth * mtp * 4 + 16;
-            if (smem > kSmemBudget) continue;
-            const int warps = (threads + 31) / 32;
-            const int ncb = (cols + NC - 1) / NC, nb = (Hmax + kCY * SB - 1) / (kCY * SB);
-            const double useful = (double)Wmax * Hmax / ((double)ncb * nb * warps * 32 * 8 * kCY);
-            const int per_sm = (int)std::min<size_t>(kSmemBudget / smem, 8);
-            const double occ = std::min(1.0, per_sm * warps / 8.0);
-            const int w4 = per_sm * warps;
-            const double bal = (double)w4 / (((w4 + 3) / 4) * 4);
-            const double lanes = (SB >= 8) ? 1.0 : 0.7;  // < 8 consecutive row-slots per column: bank conflicts
-            const double score = useful * occ * bal * lanes;
-            if (score > best) {
-                best = score;
-                *out = TileCfg{NC, SB, boxW, boxH, ncb, nb};
-                *smem_out = smem;
+    const int CY = kCY;
+    const int G = (Hmax + CY - 1) / CY, C = (Wmax + 3 + 7) / 8, nch = mtp / 8;
+    double best = 1e300;
+    for (int pj = 1; pj <= nch; pj *= 2)
+        for (int pd = 1; pd <= mth && pd <= 64; pd *= 2) {
+            const int nchp = (nch + pj - 1) / pj, ndp = (mth + pd - 1) / pd;
+            for (int GB = 1; GB <= G; ++GB) {
+                const int boxH = GB * CY + ndp - 1;
+                if (boxH > 256) break;
+                const int span = std::min(C, (kTilesPerCta - 1) / GB + 2);
+                const int boxW = 8 * span + 8 * nchp + 4;
+                if (boxW > 256) continue;
+                const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
+                if (smem + 1024 > kSmemBudget) continue;
+                const int per_sm = (2 * (smem + 1024) <= 228u * 1024u) ? 2 : 1;
+                const int bands = (G + GB - 1) / GB, ctas_band = (GB * C + kTilesPerCta - 1) / kTilesPerCta;
+                const long long ctas = (long long)n_tracks * bands * ctas_band * pj * pd;
+                const double work = 8.0 * CY * 8.0 * nchp * ndp;  // FMAs per thread
+                const long long slots = (long long)sm_count * per_sm;
+                const long long waves = (ctas + slots - 1) / slots;
+                // warps sharing a sub-partition: 2 when both CTA slots of the SM are busy
+                const double rate = (per_sm == 2 && ctas >= slots + sm_count) ? 0.435 : (per_sm == 2 && ctas > sm_count ? 0.5 : 0.62);
+                const double cyc = work / rate + 5000.0 + 0.02 * smem;
+                const double time = waves * cyc + (pj * pd > 1 ? 7000.0 : 0.0);
+                if (time < best) {
+                    best = time;
+                    *out = TileCfg{G, C, GB, bands, ctas_band, span, boxW, boxH, pj, pd};
+                    *smem_out = smem;
+                }
             }
         }
-    return best > 0;
+    return best < 1e300;
 }
 
 int encode_tmap(pvt_ctx* c)
@@ -229,8 +239,9 @@ int launch_step_kernels(pvt_ctx* c, bool profile)
     if (c->params.kernel == PVT_KERNEL_DIRECT) {
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
-        const int threads = ((c->tile.NC * c->tile.SB + 31) / 32) * 32;
-        k_ncc_tiled<kCY><<<dim3(c->tile.ncb * c->tile.nbands, d.max_tracks), threads, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        const int parts = c->tile.pj * c->tile.pd;
+        k_ncc_search<kCY><<<dim3(c->tile.bands * c->tile.ctas_band, d.max_tracks, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        if (parts > 1) k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d, parts);
     }
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_ncc"); if (r) return r; }
@@ -328,12 +339,12 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
     } else if (c->profiling || debug_sync()) {
         int r = launch_step_kernels(c, c->profiling);
         if (r) return r;
-        c->launches += 5;
+        c->launches += 5 + ((c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1) ? 1 : 0);
         if (c->profiling) c->prof.steps += 1;
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
-        c->launches += 5;
+        c->launches += 5 + ((c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1) ? 1 : 0);
     }
     if (copied) {
         CK(cudaEventRecord(c->ev_done[sd], c->compute));
@@ -535,11 +546,32 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     c->stage_bytes = (size_t)d.W * d.H * 4;
     c->track_stream.assign(d.max_tracks, -1);
 
-    if (!choose_tile(d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
+    if (!choose_plan(prop.multiProcessorCount, d.max_tracks, d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
         pvt_destroy(c);
-        return fail(PVT_ERR_UNSUPPORTED, "template too large for the shared-memory tile of k_ncc_tiled");
+        return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
     }
-    CKD(cudaFuncSetAttribute(k_ncc_tiled<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
+    if (const char* e = getenv("PVT_PLAN")) {  // experiments: "GB,pj,pd" overrides the planner
+        int GB = 0, pj = 0, pd = 0;
+        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0) {
+            TileCfg& g = c->tile;
+            const int nch = d.mtp / 8, nchp = (nch + pj - 1) / pj, ndp = (d.mth + pd - 1) / pd;
+            g.GB = std::min(GB, g.G); g.pj = pj; g.pd = pd;
+            g.bands = (g.G + g.GB - 1) / g.GB; g.ctas_band = (g.GB * g.C + kTilesPerCta - 1) / kTilesPerCta;
+            g.span = std::min(g.C, (kTilesPerCta - 1) / g.GB + 2);
+            g.boxW = 8 * g.span + 8 * nchp + 4; g.boxH = g.GB * kCY + ndp - 1;
+            c->ncc_smem = (size_t)g.boxW * g.boxH * 4 + (size_t)4 * d.mth * 32 + 128;
+            if (g.boxW > 256 || g.boxH > 256 || c->ncc_smem + 1024 > kSmemBudget) {
+                pvt_destroy(c);
+                return fail(PVT_ERR_INVALID, "PVT_PLAN does not fit the TMA box / shared memory");
+            }
+        }
+    }
+    if (getenv("PVT_DEBUG_PLAN"))
+        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu\n", d.max_tracks,
+                c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH, c->tile.pj,
+                c->tile.pd, c->ncc_smem);
+    if (c->tile.pj * c->tile.pd > 1) CR(dev_alloc(c, &d.partial, (size_t)c->tile.pj * c->tile.pd * d.max_tracks * win, false));
+    CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
     c->rowsum_pw = d.VW + 8;
     c->rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * c->rowsum_pw * sizeof(double))));
     CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -4,7 +4,7 @@
 // mallocs/frees three buffers per call, tracker/src/baseline_kernel.cu:340-358):
 //   gray     [max_streams][H][pitch]  f32   toGrayF32 image of each stream's current frame (TMA source)
 //   templ    [max_tracks][mth*mtw]    f32   the tracker's template, exactly the reference's templ_gray_f32
-//   templc   [max_tracks][mth*mtp]    f32   fl32(templ - mean_t), rows zero-padded to a multiple of 8
+//   templc   [max_tracks][mth*mtp]    f32   fl32(templ - mean_t), chunk-major [x/8][y][x%8], columns zero-padded to 8
 //   vsum/vsq [max_tracks][Hmax][VW]   f64   vertical box sums of f and f^2 over th rows (scratch)
 //   denom    [max_tracks][Hmax*Wmax]  f64   OpenCV's normaliser t = sqrt(diff2)*sigma_t*sqrt(N), 0 when flat
 //   maps     [max_tracks][Hmax*Wmax]  f32   optional (keep_maps)
@@ -22,7 +22,7 @@ namespace pvt {
 
 constexpr int kRing = 64;      // time steps that may be in flight
 constexpr int kCX = 8;         // candidates per thread along x (contiguous)
-constexpr int kCY = 4;         // candidates per thread along y (interleaved by the slot count)
+constexpr int kCY = 5;         // candidates per thread along y (adjacent rows; odd => conflict-free LDS.128)
 constexpr int kColsumRows = 16;  // candidate rows per thread in the vertical box-sum kernel
 
 struct FrameDesc {
@@ -64,6 +64,7 @@ struct Ctx {
     double* vsq;
     double* denom;
     float* maps;
+    float* partial;            // [parts][max_tracks][Hmax*Wmax] K-split partial cross terms (latency mode)
     TrackState* tracks;
     FrameDesc* table;
     pvt_result* results;
@@ -123,6 +124,10 @@ __device__ __forceinline__ void fence_mbar_init()
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {

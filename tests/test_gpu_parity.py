@@ -127,8 +127,10 @@ def test_clip_trajectory_vs_oracle_and_direct_kernel(name):
     d = Hp.check_records(rec, want[:, :7], name)
     assert d <= 2e-5 and np.array_equal(templ, wt)
     rec2, templ2 = run_clip(c["frames"], c["roi"], kernel=pvt.KERNEL_DIRECT, **kw)
-    # the verification kernel sums every candidate in the same order: bit-identical results
-    assert np.array_equal(rec, rec2) and np.array_equal(templ, templ2)
+    # the verification kernel: same boxes, flags and template; scores equal up to the summation order (a single-track
+    # context splits the template over several CTAs -- K-split -- which regroups the FP32 partial sums)
+    assert np.array_equal(rec[:, [0, 1, 2, 3, 5, 6]], rec2[:, [0, 1, 2, 3, 5, 6]]) and np.array_equal(templ, templ2)
+    assert np.abs(rec[:, 4] - rec2[:, 4]).max() <= 2e-6
 
 
 def test_batch_mode_hold_semantics():
@@ -157,7 +159,7 @@ def test_window_map(name, k):
             tr.set_state(0, (int(bbox[0]), int(bbox[1]), roi[2], roi[3]), templ)
             tr.step([frames[k]])
             m2, _ = tr.window_map(0)
-            assert np.array_equal(m, m2)
+            assert np.abs(m - m2).max() <= 1e-5 and np.argmax(m) == np.argmax(m2)
     assert win == tuple(int(v) for v in g[f"map{k}_win"])
     off, on = g[f"map{k}_ipp_off"], g[f"map{k}_ipp_on"]
     gray = O.to_gray_f32(frames[k])

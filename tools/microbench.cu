@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) k_pat(float* out, int iters, float a0,
 {
     float acc[32], w[32], t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { acc[i] = 0.f; w[i] = a0 + i * 1e-3f + threadIdx.x * 1e-5f; t[i] = b0 + i * 1e-4f; }
+    for (int i = 0; i < 32; ++i) { acc[i] = 0.f; w[i] = a0 + i * 1e-3f + threadIdx.x * 1e-5f; t[i] = b0 + i * 1e-4f + threadIdx.x * 1e-7f; }
     long long c0 = clock64();
     unsigned long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     for (int it = 0; it < iters; ++it) {
@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(256, 1) k_pat(float* out, int iters, float a0,
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                acc[i] = PAT == 0 ? fmaf(a0, b0, acc[i]) : PAT == 1 ? fmaf(w[i], b0, acc[i]) : fmaf(w[i], t[i], acc[i]);
+                acc[i] = PAT == 0 ? fmaf(a0, b0, acc[i]) : PAT == 1 ? fmaf(w[i], b0, acc[i]) : PAT == 2 ? fmaf(w[i], t[i], acc[i])
+                       : PAT == 3 ? fmaf(w[i], t[r], acc[i])            /* vector t, same for the 32 FMAs of a group (.reuse) */
+                       : PAT == 4 ? fmaf(w[i], w[i], acc[i])            /* two reads of ONE register + accumulator */
+                                  : fmaf(w[(i + r) & 31], t[r], acc[i]); /* sliding pairing + reused vector t */
     }
     long long c1 = clock64();
     unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
@@ -202,10 +205,12 @@ int main()
     printf("device %s, %d SMs, max clock %.3f GHz\n", p.name, p.multiProcessorCount, ghz);
     const int sms = p.multiProcessorCount;
     run_pat<0>("FFMA acc+=a*b (invariant a,b)", sms, ghz, 256);
-    run_pat<0>("FFMA acc+=a*b (invariant a,b)", sms, ghz, 512);
     run_pat<1>("FFMA acc+=w[i]*b (fixed pairing)", sms, ghz, 256);
-    run_pat<1>("FFMA acc+=w[i]*b (fixed pairing)", sms, ghz, 512);
     run_pat<2>("FFMA acc+=w[i]*t[i] (3 fresh)", sms, ghz, 256);
+    run_pat<3>("FFMA acc+=w[i]*t[r] (vector t reused x32)", sms, ghz, 256);
+    run_pat<3>("FFMA acc+=w[i]*t[r] (vector t reused x32)", sms, ghz, 128);
+    run_pat<4>("FFMA acc+=w[i]*w[i]", sms, ghz, 256);
+    run_pat<5>("FFMA acc+=w[(i+r)%32]*t[r] (sliding, t reused)", sms, ghz, 256);
     run<0, 4>("FFMA  regs only", sms, ghz, 256, 1);
     run<0, 4>("FFMA  regs only", sms, ghz, 128, 1);
     run<0, 4>("FFMA  regs only", sms, ghz, 128, 3);
