@@ -1,0 +1,72 @@
+"""The C++ host layer (reference interface mirror + CLI twin) over the C ABI.
+CPU part: it builds and rejects what it must.  GPU part: same trajectories / maps as the golden vectors."""
+import importlib
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import helpers as Hp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "parallel-video-object-tracker_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def built():
+    importlib.import_module("parallel-video-object-tracker_b200").lib()
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return HOST
+
+
+def write_clip(path, frames):
+    n, h, w, _ = frames.shape
+    with open(path, "wb") as f:
+        f.write(b"PVTBGR1\n" + struct.pack("<iii", w, h, n))
+        f.write(np.ascontiguousarray(frames).tobytes())
+
+
+def test_cli_builds_and_rejects_cpu_mode(built, tmp_path):
+    r = subprocess.run([os.path.join(built, "tracker"), "--cpu", "nothing.bgr"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU path" in r.stderr
+    assert "Mode        : cpu" in r.stdout                      # the reference banner, main.cpp:43-49
+    r = subprocess.run([os.path.join(built, "tracker"), str(tmp_path / "missing.bgr"), "--roi", "1,1,4,4"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Cannot open video." in r.stderr   # main.cpp:54
+    (c, _) = Hp.clip("small")
+    write_clip(tmp_path / "c.bgr", c["frames"][:2])
+    r = subprocess.run([os.path.join(built, "tracker"), str(tmp_path / "c.bgr")], capture_output=True, text=True)
+    assert r.returncode != 0 and "No ROI selected." in r.stderr      # main.cpp:66-69
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,flags", [("small", []), ("small", ["--const_tiled"]), ("lost", ["--shared"]), ("batch4", ["--batch=4"])])
+def test_cli_trajectory_matches_golden(built, tmp_path, name, flags):
+    (c, tk) = Hp.clip(name)
+    g = Hp.golden(f"clip_{name}.npz")["records"]
+    write_clip(tmp_path / "c.bgr", c["frames"])
+    roi = ",".join(str(v) for v in c["roi"])
+    r = subprocess.run([os.path.join(built, "tracker"), *flags, str(tmp_path / "c.bgr"), "--roi", roi, "--out", str(tmp_path / "o.csv")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert " Tracking Complete" in r.stdout and f" Frames     : {len(c['frames']) - 1}" in r.stdout   # main.cpp:175-182
+    rows = np.genfromtxt(tmp_path / "o.csv", delimiter=",", skip_header=1)
+    got = np.column_stack([rows[:, 1:5], rows[:, 5], rows[:, 6:8]])
+    Hp.check_records(got, g, f"cli {name} {flags}")
+
+
+@pytest.mark.gpu
+def test_cpp_operators_match_golden(built, tmp_path):
+    g = Hp.golden("maps.npz")
+    f, t = g["frame"], g["templ"]
+    f.tofile(tmp_path / "f.f32"); t.tofile(tmp_path / "t.f32")
+    r = subprocess.run([os.path.join(built, "ops_demo"), str(tmp_path / "f.f32"), str(f.shape[1]), str(f.shape[0]),
+                        str(tmp_path / "t.f32"), str(t.shape[1]), str(t.shape[0]), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    ref = g["full_ipp_off"]
+    maps = {k: np.fromfile(tmp_path / f"o.{k}.f32", np.float32).reshape(ref.shape)
+            for k in ("naive", "shared", "const", "const_tiled", "view", "batched0", "batched1")}
+    for k, m in maps.items():
+        assert np.abs(m - ref).max() <= Hp.TOL_SCORE, k
+        assert np.array_equal(m, maps["naive"]), k          # every mode runs the same kernels
