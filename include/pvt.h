@@ -188,6 +188,11 @@ PVT_API int pvt_ncc_match_batched(int device, int n, const float* const* frames,
 /* measurement hooks */
 PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA events, plain stream launches */
 PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);
+/* device-side timeline: with tracing on, every kernel stamps %globaltimer (ns) at its first CTA's start and last
+ * CTA's end; pvt_trace_get copies the stamps of the last <= 64 steps: out[step][8 kernel slots][2], slots =
+ * ingest, colprefix, rowsum, ncc_search, ncc_finalize, update.  Returns the number of steps written. */
+PVT_API int pvt_trace_enable(pvt_ctx* ctx, int on);
+PVT_API int pvt_trace_get(pvt_ctx* ctx, uint64_t* out, int max_steps);
 PVT_API int64_t pvt_launch_count(pvt_ctx* ctx); /* kernels launched by this context so far (graph nodes counted per launch) */
 /* device time of everything submitted between pvt_timer_start and pvt_timer_stop, CUDA events on the context's stream */
 PVT_API int pvt_timer_start(pvt_ctx* ctx);

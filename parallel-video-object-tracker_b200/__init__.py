@@ -35,7 +35,7 @@ SYMBOLS = [
     "pvt_destroy", "pvt_set_params", "pvt_alloc_pinned", "pvt_free_pinned", "pvt_track_init", "pvt_track_remove",
     "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
-    "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop",
+    "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
 ]
 
 
@@ -118,6 +118,8 @@ def lib():
                                         C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t]
     L.pvt_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.pvt_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_int]
+    L.pvt_trace_enable.argtypes = [C.c_void_p, C.c_int]
+    L.pvt_trace_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.pvt_timer_start.argtypes = [C.c_void_p]
     L.pvt_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pvt_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -319,6 +321,16 @@ class Tracker:
         p = Profile()
         _ck(lib().pvt_profile_get(self._h, C.byref(p), 1 if reset else 0))
         return {k: getattr(p, k) for k, _ in Profile._fields_}
+
+    def trace_enable(self, on=True):
+        _ck(lib().pvt_trace_enable(self._h, 1 if on else 0))
+
+    def trace_get(self, max_steps=64) -> np.ndarray:
+        """[steps, 8 kernel slots, 2] globaltimer ns (start of first CTA, end of last CTA); slots: ingest, colprefix,
+        rowsum, ncc_search, ncc_finalize, update."""
+        out = np.zeros((max_steps, 8, 2), np.uint64)
+        n = _ck(lib().pvt_trace_get(self._h, out.ctypes.data, max_steps))
+        return out[:n]
 
     def launch_count(self) -> int:
         return int(lib().pvt_launch_count(self._h))

@@ -1,5 +1,5 @@
 // Hand-written sm_100a kernels of the NCC tracking hot path.  One time step = the launch sequence
-//   k_ingest -> k_colsum -> k_rowsum -> k_ncc_search [-> k_ncc_finalize] (or k_ncc_direct) -> k_update
+//   k_ingest -> k_colprefix -> k_rowsum -> k_ncc_search [-> k_ncc_finalize] (or k_ncc_direct) -> k_update
 // captured once as a CUDA graph; every kernel finds "which frame / which step" through the
 // device-side step counter and frame table, so the graph is launched unchanged for every frame and
 // nothing returns to the host between frames.
@@ -9,6 +9,10 @@
 #include "pvt_device.cuh"
 
 namespace pvt {
+
+// defined in section (5), used earlier
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red);
+__device__ void track_update(const Ctx& c, int track, unsigned long long step, bool stepped, float* s_t, double* red);
 
 // =============================================================================================
 // (1) ingest: BGR u8 -> gray -> f32/255          reference: tracker/include/utils.hpp:5-14
@@ -27,8 +31,9 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
 {
     const unsigned long long step = *c.step;
     const int stream = blockIdx.y;
-    const FrameDesc d = c.table[(step % kRing) * c.max_streams + stream];
+    const FrameDesc d = c.table[table_row(c, step) + stream];
     if (!d.valid) return;
+    trace_begin(c, step, TR_INGEST);
     const int gpr = (c.W + 3) >> 2;  // 4-pixel groups per row
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)gpr * c.H) return;
@@ -64,6 +69,7 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
         o = make_float4(v[0], v[1], v[2], v[3]);
     }
     *reinterpret_cast<float4*>(out) = o;  // pitch is a multiple of 4 floats: always in bounds, 16-byte aligned
+    trace_end(c, step, TR_INGEST);
 }
 
 // =============================================================================================
@@ -72,49 +78,78 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
 //     normaliser (common_matchTemplate, TM_CCOEFF_NORMED):
 //       diff2 = max(wsq - wsum^2 * invArea, 0)
 //       t     = diff2 <= min(0.5, 10*FLT_EPSILON*wsq) ? 0 : sqrt(diff2) * sigma_t / sqrt(invArea)
-//     Separable box sums: k_colsum (vertical, sliding) then k_rowsum (row prefix, difference).
+//     Two scan kernels with short dependency chains and many independent loads (the tile is L2-resident; what
+//     costs is serialised L2 latency, not bandwidth):
+//       k_colprefix: C[r][X] = sum_{r' < r} f[r'][X] over the search tile, per 32-column strip; each thread owns a
+//                    chunk of rows (independent loads), chunk offsets through shared memory.
+//       k_rowsum:    one warp per candidate row y: D[X] = C[y+th][X] - C[y][X] (vertical box sums), inclusive prefix
+//                    of D along x (8 values per lane + warp scan), box = P[x+tw] - P[x], normaliser.
 //     For u8-sourced frames every partial sum of f is exactly representable in double, so wsum is
-//     bit-identical to OpenCV's whole-frame integral; wsq agrees to ~1e-16 relative.
+//     bit-identical to OpenCV's whole-frame integral; wsq agrees to ~1e-15 relative.
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_colsum(Ctx c)
+__global__ void __launch_bounds__(1024) k_colprefix(Ctx c)
 {
-    const int track = blockIdx.z;
+    __shared__ double tot[2][32][33];
+    const int track = blockIdx.y;
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
+    trace_begin(c, step, TR_COLPREFIX);
     const DevParams P = *c.params;
     int win[4];
     search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) t.win[threadIdx.x] = win[threadIdx.x];
-    const int X = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tileW = win[2] + t.w - 1;
-    const int yb = blockIdx.y * kColsumRows;
-    if (X >= tileW || yb >= win[3]) return;
-    const int ye = min(yb + kColsumRows, win[3]);
-    const int th = t.h;
-    const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)(win[1] + yb) * c.pitch + win[0] + X;
+    if (blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x < 4) t.win[threadIdx.x] = win[threadIdx.x];
+    const int tileW = win[2] + t.w - 1, tileH = win[3] + t.h - 1;
+    const int lx = threadIdx.x, ch = threadIdx.y, nch = blockDim.y;
+    const int X = blockIdx.x * 32 + lx;
+    if (blockIdx.x * 32 >= tileW) return;
+    const int rc = (tileH + nch - 1) / nch;                    // rows per chunk
+    const int r0 = min(ch * rc, tileH), r1 = min(r0 + rc, tileH);
+    const bool okx = X < tileW;
+    const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)win[1] * c.pitch + win[0] + X;
     double s = 0.0, q = 0.0;
-    for (int dy = 0; dy < th; ++dy) {
-        double v = (double)col[(size_t)dy * c.pitch];
-        s += v;
-        q += v * v;
+    if (okx) {
+        // loads are issued in batches of 16 before any is consumed: one L2 round trip per batch instead of one per row
+        for (int r = r0; r < r1; r += 16) {
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = (r + k < r1) ? __ldg(col + (size_t)(r + k) * c.pitch) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double d = (double)v[k];
+                s += d;
+                q += d * d;
+            }
+        }
     }
-    size_t o = ((size_t)track * c.Hmax + yb) * c.VW + X;
-    c.vsum[o] = s;
-    c.vsq[o] = q;
-    for (int y = yb + 1; y < ye; ++y) {
-        double vn = (double)col[(size_t)(y - yb + th - 1) * c.pitch];
-        double vo = (double)col[(size_t)(y - yb - 1) * c.pitch];
-        s = (s + vn) - vo;
-        q = (q + vn * vn) - vo * vo;
-        o += c.VW;
-        c.vsum[o] = s;
-        c.vsq[o] = q;
+    tot[0][ch][lx] = s;
+    tot[1][ch][lx] = q;
+    __syncthreads();
+    if (!okx) return;
+    s = 0.0; q = 0.0;
+    for (int k = 0; k < ch; ++k) { s += tot[0][k][lx]; q += tot[1][k][lx]; }
+    const int rows = c.Hmax + c.mth;                             // C has tileH + 1 <= Hmax + mth rows
+    double* cs = c.vsum + ((size_t)track * rows) * c.VW + X;
+    double* cq = c.vsq + ((size_t)track * rows) * c.VW + X;
+    if (ch == 0) { cs[0] = 0.0; cq[0] = 0.0; }
+    for (int r = r0; r < r1; r += 16) {                         // second pass over the chunk: L1 hits
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (r + k < r1) ? __ldg(col + (size_t)(r + k) * c.pitch) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (r + k < r1) {
+                const double d = (double)v[k];
+                s += d;
+                q += d * d;
+                cs[(size_t)(r + k + 1) * c.VW] = s;
+                cq[(size_t)(r + k + 1) * c.VW] = q;
+            }
+        }
     }
+    if (lx == 0) { if (c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_COLPREFIX) * 2 + 1], gtime()); }
 }
 
-// one warp per candidate row: inclusive prefix of the vertical sums along x (8 consecutive values per
-// lane + warp scan, with a carry between 256-wide segments), then box sum = P[x+tw] - P[x].
 __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per prefix row in smem */)
 {
     extern __shared__ double sm_d[];
@@ -122,24 +157,36 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     const TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
+    trace_begin(c, step, TR_ROWSUM);
     const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * warps + w;
-    const int ww = t.win[2], wh = t.win[3], tw = t.w;
+    const int ww = t.win[2], wh = t.win[3], tw = t.w, th = t.h;
     if (y >= wh) return;  // warp-uniform
     const int tileW = ww + tw - 1;
     double* Ps = sm_d + (size_t)w * 2 * pw;
     double* Pq = Ps + pw;
-    const double* vs = c.vsum + ((size_t)track * c.Hmax + y) * c.VW;
-    const double* vq = c.vsq + ((size_t)track * c.Hmax + y) * c.VW;
+    const int rows = c.Hmax + c.mth;
+    const double* cs0 = c.vsum + ((size_t)track * rows + y) * c.VW;
+    const double* cq0 = c.vsq + ((size_t)track * rows + y) * c.VW;
+    const double* cs1 = cs0 + (size_t)th * c.VW;
+    const double* cq1 = cq0 + (size_t)th * c.VW;
     double carry_s = 0.0, carry_q = 0.0;
     for (int base = 0; base < tileW; base += 256) {
         const int i0 = base + lane * 8;
+        double a0[8], a1[8], b0[8], b1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                       // 32 independent loads in flight per lane
+            const bool ok = i0 + k < tileW;
+            a0[k] = ok ? __ldg(cs0 + i0 + k) : 0.0;
+            a1[k] = ok ? __ldg(cs1 + i0 + k) : 0.0;
+            b0[k] = ok ? __ldg(cq0 + i0 + k) : 0.0;
+            b1[k] = ok ? __ldg(cq1 + i0 + k) : 0.0;
+        }
         double ls[8], lq[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const bool ok = i0 + k < tileW;
-            ls[k] = ok ? vs[i0 + k] : 0.0;
-            lq[k] = ok ? vq[i0 + k] : 0.0;
+            ls[k] = a1[k] - a0[k];                          // vertical box sum of column i0+k
+            lq[k] = b1[k] - b0[k];
         }
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
@@ -164,7 +211,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     }
     if (lane == 0) { Ps[0] = 0.0; Pq[0] = 0.0; }
     __syncwarp();
-    const double invArea = 1.0 / ((double)t.h * (double)tw);
+    const double invArea = 1.0 / ((double)th * (double)tw);
     const double tn = t.templ_norm;
     double* dn = c.denom + (size_t)track * c.Hmax * c.Wmax + (size_t)y * ww;
     for (int x = lane; x < ww; x += 32) {
@@ -178,6 +225,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
         if (lim > 0.5) lim = 0.5;
         dn[x] = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
     }
+    if (lane == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
 
 // OpenCV's final rule for TM_CCOEFF_NORMED (common_matchTemplate): never NaN, always in [-1, 1]
@@ -278,11 +326,19 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
-    const int ww = t.win[2], wh = t.win[3];
+    trace_begin(c, step, TR_NCC);
+    // the window is derived here (not read from t.win): in K-split mode this kernel runs concurrently with the
+    // statistics kernels, which are the ones that store it
+    int win[4];
+    {
+        const DevParams P = *c.params;
+        search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    }
+    const int ww = win[2], wh = win[3];
     const int th = t.h, nchunk = t.tp >> 3;
     // the TMA tile must start on a 16-byte boundary in x: the column grid starts at the window origin rounded
     // DOWN to a multiple of 4 pixels; the xs (0..3) grid columns in front of the window are masked
-    const int xs = t.win[0] & 3;
+    const int xs = win[0] & 3;
     const int band = blockIdx.x / g.ctas_band, q0 = (blockIdx.x - band * g.ctas_band) * kTilesPerCta;
     const int c_lo = q0 / g.GB;
     const int row0 = band * g.GB * CY;  // first candidate row of this band
@@ -314,14 +370,16 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         }
         fence_mbar_init();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
-        tma_load_3d(s_tile, &tmap, &bars[0], t.win[0] - xs + (c_lo + j0) * 8, t.win[1] + row0 + d0, t.stream);
+        tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, t.stream);
         for (int s = 0; s < 2 && s < nj; ++s) {
             mbar_arrive_expect_tx(&full[s], slice_bytes);
             bulk_load(s_templ + (size_t)s * c.mth * 8, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
         }
     }
     __syncthreads();  // barriers initialised before anybody polls them
+    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2] = gtime();
     mbar_wait(&bars[0], 0);
+    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2 + 1] = gtime();
 
     const int q = q0 + threadIdx.x;
     const int col = q / g.GB, gl = q - col * g.GB;
@@ -399,22 +457,20 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done with the slice
     }
 
+    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 7) * 2] = gtime();
     unsigned long long key = 0ull;
     if (active) {
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;
         if (g.pj * g.pd > 1) {
-            // K-split: store the partial sums; k_ncc_finalize adds the parts in order and normalises
-            float* part_out = c.partial + ((size_t)part * c.max_tracks) * c.Hmax * c.Wmax + woff;
+            // K-split: store the partial sums TILE-MAJOR (this thread's 8 x CY values contiguous: coalesced float4
+            // stores, no write amplification); k_ncc_finalize adds the parts in order and normalises
+            const size_t tiles_track = (size_t)g.bands * g.ctas_band * kTilesPerCta;
+            float4* po = reinterpret_cast<float4*>(c.partial + (((size_t)part * c.max_tracks + track) * tiles_track +
+                                                                (size_t)blockIdx.x * kTilesPerCta + threadIdx.x) * (8 * CY));
 #pragma unroll
             for (int i = 0; i < CY; ++i) {
-                const int y = grp * CY + i;
-                if (y < wh) {
-#pragma unroll
-                    for (int cx = 0; cx < 8; ++cx) {
-                        const int x = col * 8 + cx - xs;
-                        if (x >= 0 && x < ww) part_out[y * ww + x] = acc[i][cx];
-                    }
-                }
+                po[2 * i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
             }
         } else {
             const double* dn = c.denom + woff;
@@ -454,65 +510,154 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         }
         if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
     }
+    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 7) * 2 + 1] = gtime();
+    trace_end(c, step, TR_NCC);
 }
 
 // K-split second stage: add the parts' partial sums in part order, normalise, pick the peak.
 // NOTE the summation order differs from the unsplit kernel (parts regroup template rows), so scores may differ
 // from it in the last bits; within one configuration every candidate is summed identically (exact ties stay exact).
-__global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, int parts)
+__global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, TileCfg g)
 {
-    const int track = blockIdx.y;
+    extern __shared__ float sm_f[];
+    __shared__ double red[64];
+    __shared__ int s_last;
+    const int track = blockIdx.y, parts = g.pj * g.pd;
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
-    if (!track_stepped(c, t, step)) return;
-    const int n = t.win[2] * t.win[3];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long key = 0ull;
-    if (idx < n) {
-        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
-        const size_t pstride = (size_t)c.max_tracks * c.Hmax * c.Wmax;
-        float acc = 0.f;
-        for (int p = 0; p < parts; ++p) acc += c.partial[p * pstride + woff + idx];
-        const float v = ncc_finalize(acc, c.denom[woff + idx], t.flat);
-        if (c.params->keep_maps) c.maps[woff + idx] = v;
-        key = peak_key(v, (unsigned int)idx);
-    }
+    const bool stepped = track_stepped(c, t, step);
+    trace_begin(c, step, TR_FINALIZE);
+    if (stepped) {
+        const int ww = t.win[2], n = ww * t.win[3];
+        const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned long long key = 0ull;
+        if (idx < n) {
+            // candidate -> (thread tile, slot) of k_ncc_search: column-major tiles inside row bands
+            const int y = idx / ww, x = idx - y * ww;
+            const int gx = x + (t.win[0] & 3), col = gx >> 3, cx = gx & 7;
+            const int grp = y / kCY, i = y - grp * kCY;
+            const int band = grp / g.GB, gl = grp - band * g.GB;
+            const size_t tile = (size_t)band * g.ctas_band * kTilesPerCta + (size_t)col * g.GB + gl;
+            const size_t tiles_track = (size_t)g.bands * g.ctas_band * kTilesPerCta;
+            const size_t off = ((size_t)track * tiles_track + tile) * (8 * kCY) + i * 8 + cx;
+            const size_t pstride = (size_t)c.max_tracks * tiles_track * (8 * kCY);
+            const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+            const double dnv = __ldg(c.denom + woff + idx);
+            float acc = 0.f;
+            for (int p0 = 0; p0 < parts; p0 += 16) {           // 16 independent loads in flight, added in part order
+                float pv[16];
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        unsigned long long o = shfl_xor_u64(key, m);
-        key = o > key ? o : key;
+                for (int k = 0; k < 16; ++k) pv[k] = (p0 + k < parts) ? __ldg(c.partial + (size_t)(p0 + k) * pstride + off) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (p0 + k < parts) acc += pv[k];
+            }
+            const float v = ncc_finalize(acc, dnv, t.flat);
+            if (c.params->keep_maps) c.maps[woff + idx] = v;
+            key = peak_key(v, (unsigned int)idx);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            unsigned long long o = shfl_xor_u64(key, m);
+            key = o > key ? o : key;
+        }
+        if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
     }
-    if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+    // the last CTA of this track (all peaks are in) performs the gate / EMA / state update: no extra launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int k = atomicAdd(&t.ticket, 1u);
+        s_last = (k == gridDim.x - 1);
+        if (s_last) t.ticket = 0u;
+    }
+    __syncthreads();
+    trace_end(c, step, TR_FINALIZE);
+    if (!s_last) return;
+    __threadfence();
+    if (c.trace && threadIdx.x == 0) c.trace[((step % kRing) * 8 + TR_UPDATE) * 2] = gtime();
+    track_update(c, track, step, stepped, sm_f, red);
+    trace_end(c, step, TR_UPDATE);
 }
 
 // =============================================================================================
-// (4) template statistics + centred template (block-cooperative, 256 threads)
-//     cv::meanStdDev in double: mean = s/N, sigma^2 = max(sq/N - mean^2, 0);
-//     matchTemplate: all-ones map if sigma^2 < DBL_EPSILON; templNorm = sqrt(sigma^2)/sqrt(1/N).
+// (4) track initialisation / state injection (single CTA): main.cpp:70-71  templ = frame_gray_f32(bbox).clone()
+//     template statistics follow cv::meanStdDev in double (mean = s/N, sigma^2 = max(sq/N - mean^2, 0));
+//     matchTemplate returns an all-ones map if sigma^2 < DBL_EPSILON; templNorm = sqrt(sigma^2)/sqrt(1/N).
 // =============================================================================================
-__device__ void refresh_template(const Ctx& c, int track, TrackState& t, double* red /* 2*256 doubles of smem */)
+__global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream, int x, int y, int w, int h)
+{
+    extern __shared__ float sm_f[];
+    __shared__ double red[64];
+    TrackState& t = c.tracks[track];
+    const float* g = c.gray + (size_t)stream * c.plane;
+    float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int r = i / w, col = i - r * w;
+        const float v = g[(size_t)(y + r) * c.pitch + x + col];
+        tp_[i] = v;
+        sm_f[i] = v;
+    }
+    if (threadIdx.x == 0) {
+        t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull; t.ticket = 0u;
+        t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
+    }
+    __syncthreads();
+    finish_template(c, track, t, sm_f, red);
+}
+
+// re-derive statistics after pvt_set_state wrote bbox/template from the host
+__global__ void __launch_bounds__(256) k_track_refresh(Ctx c, int track)
+{
+    extern __shared__ float sm_f[];
+    __shared__ double red[64];
+    TrackState& t = c.tracks[track];
+    const float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    for (int i = threadIdx.x; i < t.w * t.h; i += blockDim.x) sm_f[i] = tp_[i];
+    __syncthreads();
+    finish_template(c, track, t, sm_f, red);
+}
+
+// =============================================================================================
+// (5) track_update: peak -> gates -> bbox -> EMA -> next frame's template statistics, by ONE CTA per track.
+//     main.cpp:150-161.  bestVal is the float peak widened to double and compared in double
+//     (0.7f < 0.7, so a float compare would flip decisions).  cv::addWeighted on CV_32F:
+//     templ' = (float) fma((double)templ, 1-lr, (double)patch * lr)   -- bit-exact (tests G5).
+//     The new template goes through shared memory once: EMA, its FP64 sum / sum of squares (cv::meanStdDev),
+//     then the centred chunk-major copy -- no second trip to HBM.
+//     The CTA that finishes the last track of the step advances the device step counter, so the next graph
+//     launch picks the next frame-table entry without any host action.
+//     Called by k_update (its own launch) or by the last k_ncc_finalize CTA of the track (K-split mode).
+// =============================================================================================
+__device__ void block_sum2(double& s, double& q, double* red /* 2 * 32 doubles */)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        s += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(s), m), __shfl_xor_sync(0xffffffffu, __double2loint(s), m));
+        q += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(q), m), __shfl_xor_sync(0xffffffffu, __double2loint(q), m));
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[w] = s; red[32 + w] = q; }
+    __syncthreads();
+    s = 0.0; q = 0.0;
+    for (int i = 0; i < nw; ++i) { s += red[i]; q += red[32 + i]; }   // same order in every thread: identical result
+}
+
+// statistics + centred chunk-major template from the template held in shared memory (s_t, th*tw floats)
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red)
 {
     const int tw = t.w, th = t.h, n = tw * th, tid = threadIdx.x;
-    const float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
     double s = 0.0, q = 0.0;
     for (int i = tid; i < n; i += blockDim.x) {
-        double v = (double)tp_[i];
+        const double v = (double)s_t[i];
         s += v;
         q += v * v;
     }
-    red[tid] = s;
-    red[256 + tid] = q;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if (tid < d) {
-            red[tid] += red[tid + d];
-            red[256 + tid] += red[256 + tid + d];
-        }
-        __syncthreads();
-    }
+    block_sum2(s, q, red);
     const double scale = 1.0 / (double)n;
-    const double mean = __dmul_rn(red[0], scale);
-    double var = __dsub_rn(__dmul_rn(red[256], scale), __dmul_rn(mean, mean));
+    const double mean = __dmul_rn(s, scale);
+    double var = __dsub_rn(__dmul_rn(q, scale), __dmul_rn(mean, mean));
     if (var < 0.0) var = 0.0;
     const double sdv = sqrt(var);
     const double norm2 = __dmul_rn(sdv, sdv);
@@ -527,56 +672,17 @@ __device__ void refresh_template(const Ctx& c, int track, TrackState& t, double*
     float* tc = c.templc + (size_t)track * c.mth * c.mtp;
     for (int i = tid; i < th * tpad; i += blockDim.x) {
         const int ch = i / (th * 8), r = i - ch * th * 8, y = r >> 3, x = ch * 8 + (r & 7);
-        tc[i] = x < tw ? (float)((double)tp_[y * tw + x] - mean) : 0.f;
+        tc[i] = x < tw ? (float)((double)s_t[y * tw + x] - mean) : 0.f;
     }
-    __syncthreads();
 }
 
-// main.cpp:70-71: templ = frame_gray_f32(bbox).clone()
-__global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream, int x, int y, int w, int h)
+__device__ void track_update(const Ctx& c, int track, unsigned long long step, bool stepped, float* s_t, double* red)
 {
-    __shared__ double red[512];
     TrackState& t = c.tracks[track];
-    const float* g = c.gray + (size_t)stream * c.plane;
-    float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
-    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-        const int r = i / w, col = i - r * w;
-        tp_[i] = g[(size_t)(y + r) * c.pitch + x + col];
-    }
-    if (threadIdx.x == 0) {
-        t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull;
-        t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
-    }
-    __syncthreads();
-    refresh_template(c, track, t, red);
-}
-
-// re-derive statistics after pvt_set_state wrote bbox/template from the host
-__global__ void __launch_bounds__(256) k_track_refresh(Ctx c, int track)
-{
-    __shared__ double red[512];
-    refresh_template(c, track, c.tracks[track], red);
-}
-
-// =============================================================================================
-// (5) k_update: peak -> gates -> bbox -> EMA -> next frame's template statistics, one CTA per track.
-//     main.cpp:150-161.  bestVal is the float peak widened to double and compared in double
-//     (0.7f < 0.7, so a float compare would flip decisions).  cv::addWeighted on CV_32F:
-//     templ' = (float) fma((double)templ, 1-lr, (double)patch * lr)   -- bit-exact (tests G5).
-//     The last CTA to finish advances the device step counter: the next graph launch then picks the
-//     next frame-table entry without any host action.
-// =============================================================================================
-__global__ void __launch_bounds__(256) k_update(Ctx c)
-{
-    __shared__ double red[512];
-    const int track = blockIdx.x;
-    TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
     pvt_result* res = c.results + (step % kRing) * c.max_tracks + track;
-    const bool stepped = track_stepped(c, t, step);
     if (stepped) {
         const DevParams P = *c.params;
-        const unsigned long long key = t.peak;
+        const unsigned long long key = *((volatile unsigned long long*)&t.peak);
         const float val = unord_f32((unsigned int)(key >> 32));
         const unsigned int idx = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
         const int ww = t.win[2];
@@ -591,13 +697,28 @@ __global__ void __launch_bounds__(256) k_update(Ctx c)
             const double alpha = 1.0 - P.lr, beta = P.lr;
             float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
             const float* g = c.gray + (size_t)t.stream * c.plane + (size_t)ny * c.pitch + nx;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int r = i / tw, col = i - r * tw;
-                const double pb = __dmul_rn((double)g[(size_t)r * c.pitch + col], beta);
-                tp_[i] = (float)fma((double)tp_[i], alpha, pb);
+            for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {   // 16 loads in flight per thread, then the EMA
+                float pv[8], tv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * blockDim.x;
+                    const int r = i / tw, col = i - r * tw;
+                    pv[k] = i < n ? g[(size_t)r * c.pitch + col] : 0.f;
+                    tv[k] = i < n ? tp_[i] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * blockDim.x;
+                    if (i < n) {
+                        const double pb = __dmul_rn((double)pv[k], beta);
+                        const float v = (float)fma((double)tv[k], alpha, pb);
+                        tp_[i] = v;
+                        s_t[i] = v;
+                    }
+                }
             }
             __syncthreads();
-            refresh_template(c, track, t, red);
+            finish_template(c, track, t, s_t, red);
         }
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
@@ -612,17 +733,28 @@ __global__ void __launch_bounds__(256) k_update(Ctx c)
         res->moved = 0; res->updated = 0; res->searched = 0; res->valid = (uint8_t)(t.active != 0);
         res->track = track; res->step = (int32_t)step;
     }
-    // last CTA done -> advance the time step (every CTA has read *c.step before taking a ticket)
+    // last track done -> advance the time step (every kernel of this step has read *c.step already)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int n = atomicAdd(c.ticket, 1u);
-        if (n == gridDim.x - 1) {
+        if (n == (unsigned int)c.max_tracks - 1u) {
             *c.ticket = 0u;
             *c.step = step + 1ull;
             __threadfence();
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_update(Ctx c)
+{
+    extern __shared__ float sm_f[];
+    __shared__ double red[64];
+    const int track = blockIdx.x;
+    const unsigned long long step = *c.step;
+    trace_begin(c, step, TR_UPDATE);
+    track_update(c, track, step, track_stepped(c, c.tracks[track], step), sm_f, red);
+    trace_end(c, step, TR_UPDATE);
 }
 
 // hold step (batch mode, main.cpp:118-123): no NCC, no update; emit the stale box and advance

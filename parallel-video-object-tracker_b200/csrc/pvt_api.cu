@@ -58,7 +58,10 @@ struct pvt_ctx {
     CUtensorMap tmap{};
     size_t ncc_smem = 0;
     int rowsum_warps = 8, rowsum_pw = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
+    size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
+    cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr;   // aux: second branch inside the captured graph
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr;
     bool graph_valid = false;
     std::vector<void*> allocs;
@@ -71,12 +74,14 @@ struct pvt_ctx {
     bool ev_done_used[kStageDepth]{};
     unsigned long long submitted = 0;  // time steps enqueued
     int hold_pending = 0;              // batch mode: frames since the last searched one
+    bool seq_default = true;           // device SeqDesc is {0, kRing, 0}
     int64_t launches = 0;
     bool profiling = false;
     std::vector<EventPair> ev_pool;
     size_t ev_next = 0;
     pvt_profile prof{};
     unsigned long long* d_macs = nullptr;
+    unsigned long long* d_trace = nullptr;
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     pvt_result* h_results = nullptr;  // pinned, [kRing][max_tracks]
     std::vector<int> track_stream;    // host mirror: -1 = inactive
@@ -99,37 +104,40 @@ int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
 // template's 8-column chunks x pd parts along its rows).  K-split serves two purposes: (1) large templates / windows
 // (4K, 128x128, R=160) only fit the 256-row TMA box and the shared memory when a CTA sees part of the template;
 // (2) with few tracks (a single 1080p stream is 106 MMAC = 2.9 us of FP32 peak) the work must be cut finely enough
-// to occupy all SMs.  The model: CTAs run in waves of sm_count * per_sm; a CTA costs its per-thread FMA count over
-// the measured loop rate (tools/microbench2.cu: 0.87 FMA/clk/SMSP with 2 warps per sub-partition, ~0.6 with one)
-// plus a fixed prologue; a second-stage reduction is charged when parts > 1.  Smallest estimated time wins.
+// to occupy all SMs.  Cost model, calibrated on B200 with the device timeline (tools/timeline.py, profiles/):
+// CTAs run in rounds of 2 per SM; a round costs ~3 us of fixed latency (launch, TMA tile, partial-sum stores) plus the
+// per-thread FMA count over ~870 FMA/us (two warps per sub-partition) or ~1250 FMA/us (one); K-split adds the
+// second-stage reduction.  Smallest estimate wins; ties go to fewer parts, then taller bands.
 bool choose_plan(int sm_count, int n_tracks, int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
 {
     const int CY = kCY;
     const int G = (Hmax + CY - 1) / CY, C = (Wmax + 3 + 7) / 8, nch = mtp / 8;
+    const long long slots = (long long)sm_count * 2;
     double best = 1e300;
-    for (int pj = 1; pj <= nch; pj *= 2)
-        for (int pd = 1; pd <= mth && pd <= 64; pd *= 2) {
+    for (int pj = 1; pj <= nch; ++pj)
+        for (int pd = 1; pd <= mth && pd <= 32; ++pd) {
             const int nchp = (nch + pj - 1) / pj, ndp = (mth + pd - 1) / pd;
-            for (int GB = 1; GB <= G; ++GB) {
+            if ((pj > 1 && (pj - 1) * nchp >= nch) || (pd > 1 && (pd - 1) * ndp >= mth)) continue;  // a part would be empty
+            for (int GB = G; GB >= 1; --GB) {
                 const int boxH = GB * CY + ndp - 1;
-                if (boxH > 256) break;
+                if (boxH > 256) continue;
                 const int span = std::min(C, (kTilesPerCta - 1) / GB + 2);
                 const int boxW = 8 * span + 8 * nchp + 4;
                 if (boxW > 256) continue;
                 const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
-                if (smem + 1024 > kSmemBudget) continue;
-                const int per_sm = (2 * (smem + 1024) <= 228u * 1024u) ? 2 : 1;
+                if (2 * (smem + 1024) > 228u * 1024u) continue;   // two CTAs per SM
                 const int bands = (G + GB - 1) / GB, ctas_band = (GB * C + kTilesPerCta - 1) / kTilesPerCta;
                 const long long ctas = (long long)n_tracks * bands * ctas_band * pj * pd;
                 const double work = 8.0 * CY * 8.0 * nchp * ndp;  // FMAs per thread
-                const long long slots = (long long)sm_count * per_sm;
-                const long long waves = (ctas + slots - 1) / slots;
-                // warps sharing a sub-partition: 2 when both CTA slots of the SM are busy
-                const double rate = (per_sm == 2 && ctas >= slots + sm_count) ? 0.435 : (per_sm == 2 && ctas > sm_count ? 0.5 : 0.62);
-                const double cyc = work / rate + 5000.0 + 0.02 * smem;
-                const double time = waves * cyc + (pj * pd > 1 ? 7000.0 : 0.0);
-                if (time < best) {
-                    best = time;
+                const long long rounds = (ctas + slots - 1) / slots;
+                const double rate = ctas > sm_count ? 870.0 : 1250.0;
+                const int parts = pj * pd;
+                // the second stage reads parts*4+8 bytes and the first writes parts*4 bytes per candidate and track
+                const double split_us = parts > 1 ? 3.0 + 0.05 * parts + 1.5e-5 * (double)n_tracks * Wmax * Hmax * parts : 0.0;
+                const double us = rounds * (3.0 + work / rate) + split_us;
+                const double key = us * (1.0 + 1e-4 * parts) - 1e-6 * GB;
+                if (key < best) {
+                    best = key;
                     *out = TileCfg{G, C, GB, bands, ctas_band, span, boxW, boxH, pj, pd};
                     *smem_out = smem;
                 }
@@ -167,6 +175,14 @@ int upload_params(pvt_ctx* c)
     p.keep_maps = c->params.keep_maps;
     CK(cudaMemcpyAsync(c->d.params, &p, sizeof(p), cudaMemcpyHostToDevice, c->compute));
     CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+int upload_seq(pvt_ctx* c, unsigned long long step0, int ring_len, int row0)
+{
+    SeqDesc q{step0, ring_len, row0};
+    CK(cudaMemcpyAsync(c->d.seq, &q, sizeof(q), cudaMemcpyHostToDevice, c->compute));  // pageable source: staged before return
+    c->seq_default = (step0 == 0 && ring_len == kRing && row0 == 0);
     return PVT_OK;
 }
 
@@ -216,7 +232,7 @@ int prof_begin(pvt_ctx* c, int cls, EventPair** out)
 }
 
 // the kernels of one searched time step, on c->compute (captured into the graph or launched directly)
-int launch_step_kernels(pvt_ctx* c, bool profile)
+int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
 {
     const Ctx& d = c->d;
     EventPair* ep = nullptr;
@@ -227,13 +243,24 @@ int launch_step_kernels(pvt_ctx* c, bool profile)
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_ingest"); if (r) return r; }
 
+    // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
+    // run as two concurrent branches (fork after ingest, join before finalize)
+    const bool ksplit = c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1;
+    const bool fork = capturing && ksplit;
+    cudaStream_t sstats = c->compute;
+    if (fork) {
+        CK(cudaEventRecord(c->ev_fork, c->compute));
+        CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+        sstats = c->aux;
+    }
     if (profile) { int r = prof_begin(c, CLS_STATS, &ep); if (r) return r; }
-    k_colsum<<<dim3((d.VW + 127) / 128, (d.Hmax + kColsumRows - 1) / kColsumRows, d.max_tracks), 128, 0, c->compute>>>(d);
-    { int r = dbg(c, "k_colsum"); if (r) return r; }
+    k_colprefix<<<dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, c->colprefix_chunks), 0, sstats>>>(d);
+    { int r = dbg(c, "k_colprefix"); if (r) return r; }
     k_rowsum<<<dim3((d.Hmax + c->rowsum_warps - 1) / c->rowsum_warps, d.max_tracks), c->rowsum_warps * 32,
-               (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), c->compute>>>(d, c->rowsum_pw);
+               (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), sstats>>>(d, c->rowsum_pw);
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
+    if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
     if (profile) { int r = prof_begin(c, CLS_NCC, &ep); if (r) return r; }
     if (c->params.kernel == PVT_KERNEL_DIRECT) {
@@ -241,15 +268,18 @@ int launch_step_kernels(pvt_ctx* c, bool profile)
     } else {
         const int parts = c->tile.pj * c->tile.pd;
         k_ncc_search<kCY><<<dim3(c->tile.bands * c->tile.ctas_band, d.max_tracks, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
-        if (parts > 1) k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d, parts);
+        if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
+        if (parts > 1) k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, c->tile);
     }
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_ncc"); if (r) return r; }
 
-    if (profile) { int r = prof_begin(c, CLS_UPDATE, &ep); if (r) return r; }
-    k_update<<<d.max_tracks, 256, 0, c->compute>>>(d);
-    if (profile) CK(cudaEventRecord(ep->b, c->compute));
-    { int r = dbg(c, "k_update"); if (r) return r; }
+    if (c->params.kernel == PVT_KERNEL_DIRECT || c->tile.pj * c->tile.pd == 1) {   // otherwise the update ran inside k_ncc_finalize
+        if (profile) { int r = prof_begin(c, CLS_UPDATE, &ep); if (r) return r; }
+        k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
+        if (profile) CK(cudaEventRecord(ep->b, c->compute));
+        { int r = dbg(c, "k_update"); if (r) return r; }
+    }
     CK(cudaGetLastError());
     return PVT_OK;
 }
@@ -260,7 +290,7 @@ int build_graphs(pvt_ctx* c)
     if (c->graph_hold) { cudaGraphExecDestroy(c->graph_hold); c->graph_hold = nullptr; }
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-    int r = launch_step_kernels(c, false);
+    int r = launch_step_kernels(c, false, true);
     cudaError_t e = cudaStreamEndCapture(c->compute, &g);
     if (r) return r;
     CK(e);
@@ -296,6 +326,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
 {
     const int slot = (int)(c->submitted % kRing);
     const int ms = c->cfg.max_streams;
+    if (!c->seq_default) { int r = upload_seq(c, 0, kRing, 0); if (r) return r; }
     FrameDesc* row = c->h_table + (size_t)slot * ms;
     if (c->table_ev_used[slot]) CK(cudaEventSynchronize(c->table_ev[slot]));  // previous upload of this pinned row is done
     for (int s = 0; s < ms; ++s) row[s] = FrameDesc{nullptr, 0, 0, 0};
@@ -339,12 +370,12 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
     } else if (c->profiling || debug_sync()) {
         int r = launch_step_kernels(c, c->profiling);
         if (r) return r;
-        c->launches += 5 + ((c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1) ? 1 : 0);
+        c->launches += 5;
         if (c->profiling) c->prof.steps += 1;
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
-        c->launches += 5 + ((c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1) ? 1 : 0);
+        c->launches += 5;
     }
     if (copied) {
         CK(cudaEventRecord(c->ev_done[sd], c->compute));
@@ -445,6 +476,9 @@ int pvt_destroy(pvt_ctx* c)
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     }
     for (auto& p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux) cudaStreamDestroy(c->aux);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -517,22 +551,27 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
 
     CKD(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
     CKD(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     const size_t win = (size_t)d.Wmax * d.Hmax;
     CR(dev_alloc(c, &d.gray, d.plane * d.max_streams));
     CR(dev_alloc(c, &d.templ, (size_t)d.max_tracks * d.mth * d.mtw));
     CR(dev_alloc(c, &d.templc, (size_t)d.max_tracks * d.mth * d.mtp));
-    CR(dev_alloc(c, &d.vsum, (size_t)d.max_tracks * d.Hmax * d.VW, false));
-    CR(dev_alloc(c, &d.vsq, (size_t)d.max_tracks * d.Hmax * d.VW, false));
+    CR(dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));   // column prefix sums, tileH + 1 rows
+    CR(dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));
     CR(dev_alloc(c, &d.denom, (size_t)d.max_tracks * win, false));
     if (params->keep_maps) CR(dev_alloc(c, &d.maps, (size_t)d.max_tracks * win));
     CR(dev_alloc(c, &d.tracks, (size_t)d.max_tracks));
     CR(dev_alloc(c, &d.table, (size_t)kRing * d.max_streams));
+    CR(dev_alloc(c, &d.seq, 1));
     CR(dev_alloc(c, &d.results, (size_t)kRing * d.max_tracks));
     CR(dev_alloc(c, &d.params, 1));
     CR(dev_alloc(c, &d.step, 1));
     CR(dev_alloc(c, &d.ticket, 1));
     CR(dev_alloc(c, &d.macs, 1));
     c->d_macs = d.macs;
+    CR(dev_alloc(c, &c->d_trace, (size_t)kRing * 16));
     CKD(cudaHostAlloc((void**)&c->h_table, sizeof(FrameDesc) * kRing * d.max_streams, cudaHostAllocDefault));
     CKD(cudaHostAlloc((void**)&c->h_results, sizeof(pvt_result) * kRing * d.max_tracks, cudaHostAllocDefault));
     for (int i = 0; i < kRing; ++i) CKD(cudaEventCreateWithFlags(&c->table_ev[i], cudaEventDisableTiming));
@@ -570,14 +609,25 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu\n", d.max_tracks,
                 c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH, c->tile.pj,
                 c->tile.pd, c->ncc_smem);
-    if (c->tile.pj * c->tile.pd > 1) CR(dev_alloc(c, &d.partial, (size_t)c->tile.pj * c->tile.pd * d.max_tracks * win, false));
+    if (c->tile.pj * c->tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
+        CR(dev_alloc(c, &d.partial, (size_t)c->tile.pj * c->tile.pd * d.max_tracks * c->tile.bands * c->tile.ctas_band * kTilesPerCta * 8 * kCY, false));
     CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
     c->rowsum_pw = d.VW + 8;
     c->rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * c->rowsum_pw * sizeof(double))));
     CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double))));
+    // k_colprefix: ~28 rows per thread (8 chunks for a 224-row tracker tile, up to 32 for full-frame maps)
+    c->colprefix_chunks = std::max(1, std::min(32, (d.Hmax + d.mth - 1 + 27) / 28));
+    c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
+    if (c->templ_smem > 48u * 1024u) {
+        CKD(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+        CKD(cudaFuncSetAttribute(k_ncc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+        CKD(cudaFuncSetAttribute(k_track_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+        CKD(cudaFuncSetAttribute(k_track_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+    }
     CR(encode_tmap(c));
     CR(upload_params(c));
+    CR(upload_seq(c, 0, kRing, 0));
     CKD(cudaDeviceSynchronize());  // the zero-fills above ran on the default stream; kernels use non-blocking streams
 #undef CR
 #undef CKD
@@ -619,6 +669,7 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
     if (r) return r;
     const Ctx& d = c->d;
     // a private table row at the CURRENT device step, then k_ingest alone; the step counter is untouched
+    if (!c->seq_default) { int r2 = upload_seq(c, 0, kRing, 0); if (r2) return r2; }
     const int slot = (int)(c->submitted % kRing);
     std::vector<FrameDesc> row(d.max_streams, FrameDesc{nullptr, 0, 0, 0});
     FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
@@ -666,7 +717,7 @@ int pvt_track_init(pvt_ctx* c, int track, int stream, const pvt_frame* frame0, i
         int r = pvt_sync(c);
         if (r) return r;
     }
-    k_track_init<<<1, 256, 0, c->compute>>>(c->d, track, stream, x, y, w, h);
+    k_track_init<<<1, 256, c->templ_smem, c->compute>>>(c->d, track, stream, x, y, w, h);
     c->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->compute));
@@ -725,6 +776,55 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
     if (n_steps < 0 || n_frames <= 0 || ring_len <= 0 || !frames) return fail(PVT_ERR_INVALID, "bad sequence arguments");
     if (collect_every > kRing) return fail(PVT_ERR_INVALID, "collect_every exceeds the 64-step results ring");
     const int mt = c->cfg.max_tracks;
+    // Resident ring fast path: every frame is device memory and the ring fits the table -> upload the ring's rows and a
+    // SeqDesc ONCE; after that a time step is a bare graph launch (no H2D, no host-side bookkeeping per frame).
+    bool resident = ring_len <= kRing && !c->profiling && !debug_sync() && n_steps > 0;
+    for (int i = 0; resident && i < ring_len * n_frames; ++i) resident = frames[i].memory == PVT_MEM_DEVICE;
+    if (resident) {
+        CK(cudaSetDevice(c->cfg.device));
+        const int ms = c->cfg.max_streams;
+        for (int k = 0; k < kRing; ++k)
+            if (c->table_ev_used[k]) { CK(cudaEventSynchronize(c->table_ev[k])); c->table_ev_used[k] = false; }
+        for (int k = 0; k < ring_len; ++k) {
+            FrameDesc* row = c->h_table + (size_t)k * ms;
+            for (int s = 0; s < ms; ++s) row[s] = FrameDesc{nullptr, 0, 0, 0};
+            for (int i = 0; i < n_frames; ++i) {
+                const pvt_frame* f = frames + (size_t)k * n_frames + i;
+                int r = check_frame(c, f);
+                if (r) return r;
+                if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
+                row[f->stream] = FrameDesc{f->data, (unsigned long long)f->step, f->format, 1};
+            }
+        }
+        CK(cudaMemcpyAsync(c->d.table, c->h_table, sizeof(FrameDesc) * (size_t)ring_len * ms, cudaMemcpyHostToDevice, c->compute));
+        CK(cudaEventRecord(c->table_ev[0], c->compute));
+        c->table_ev_used[0] = true;
+        int r = upload_seq(c, c->submitted, ring_len, 0);
+        if (r) return r;
+        if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }
+        const bool batch = c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1;
+        for (int s = 0; s < n_steps; ++s) {
+            bool hold = false;
+            if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
+            CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
+            c->launches += hold ? 1 : 5;
+            c->submitted += 1;
+            if (collect_every > 0 && (s + 1) % collect_every == 0) {
+                const unsigned long long first = c->submitted - collect_every;
+                for (int k = 0; k < collect_every; ++k) {
+                    const int slot = (int)((first + k) % kRing);
+                    CK(cudaMemcpyAsync(c->h_results + (size_t)slot * mt, c->d.results + (size_t)slot * mt, sizeof(pvt_result) * mt,
+                                       cudaMemcpyDeviceToHost, c->compute));
+                }
+                CK(cudaStreamSynchronize(c->compute));
+                if (results_out)
+                    for (int k = 0; k < collect_every; ++k)
+                        std::memcpy(results_out + (size_t)(s + 1 - collect_every + k) * mt, c->h_results + (size_t)((first + k) % kRing) * mt,
+                                    sizeof(pvt_result) * mt);
+            }
+        }
+        return PVT_OK;
+    }
     for (int s = 0; s < n_steps; ++s) {
         int r = pvt_submit(c, n_frames, frames + (size_t)(s % ring_len) * n_frames);
         if (r) return r;
@@ -805,7 +905,7 @@ int pvt_set_state(pvt_ctx* c, int track, const int32_t bbox[4], const float* tem
         CK(cudaMemcpy2DAsync(c->d.templ + (size_t)track * c->d.mth * c->d.mtw, (size_t)w * 4, templ, templ_step_bytes, (size_t)w * 4, h,
                              cudaMemcpyHostToDevice, c->compute));
     }
-    k_track_refresh<<<1, 256, 0, c->compute>>>(c->d, track);
+    k_track_refresh<<<1, 256, c->templ_smem, c->compute>>>(c->d, track);
     c->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->compute));
@@ -937,6 +1037,35 @@ int pvt_profile_get(pvt_ctx* c, pvt_profile* out, int reset)
         CK(cudaStreamSynchronize(c->compute));
     }
     return PVT_OK;
+}
+
+int pvt_trace_enable(pvt_ctx* c, int on)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    c->d.trace = on ? c->d_trace : nullptr;
+    c->graph_valid = false;  // kernel arguments are baked into the graph
+    CK(cudaMemsetAsync(c->d_trace, 0, sizeof(unsigned long long) * kRing * 16, c->compute));
+    CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+int pvt_trace_get(pvt_ctx* c, uint64_t* out, int max_steps)
+{
+    if (!c || !out) return fail(PVT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    const int n = (int)std::min<unsigned long long>(std::min<unsigned long long>(c->submitted, (unsigned long long)std::max(max_steps, 0)), kRing);
+    std::vector<unsigned long long> h((size_t)kRing * 16);
+    CK(cudaMemcpy(h.data(), c->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long s = c->submitted - n + i;
+        std::memcpy(out + (size_t)i * 16, h.data() + (size_t)(s % kRing) * 16, 16 * sizeof(unsigned long long));
+    }
+    return n;
 }
 
 int64_t pvt_launch_count(pvt_ctx* c) { return c ? c->launches : 0; }

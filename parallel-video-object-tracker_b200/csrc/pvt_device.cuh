@@ -5,7 +5,7 @@
 //   gray     [max_streams][H][pitch]  f32   toGrayF32 image of each stream's current frame (TMA source)
 //   templ    [max_tracks][mth*mtw]    f32   the tracker's template, exactly the reference's templ_gray_f32
 //   templc   [max_tracks][mth*mtp]    f32   fl32(templ - mean_t), chunk-major [x/8][y][x%8], columns zero-padded to 8
-//   vsum/vsq [max_tracks][Hmax][VW]   f64   vertical box sums of f and f^2 over th rows (scratch)
+//   vsum/vsq [max_tracks][Hmax+mth][VW] f64 column prefix sums of f and f^2 over the search tile (scratch)
 //   denom    [max_tracks][Hmax*Wmax]  f64   OpenCV's normaliser t = sqrt(diff2)*sigma_t*sqrt(N), 0 when flat
 //   maps     [max_tracks][Hmax*Wmax]  f32   optional (keep_maps)
 //   tracks   [max_tracks]             TrackState
@@ -23,13 +23,19 @@ namespace pvt {
 constexpr int kRing = 64;      // time steps that may be in flight
 constexpr int kCX = 8;         // candidates per thread along x (contiguous)
 constexpr int kCY = 5;         // candidates per thread along y (adjacent rows; odd => conflict-free LDS.128)
-constexpr int kColsumRows = 16;  // candidate rows per thread in the vertical box-sum kernel
 
 struct FrameDesc {
     const void* data;
     unsigned long long step;
     int format;
     int valid;
+};
+
+// which frame-table row a time step reads: row0 + (step - step0) % ring_len.  Default {0, kRing, 0} = step % kRing
+// (one row uploaded per step); a resident frame ring uploads its rows once and every later step needs no H2D at all.
+struct SeqDesc {
+    unsigned long long step0;
+    int ring_len, row0;
 };
 
 struct TrackState {
@@ -40,7 +46,8 @@ struct TrackState {
     double mean, templ_norm;   // mean_t, sigma_t * sqrt(N)
     unsigned long long peak;   // packed (ordered score << 32 | ~index); 0 = empty
     int win[4];                // minTx, minTy, width, height of the current search window
-    int pad[2];
+    unsigned int ticket;       // CTAs of k_ncc_finalize that are done with this track (last one runs the update)
+    int pad;
 };
 
 struct DevParams {
@@ -64,14 +71,16 @@ struct Ctx {
     double* vsq;
     double* denom;
     float* maps;
-    float* partial;            // [parts][max_tracks][Hmax*Wmax] K-split partial cross terms (latency mode)
+    float* partial;            // [parts][max_tracks][tiles][8*kCY] K-split partial cross terms, tile-major
     TrackState* tracks;
     FrameDesc* table;
+    SeqDesc* seq;
     pvt_result* results;
     DevParams* params;
     unsigned long long* step;  // device-side time-step counter (advanced by the update kernel)
-    unsigned int* ticket;      // last-block-done counter of the update kernel
+    unsigned int* ticket;      // tracks whose update is done in this step (the last one advances the step counter)
     unsigned long long* macs;  // algorithmic MACs searched so far (n_cand * tw * th per track per step)
+    unsigned long long* trace; // optional [kRing][8 kernels][2] globaltimer stamps (first CTA start, last CTA end); NULL = off
 };
 
 // tracker/src/main.cpp:135-146, same int arithmetic (all operands >= 0, so / truncates like C)
@@ -85,10 +94,15 @@ __host__ __device__ inline void search_window(int x, int y, int w, int h, int ou
     win[0] = minTx; win[1] = minTy; win[2] = maxTx - minTx + 1; win[3] = maxTy - minTy + 1;
 }
 
+__device__ __forceinline__ size_t table_row(const Ctx& c, unsigned long long step)
+{
+    const SeqDesc q = *c.seq;
+    return (size_t)(q.row0 + (int)((step - q.step0) % (unsigned long long)q.ring_len)) * c.max_streams;
+}
 __device__ __forceinline__ bool track_stepped(const Ctx& c, const TrackState& t, unsigned long long step)
 {
     if (!t.active) return false;
-    return c.table[(step % kRing) * c.max_streams + t.stream].valid != 0;
+    return c.table[table_row(c, step) + t.stream].valid != 0;
 }
 
 // monotone float -> uint map (larger float <=> larger uint); -0 is folded into +0 first so that it
@@ -107,6 +121,24 @@ __device__ __forceinline__ float unord_f32(unsigned int o)
 __device__ __forceinline__ unsigned long long peak_key(float v, unsigned int idx)
 {
     return ((unsigned long long)ord_f32(v) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// ---- optional device-side timeline (pvt_trace_enable): first-CTA start and last-CTA end of every kernel, per step
+enum { TR_INGEST = 0, TR_COLPREFIX = 1, TR_ROWSUM = 2, TR_NCC = 3, TR_FINALIZE = 4, TR_UPDATE = 5 };
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(const Ctx& c, unsigned long long step, int k)
+{
+    if (c.trace && threadIdx.x == 0 && threadIdx.y == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        c.trace[((step % kRing) * 8 + k) * 2] = gtime();
+}
+__device__ __forceinline__ void trace_end(const Ctx& c, unsigned long long step, int k)
+{
+    if (c.trace && threadIdx.x == 0 && threadIdx.y == 0) atomicMax(&c.trace[((step % kRing) * 8 + k) * 2 + 1], gtime());
 }
 
 // ---- PTX helpers: mbarrier, TMA tensor load, bulk copy -------------------------------------

@@ -159,7 +159,7 @@ def test_window_map(name, k):
             tr.set_state(0, (int(bbox[0]), int(bbox[1]), roi[2], roi[3]), templ)
             tr.step([frames[k]])
             m2, _ = tr.window_map(0)
-            assert np.abs(m - m2).max() <= 1e-5 and np.argmax(m) == np.argmax(m2)
+            assert np.abs(m - m2).max() <= 5e-5 and np.argmax(m) == np.argmax(m2)
     assert win == tuple(int(v) for v in g[f"map{k}_win"])
     off, on = g[f"map{k}_ipp_off"], g[f"map{k}_ipp_on"]
     gray = O.to_gray_f32(frames[k])
@@ -207,9 +207,13 @@ def test_multi_stream_multi_track_matches_single_runs():
         for k in range(1, n):
             out.append(tr.step([c["frames"][k] for c in clips]))
     out = np.array(out)
+    def same(a, b):   # boxes and flags identical; scores up to the summation order (contexts of different size plan
+        # the template split differently, which regroups the FP32 partial sums)
+        return np.array_equal(a[:, [0, 1, 2, 3, 5, 6]], b[:, [0, 1, 2, 3, 5, 6]]) and np.abs(a[:, 4] - b[:, 4]).max() <= 2e-6
     for i in range(3):
-        assert np.array_equal(records_of(out[:, i]), singles[i])
-    assert np.array_equal(records_of(out[:, 4]), singles[0])           # same ROI, same stream -> same trajectory
+        assert same(records_of(out[:, i]), singles[i])
+    assert np.array_equal(records_of(out[:, 4]), records_of(out[:, 0]))   # same ROI, same stream, same context -> bit-identical
+    assert same(records_of(out[:, 4]), singles[0])
     assert np.all(out[:, 3]["valid"] == 1)
     # a stream that gets no frame in a step is not stepped
     with pvt.Tracker(W, H, 32, 32, max_streams=2, max_tracks=2) as tr:
@@ -229,7 +233,7 @@ def test_async_submit_collect_equals_step():
         tr.init_track(0, frames[0], roi)
         keep = [tr.submit([frames[k]]) for k in range(1, len(frames))]
         got = tr.collect(len(frames) - 1)
-        assert tr.launch_count() >= 5 * (len(frames) - 1)
+        assert tr.launch_count() >= 4 * (len(frames) - 1)
     assert np.array_equal(records_of(got[:, 0]), want)
     assert list(got[:, 0]["step"]) == list(range(len(frames) - 1))
 

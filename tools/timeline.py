@@ -1,0 +1,37 @@
+"""Measurement tool: warm device-side timeline of one workload's step (globaltimer stamps, no profiler attached)."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+pvt = importlib.import_module("parallel-video-object-tracker_b200")
+wname = sys.argv[1] if len(sys.argv) > 1 else "C2"
+wl = dict(bench.WORKLOADS[wname])
+W, H, tw, th, R, L, S = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], wl["ring"], wl["streams"]
+scenes, host, dev = bench.build_rings(wl, 0, torch)
+ring = bench.ring_descs(pvt, wl, dev, True)
+tr = pvt.Tracker(W, H, tw, th, max_streams=S, max_tracks=S * wl["rois"], search_radius_x=R, search_radius_y=R)
+t = 0
+for s in range(S):
+    for j, roi in enumerate(bench.rois_for(wl, scenes[s % len(scenes)])):
+        tr.init_track(t, pvt.device_frame(dev[s, 0].data_ptr(), W * 3, stream=s) if j == 0 else None, roi, stream=s); t += 1
+sh = lambda st: ring[st % L:] + ring[:st % L]
+tr.trace_enable(True)
+tr.submit_sequence(64, sh(1)); tr.sync()
+tr.timer_start(); tr.submit_sequence(64, sh(65)); ms = tr.timer_stop()
+T = tr.trace_get(64).astype(np.int64)
+names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update"]
+T = T[8:]                                     # skip the first steps
+t0 = T[:, 0, 0:1]
+print("%s: %.2f us/step (events); step-to-step %.2f us (trace)" % (wname, 1e3 * ms / 64, np.median(np.diff(T[:, 0, 0])) / 1e3))
+prev_end = None
+for k, nm in enumerate(names):
+    if not T[:, k, 0].any(): continue
+    st = np.median(T[:, k, 0] - T[:, 0, 0]) / 1e3; en = np.median(T[:, k, 1] - T[:, 0, 0]) / 1e3
+    print("  %-13s start %7.2f  end %7.2f  dur %6.2f us  gap-before %6.2f" % (nm, st, en, en - st, st - prev_end if prev_end is not None else 0.0))
+    prev_end = en
+if T[:, 6, 0].any():
+    b = T[:, 3, 0]
+    print("  ncc_search CTA(0,0,0): issue-done +%.2f  tile-arrived +%.2f  compute-done +%.2f  epilogue-done +%.2f us (from kernel start)" % tuple(
+        np.median(x - b) / 1e3 for x in (T[:, 6, 0], T[:, 6, 1], T[:, 7, 0], T[:, 7, 1])))
+nxt = np.median(T[1:, 0, 0] - T[:-1, 5, 1]) / 1e3
+print("  gap to next step's ingest: %.2f us" % nxt)
