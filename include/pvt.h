@@ -67,6 +67,12 @@ typedef enum pvt_kernel {
     PVT_KERNEL_TILED = 2
 } pvt_kernel;
 
+/* frame ingest (utils.hpp:5-14 toGrayF32).  FULL converts whole frames, as the reference does.  ROI converts only each
+ * track's search tile (window + template extent; the only pixels the path ever reads) with the window origin taken from
+ * device state; pinned host frames are then read zero-copy over PCIe instead of being copied whole.  Results are
+ * identical.  AUTO picks ROI when the tiles of a context cover less than half of its frames' area. */
+typedef enum pvt_ingest { PVT_INGEST_AUTO = 0, PVT_INGEST_FULL = 1, PVT_INGEST_ROI = 2 } pvt_ingest;
+
 typedef enum pvt_format { PVT_FMT_BGR8 = 0, PVT_FMT_GRAY8 = 1, PVT_FMT_GRAYF32 = 2 } pvt_format;
 typedef enum pvt_memory { PVT_MEM_HOST = 0, PVT_MEM_DEVICE = 1 } pvt_memory;
 
@@ -81,7 +87,8 @@ typedef struct pvt_params {
     int mode;                     /* pvt_mode */
     int kernel;                   /* pvt_kernel */
     int keep_maps;                /* != 0: keep every track's last window map for pvt_get_window_map (tests) */
-    int reserved[4];
+    int ingest;                   /* pvt_ingest */
+    int reserved[3];
 } pvt_params;
 
 typedef struct pvt_config {

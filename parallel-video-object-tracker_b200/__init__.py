@@ -28,6 +28,7 @@ MODE_NAIVE, MODE_CPU, MODE_SHARED, MODE_CONST, MODE_CONST_TILED, MODE_BATCH = ra
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TILED = range(3)
 FMT_BGR8, FMT_GRAY8, FMT_GRAYF32 = range(3)
 MEM_HOST, MEM_DEVICE = range(2)
+INGEST_AUTO, INGEST_FULL, INGEST_ROI = range(3)
 
 # every symbol include/pvt.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
@@ -43,7 +44,7 @@ class Params(C.Structure):
     _fields_ = [("search_radius_x", C.c_int), ("search_radius_y", C.c_int),
                 ("ncc_min_confidence", C.c_double), ("ncc_strong_confidence", C.c_double),
                 ("template_update_lr", C.c_double), ("batch_size", C.c_int), ("mode", C.c_int),
-                ("kernel", C.c_int), ("keep_maps", C.c_int), ("reserved", C.c_int * 4)]
+                ("kernel", C.c_int), ("keep_maps", C.c_int), ("ingest", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Config(C.Structure):

@@ -27,20 +27,9 @@ __device__ __forceinline__ unsigned int bgr_to_gray(unsigned int b, unsigned int
     return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
 }
 
-__global__ void __launch_bounds__(256) k_ingest(Ctx c)
+// 4 consecutive pixels of one source row -> 4 toGrayF32 values (n < 4 at the right frame edge)
+__device__ __forceinline__ float4 ingest_group(const FrameDesc& d, const unsigned char* row, int x, int n)
 {
-    const unsigned long long step = *c.step;
-    const int stream = blockIdx.y;
-    const FrameDesc d = c.table[table_row(c, step) + stream];
-    if (!d.valid) return;
-    trace_begin(c, step, TR_INGEST);
-    const int gpr = (c.W + 3) >> 2;  // 4-pixel groups per row
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)gpr * c.H) return;
-    const int y = (int)(gid / gpr), x = ((int)(gid - (long long)y * gpr)) << 2;
-    float* out = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch + x;
-    const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
-    const int n = min(4, c.W - x);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d.format == PVT_FMT_BGR8) {
         const unsigned char* p = row + 3 * x;
@@ -68,7 +57,50 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
         for (int i = 0; i < n; ++i) v[i] = p[i];
         o = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4*>(out) = o;  // pitch is a multiple of 4 floats: always in bounds, 16-byte aligned
+    return o;
+}
+
+__global__ void __launch_bounds__(256) k_ingest(Ctx c)
+{
+    const unsigned long long step = *c.step;
+    const int stream = blockIdx.y;
+    const FrameDesc d = c.table[table_row(c, step) + stream];
+    if (!d.valid) return;
+    trace_begin(c, step, TR_INGEST);
+    const int gpr = (c.W + 3) >> 2;  // 4-pixel groups per row
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * c.H) return;
+    const int y = (int)(gid / gpr), x = ((int)(gid - (long long)y * gpr)) << 2;
+    float* out = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch + x;
+    const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
+    *reinterpret_cast<float4*>(out) = ingest_group(d, row, x, min(4, c.W - x));  // pitch % 4 == 0: in bounds, 16-byte aligned
+    trace_end(c, step, TR_INGEST);
+}
+
+// ROI ingest: one track's search tile only (window + template extent, origin from device state).  The source may be a
+// device buffer or PINNED HOST memory read directly over PCIe (zero-copy): ~150 KB per track and step for a 1080p /
+// 64x64 / R80 track instead of a 6.2 MB frame.  Pixels outside the tiles keep older (finite) values; nothing on the
+// path reads them: every consumer (k_colprefix, the TMA tile's useful part, the EMA patch) stays inside the tile.
+__global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
+{
+    const int track = blockIdx.y;
+    const TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!t.active) return;
+    const FrameDesc d = c.table[table_row(c, step) + t.stream];
+    if (!d.valid) return;
+    trace_begin(c, step, TR_INGEST);
+    const DevParams P = *c.params;
+    int win[4];
+    search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    const int x0 = win[0] & ~3, x1 = min(c.W, win[0] + win[2] + t.w - 1), rows = win[3] + t.h - 1;
+    const int gpr = (x1 - x0 + 3) >> 2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= gpr * rows) return;
+    const int r = gid / gpr, x = x0 + ((gid - r * gpr) << 2), y = win[1] + r;
+    float* out = c.gray + (size_t)t.stream * c.plane + (size_t)y * c.pitch + x;
+    const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
+    *reinterpret_cast<float4*>(out) = ingest_group(d, row, x, min(4, c.W - x));
     trace_end(c, step, TR_INGEST);
 }
 
@@ -316,13 +348,25 @@ struct TileCfg {
     int span;            // columns one CTA's 128 tiles can touch
     int boxW, boxH;      // TMA box == shared tile [boxH][boxW]
     int pj, pd;          // K-split: parts along template chunks and along template rows (pj * pd = grid.z)
+    // 1-D item grid: item = track * cpt + CTA-in-track.  Tail splitting (only when pj * pd == 1): the items of the last,
+    // partial round (item >= n_full) are cut into tail_ps parts along the template chunks, so that round costs
+    // 1/tail_ps of a full one; their partial sums are reduced per item by k_ncc_tail_finalize.
+    int cpt, n_full, n_tail, tail_ps;
 };
 
 template <int CY>
 __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char sm_raw[];
-    const int track = blockIdx.y;
+    int item = blockIdx.x, part = blockIdx.z, pj = g.pj, pd = g.pd, tail_k = -1;
+    if (g.tail_ps > 1 && item >= g.n_full) {           // a part of a tail item
+        tail_k = item - g.n_full;
+        item = g.n_full + tail_k / g.tail_ps;
+        part = tail_k - (tail_k / g.tail_ps) * g.tail_ps;
+        pj = g.tail_ps;
+        pd = 1;
+    }
+    const int track = item / g.cpt, blk = item - track * g.cpt;
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
@@ -339,17 +383,18 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     // the TMA tile must start on a 16-byte boundary in x: the column grid starts at the window origin rounded
     // DOWN to a multiple of 4 pixels; the xs (0..3) grid columns in front of the window are masked
     const int xs = win[0] & 3;
-    const int band = blockIdx.x / g.ctas_band, q0 = (blockIdx.x - band * g.ctas_band) * kTilesPerCta;
+    const int band = blk / g.ctas_band, q0 = (blk - band * g.ctas_band) * kTilesPerCta;
     const int c_lo = q0 / g.GB;
     const int row0 = band * g.GB * CY;  // first candidate row of this band
     if (c_lo * 8 >= xs + ww || row0 >= wh) return;
 
     // K-split part -> template chunk range [j0, j1) and row range [d0, d1)
-    const int part = blockIdx.z, pjx = part % g.pj, pdx = part / g.pj;
-    const int j0 = (nchunk * pjx) / g.pj;
-    const int d0 = (th * pdx) / g.pd, d1 = (th * (pdx + 1)) / g.pd;
+    const int pjx = part % pj, pdx = part / pj;
+    const int j0 = (nchunk * pjx) / pj;
+    const int d0 = (th * pdx) / pd, d1 = (th * (pdx + 1)) / pd;
     const int nd = d1 - d0;
-    const int j1 = nd > 0 ? (nchunk * (pjx + 1)) / g.pj : j0;
+    const int j1 = nd > 0 ? (nchunk * (pjx + 1)) / pj : j0;
+    const bool split = pj * pd > 1;
 
     constexpr int kRingT = 4;  // template slices in flight (full/empty mbarrier ring; no CTA-wide sync in the loop)
     float* s_tile = reinterpret_cast<float*>(sm_raw);
@@ -461,12 +506,13 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     unsigned long long key = 0ull;
     if (active) {
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;
-        if (g.pj * g.pd > 1) {
+        if (split) {
             // K-split: store the partial sums TILE-MAJOR (this thread's 8 x CY values contiguous: coalesced float4
             // stores, no write amplification); k_ncc_finalize adds the parts in order and normalises
-            const size_t tiles_track = (size_t)g.bands * g.ctas_band * kTilesPerCta;
-            float4* po = reinterpret_cast<float4*>(c.partial + (((size_t)part * c.max_tracks + track) * tiles_track +
-                                                                (size_t)blockIdx.x * kTilesPerCta + threadIdx.x) * (8 * CY));
+            const size_t tiles_track = (size_t)g.cpt * kTilesPerCta;
+            float4* po = reinterpret_cast<float4*>(
+                c.partial + (tail_k >= 0 ? ((size_t)tail_k * kTilesPerCta + threadIdx.x)
+                                         : (((size_t)part * c.max_tracks + track) * tiles_track + (size_t)blk * kTilesPerCta + threadIdx.x)) * (8 * CY));
 #pragma unroll
             for (int i = 0; i < CY; ++i) {
                 po[2 * i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -502,7 +548,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
             }
         }
     }
-    if (g.pj * g.pd == 1) {
+    if (!split) {
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
             unsigned long long o = shfl_xor_u64(key, m);
@@ -512,6 +558,73 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     }
     if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 7) * 2 + 1] = gtime();
     trace_end(c, step, TR_NCC);
+}
+
+// Tail items' second stage (throughput mode): one CTA per tail item, thread = thread tile of k_ncc_search; adds the
+// tail_ps partial sums of its 8 x CY candidates in part order, then the same FP64 normalisation / peak epilogue.
+template <int CY>
+__global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileCfg g)
+{
+    const int item = g.n_full + blockIdx.x;
+    const int track = item / g.cpt, blk = item - track * g.cpt;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    const int ww = t.win[2], wh = t.win[3], xs = t.win[0] & 3;
+    const int band = blk / g.ctas_band, q = (blk - band * g.ctas_band) * kTilesPerCta + threadIdx.x;
+    const int col = q / g.GB, grp = band * g.GB + (q - col * g.GB);
+    unsigned long long key = 0ull;
+    if (col < g.C && col * 8 < xs + ww && grp * CY < wh) {
+        float acc[CY][8];
+#pragma unroll
+        for (int i = 0; i < CY; ++i)
+#pragma unroll
+            for (int cx = 0; cx < 8; ++cx) acc[i][cx] = 0.f;
+        for (int p = 0; p < g.tail_ps; ++p) {
+            const float4* pi = reinterpret_cast<const float4*>(c.partial + (((size_t)blockIdx.x * g.tail_ps + p) * kTilesPerCta + threadIdx.x) * (8 * CY));
+            float4 v[2 * CY];
+#pragma unroll
+            for (int i = 0; i < 2 * CY; ++i) v[i] = __ldg(pi + i);
+#pragma unroll
+            for (int i = 0; i < CY; ++i) {
+                acc[i][0] += v[2 * i].x; acc[i][1] += v[2 * i].y; acc[i][2] += v[2 * i].z; acc[i][3] += v[2 * i].w;
+                acc[i][4] += v[2 * i + 1].x; acc[i][5] += v[2 * i + 1].y; acc[i][6] += v[2 * i + 1].z; acc[i][7] += v[2 * i + 1].w;
+            }
+        }
+        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+        const double* dn = c.denom + woff;
+        float* mp = c.params->keep_maps ? c.maps + woff : nullptr;
+        const int flat = t.flat;
+#pragma unroll
+        for (int i = 0; i < CY; ++i) {
+            const int y = grp * CY + i;
+            if (y < wh) {
+                double d8[8];
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) {
+                    const int x = col * 8 + cx - xs;
+                    d8[cx] = (x >= 0 && x < ww) ? __ldg(dn + y * ww + x) : 0.0;
+                }
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) {
+                    const int x = col * 8 + cx - xs;
+                    if (x >= 0 && x < ww) {
+                        const unsigned int idx = (unsigned int)(y * ww + x);
+                        const float v = ncc_finalize(acc[i][cx], d8[cx], flat);
+                        if (mp) mp[idx] = v;
+                        const unsigned long long k = peak_key(v, idx);
+                        key = k > key ? k : key;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(key, m);
+        key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
 }
 
 // K-split second stage: add the parts' partial sums in part order, normalise, pick the peak.

@@ -58,6 +58,8 @@ struct pvt_ctx {
     CUtensorMap tmap{};
     size_t ncc_smem = 0;
     int rowsum_warps = 8, rowsum_pw = 0;
+    int kps = 5;               // kernels per searched time step (for pvt_launch_count)
+    bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr;   // aux: second branch inside the captured graph
@@ -114,8 +116,17 @@ bool choose_plan(int sm_count, int n_tracks, int mtp, int mth, int Wmax, int Hma
     const int G = (Hmax + CY - 1) / CY, C = (Wmax + 3 + 7) / 8, nch = mtp / 8;
     const long long slots = (long long)sm_count * 2;
     double best = 1e300;
-    for (int pj = 1; pj <= nch; ++pj)
-        for (int pd = 1; pd <= mth && pd <= 32; ++pd) {
+    // does the unsplit plan exist and fill at least one whole round?  then never K-split globally: the partial round at
+    // the end is handled by tail splitting (pvt_create), which has none of the K-split's traffic
+    bool unsplit_fills = false;
+    {
+        const int boxH = G * CY + mth - 1, span = std::min(C, (kTilesPerCta - 1) / G + 2), boxW = 8 * span + mtp + 4;
+        const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
+        const long long ctas = (long long)n_tracks * ((G * C + kTilesPerCta - 1) / kTilesPerCta);
+        unsplit_fills = boxH <= 256 && boxW <= 256 && 2 * (smem + 1024) <= 228u * 1024u && ctas >= slots;
+    }
+    for (int pj = 1; pj <= (unsplit_fills ? 1 : nch); ++pj)
+        for (int pd = 1; pd <= (unsplit_fills ? 1 : std::min(mth, 32)); ++pd) {
             const int nchp = (nch + pj - 1) / pj, ndp = (mth + pd - 1) / pd;
             if ((pj > 1 && (pj - 1) * nchp >= nch) || (pd > 1 && (pd - 1) * ndp >= mth)) continue;  // a part would be empty
             for (int GB = G; GB >= 1; --GB) {
@@ -138,7 +149,7 @@ bool choose_plan(int sm_count, int n_tracks, int mtp, int mth, int Wmax, int Hma
                 const double key = us * (1.0 + 1e-4 * parts) - 1e-6 * GB;
                 if (key < best) {
                     best = key;
-                    *out = TileCfg{G, C, GB, bands, ctas_band, span, boxW, boxH, pj, pd};
+                    *out = TileCfg{G, C, GB, bands, ctas_band, span, boxW, boxH, pj, pd, bands * ctas_band, 0, 0, 0};
                     *smem_out = smem;
                 }
             }
@@ -193,6 +204,7 @@ int validate_params(const pvt_params* p)
         return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path (the CPU oracle lives in oracle/, test-only)");
     if (p->mode < PVT_MODE_NAIVE || p->mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
     if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TILED) return fail(PVT_ERR_INVALID, "unknown kernel variant");
+    if (p->ingest < PVT_INGEST_AUTO || p->ingest > PVT_INGEST_ROI) return fail(PVT_ERR_INVALID, "unknown ingest mode");
     if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
     if (!(p->template_update_lr >= 0.0 && p->template_update_lr <= 1.0)) return fail(PVT_ERR_INVALID, "template_update_lr outside [0,1]");
@@ -239,7 +251,12 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
     const int gpr = (d.W + 3) / 4;
     const long long groups = (long long)gpr * d.H;
     if (profile) { int r = prof_begin(c, CLS_INGEST, &ep); if (r) return r; }
-    k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+    if (c->roi_ingest) {
+        const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
+        k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
+    } else {
+        k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+    }
     if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_ingest"); if (r) return r; }
 
@@ -267,7 +284,9 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
         const int parts = c->tile.pj * c->tile.pd;
-        k_ncc_search<kCY><<<dim3(c->tile.bands * c->tile.ctas_band, d.max_tracks, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        const unsigned nbx = (unsigned)(c->tile.n_full + c->tile.n_tail * std::max(c->tile.tail_ps, 1));
+        k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        if (c->tile.tail_ps > 1) k_ncc_tail_finalize<kCY><<<c->tile.n_tail, kTilesPerCta, 0, c->compute>>>(d, c->tile);
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
         if (parts > 1) k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, c->tile);
     }
@@ -339,7 +358,19 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             if (r) return r;
             if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
             FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
-            if (f->memory == PVT_MEM_HOST) {
+            bool zero_copy = false;
+            if (f->memory == PVT_MEM_HOST && c->roi_ingest) {
+                // pinned (cudaHostAlloc / cudaHostRegister) memory is readable from the device under UVA: let k_ingest_roi
+                // pull just the search tiles over PCIe; pageable memory falls back to the staged full-frame copy
+                cudaPointerAttributes pa{};
+                if (cudaPointerGetAttributes(&pa, f->data) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+                    fd.data = pa.devicePointer;
+                    zero_copy = true;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            if (f->memory == PVT_MEM_HOST && !zero_copy) {
                 void*& st = c->stage[(size_t)f->stream * kStageDepth + sd];
                 if (!st) {
                     CK(cudaMalloc(&st, c->stage_bytes));
@@ -353,7 +384,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
                 fd.step = rb;
             }
             row[f->stream] = fd;
-            c->prof.ingest_bytes += c->profiling ? (double)c->cfg.frame_w * c->cfg.frame_h * ((f->format == PVT_FMT_BGR8 ? 3 : f->format == PVT_FMT_GRAY8 ? 1 : 4) + 4) : 0.0;
+            c->prof.ingest_bytes += (c->profiling && !c->roi_ingest) ? (double)c->cfg.frame_w * c->cfg.frame_h * ((f->format == PVT_FMT_BGR8 ? 3 : f->format == PVT_FMT_GRAY8 ? 1 : 4) + 4) : 0.0;
         }
     }
     if (copied) {
@@ -370,12 +401,12 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
     } else if (c->profiling || debug_sync()) {
         int r = launch_step_kernels(c, c->profiling);
         if (r) return r;
-        c->launches += 5;
+        c->launches += c->kps;
         if (c->profiling) c->prof.steps += 1;
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
-        c->launches += 5;
+        c->launches += c->kps;
     }
     if (copied) {
         CK(cudaEventRecord(c->ev_done[sd], c->compute));
@@ -605,10 +636,32 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
             }
         }
     }
+    {   // item grid + tail splitting (see TileCfg)
+        TileCfg& g = c->tile;
+        g.cpt = g.bands * g.ctas_band;
+        const long long items = (long long)d.max_tracks * g.cpt, slots = (long long)prop.multiProcessorCount * 2;
+        g.n_full = (int)items; g.n_tail = 0; g.tail_ps = 0;
+        const char* no_tail = getenv("PVT_NO_TAIL_SPLIT");
+        if (g.pj * g.pd == 1 && items > slots && !(no_tail && *no_tail == '1')) {
+            const long long rem = items % slots;
+            const int nch = d.mtp / 8;
+            const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
+            if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) {
+                g.n_tail = (int)rem; g.n_full = (int)(items - rem); g.tail_ps = ps;
+            }
+        }
+    }
+    {
+        const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
+        c->roi_ingest = params->ingest == PVT_INGEST_ROI || (params->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
+    }
+    c->kps = 4 + ((c->tile.pj * c->tile.pd > 1) ? 1 : (c->tile.tail_ps > 1 ? 2 : 1));  // ingest, 2 stats, search, [tail] + update | finalize
     if (getenv("PVT_DEBUG_PLAN"))
-        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu\n", d.max_tracks,
-                c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH, c->tile.pj,
-                c->tile.pd, c->ncc_smem);
+        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu | items full=%d tail=%d x%d\n",
+                d.max_tracks, c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH,
+                c->tile.pj, c->tile.pd, c->ncc_smem, c->tile.n_full, c->tile.n_tail, c->tile.tail_ps);
+    if (c->tile.tail_ps > 1)           // tail items' partial cross terms: [tail part][128 tiles][8 * kCY]
+        CR(dev_alloc(c, &d.partial, (size_t)c->tile.n_tail * c->tile.tail_ps * kTilesPerCta * 8 * kCY, false));
     if (c->tile.pj * c->tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
         CR(dev_alloc(c, &d.partial, (size_t)c->tile.pj * c->tile.pd * d.max_tracks * c->tile.bands * c->tile.ctas_band * kTilesPerCta * 8 * kCY, false));
     CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
@@ -645,7 +698,12 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
     if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->compute));
-    const bool regraph = p->kernel != c->params.kernel;
+    const bool regraph = p->kernel != c->params.kernel || p->ingest != c->params.ingest;
+    {
+        const Ctx& d = c->d;
+        const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
+        c->roi_ingest = p->ingest == PVT_INGEST_ROI || (p->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
+    }
     c->params = *p;
     if (regraph) c->graph_valid = false;
     return upload_params(c);
@@ -807,7 +865,7 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             bool hold = false;
             if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
             CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
-            c->launches += hold ? 1 : 5;
+            c->launches += hold ? 1 : c->kps;
             c->submitted += 1;
             if (collect_every > 0 && (s + 1) % collect_every == 0) {
                 const unsigned long long first = c->submitted - collect_every;

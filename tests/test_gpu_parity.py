@@ -279,7 +279,7 @@ def test_state_roundtrip_and_errors():
         tr.step([frames[1]])
         bbox, templ = tr.get_state(0)
         a = tr.step([frames[2]])[0]
-    with pvt.Tracker(W, H, 32, 32) as tr2:
+    with pvt.Tracker(W, H, 32, 32, max_tracks=2) as tr2:   # same context shape -> same plan -> bit-identical scores
         tr2.init_track(0, frames[0], roi)
         tr2.set_state(0, bbox, templ)
         b = tr2.step([frames[2]])[0]
@@ -309,3 +309,24 @@ def test_full_size_properties(W, H, tw, th, R):
             f1[max(dy, 0):H + min(dy, 0), max(dx, 0):W + min(dx, 0)] = f0[max(-dy, 0):H - max(dy, 0), max(-dx, 0):W - max(dx, 0)]
             r = tr.step([f1])[0]
             assert (r["x"], r["y"]) == (x + dx, y + dy) and r["conf"] > 0.99
+
+
+# ---- ingest modes: whole frames (the reference's toGrayF32) vs search tiles only, incl. zero-copy pinned host frames
+@pytest.mark.parametrize("name", ["small", "border", "lost"])
+def test_roi_ingest_equals_full_ingest(name):
+    (c, tk) = Hp.clip(name)
+    frames, roi = c["frames"], c["roi"]
+    full = run_clip(frames, roi, ingest=pvt.INGEST_FULL)
+    part = run_clip(frames, roi, ingest=pvt.INGEST_ROI)
+    assert np.array_equal(full[0], part[0]) and np.array_equal(full[1], part[1])
+    # pinned host frames: k_ingest_roi reads them over PCIe directly (no staging copy)
+    n, H, W, _ = frames.shape
+    pin = pvt.PinnedBuffer(frames.nbytes)
+    host = pin.array.reshape(frames.shape)
+    host[...] = frames
+    with pvt.Tracker(W, H, roi[2], roi[3], ingest=pvt.INGEST_ROI) as tr:
+        tr.init_track(0, host[0], roi)
+        keep = [tr.submit([host[k]]) for k in range(1, n)]
+        got = tr.collect(n - 1)
+    assert np.array_equal(records_of(got[:, 0]), full[0])
+    pin.free()
