@@ -151,28 +151,12 @@ def ring_descs(pvt, wl, buf, device_mem):
     return ring
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(0)
-    dev_index = local if world > 1 else 0
-    pvt = importlib.import_module("parallel-video-object-tracker_b200")
-    pvt.lib()  # fails loudly if libpvt.so is missing: there is no fallback path
-
-    wl = dict(WORKLOADS[args.workload])
+def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
+    """All legs of one workload on this rank.  full=False: only the resident leg + the roofline pass (used for `extra`)."""
+    wl = dict(WORKLOADS[wname])
     W, H, tw, th, R, L, S = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], wl["ring"], wl["streams"]
     n_tracks = S * wl["rois"]
-    K, Wm = args.steps, max(args.warmup, 3)
-
+    dev_index = torch.cuda.current_device()
     scenes, host, dev = build_rings(wl, rank, torch)
     info = pvt.device_info(dev_index)
 
@@ -185,18 +169,6 @@ def run_ours(args):
                 tr.init_track(t, pvt.device_frame(dev[s, 0].data_ptr(), W * 3, stream=s) if j == 0 else None, roi, stream=s)
                 t += 1
         return tr
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def maxr(x):
-        if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
 
     def shifted(ring, start):  # step s uses ring position (start + s) % L; frame 0 was the init frame
         return ring[start % L:] + ring[:start % L]
@@ -214,14 +186,22 @@ def run_ours(args):
     tr.submit_sequence(K, shifted(ring_dev, 1 + Wm))
     ms = tr.timer_stop()
     barrier()
-    clocks = sampler.stop()
     launches = tr.launch_count() - l0
+    # nvidia-smi samples every 100 ms; a timed region of a few tens of ms may see none, so the IDENTICAL load keeps
+    # running (untimed) until three samples under load exist
+    extra_steps, t_wait = 0, time.perf_counter()
+    while len(sampler.rows) < 3 and time.perf_counter() - t_wait < 3.0:
+        tr.submit_sequence(K, shifted(ring_dev, 1 + Wm + K + extra_steps))
+        tr.sync()
+        extra_steps += K
+    clocks = sampler.stop()
+    clocks["sampled_over"] = "timed region + %d further identical untimed steps" % extra_steps
     ms = maxr(ms)
     # correctness guard: the last steps must sit exactly on the synthetic ground truth
     last = tr.collect(min(64, K))
     ok = True
     for i in range(len(last)):
-        stp = Wm + K - len(last) + i + 1
+        stp = Wm + K + extra_steps - len(last) + i + 1
         for s in range(S):
             tx, ty = scenes[s % len(scenes)].obj_pos(stp % L)
             r = last[i][s * wl["rois"]]
@@ -229,30 +209,71 @@ def run_ours(args):
     if not ok:
         raise SystemExit("bench: tracked boxes left the synthetic ground truth -- refusing to report a number")
     conf_min = float(last["conf"][:, ::wl["rois"]].min())
-    frames_per_step = S                      # frames consumed per time step on this rank
-    value = world * frames_per_step * K / (ms * 1e-3)
+    value = world * S * K / (ms * 1e-3)
 
-    # ---- leg 2: identical pass with CUDA events around every kernel (roofline) -----------------------
-    Kp = min(K, 200)
+    # ---- leg 2: identical pass with CUDA event-record nodes around every kernel class inside the graph ------
+    Kp = min(K, 100)
     tr.profile_enable(True)
     tr.profile_get(reset=True)
-    tr.submit_sequence(Kp, shifted(ring_dev, 1 + Wm + K))
+    tr.submit_sequence(Kp, shifted(ring_dev, 1 + Wm + K + extra_steps))
     prof = tr.profile_get(reset=True)
     tr.profile_enable(False)
+    # warm device-side timeline of the same graph (globaltimer stamps; first CTA start .. last CTA end per kernel)
+    tr.trace_enable(True)
+    tr.submit_sequence(24, shifted(ring_dev, 1 + Wm + K + extra_steps + Kp))
+    T = tr.trace_get(16).astype(np.int64)
+    tr.trace_enable(False)
+    names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update"]
+    timeline = {nm: round(float(np.median(T[:, k, 1] - T[:, k, 0])) / 1e3, 2) for k, nm in enumerate(names) if T[:, k, 0].any()}
+    timeline["step_to_step"] = round(float(np.median(np.diff(T[:, 0, 0]))) / 1e3, 2)
+    ingest_mode = "roi" if tr.params.ingest == pvt.INGEST_ROI else "full" if tr.params.ingest == pvt.INGEST_FULL else \
+        ("roi (auto)" if n_tracks * (2 * R + 1 + tw) * (2 * R + 1 + th) <= 0.5 * S * W * H else "full (auto)")
+    tr.close()
     fmax_ghz = info["sm_clock_khz"] * 1e-6
     fp32_peak = info["sm_count"] * 128 * 2 * fmax_ghz * 1e-3  # TFLOP/s at the max SM clock
     ncc_s = prof["ncc_ms"] * 1e-3 / max(prof["ncc_launches"], 1)
     macs_per_launch = prof["ncc_macs"] / max(prof["ncc_launches"], 1)
     ncc_tf = 2.0 * macs_per_launch / ncc_s / 1e12
-    hbm_peak, hbm_src = peaks()
-    ing_s = prof["ingest_ms"] * 1e-3 / max(prof["ingest_launches"], 1)
-    ing_gbs = prof["ingest_bytes"] / max(prof["ingest_launches"], 1) / ing_s / 1e9
-    step_ms_prof = (prof["ingest_ms"] + prof["stats_ms"] + prof["ncc_ms"] + prof["update_ms"]) / max(prof["steps"], 1)
-    tr.close()
+    steps_p = max(prof["steps"], 1)
+    out = {
+        "value": value, "ms_per_step": ms / K, "launches": int(launches), "clocks": clocks, "conf_min": conf_min,
+        "macs_per_step": macs_per_launch, "n_tracks": n_tracks, "wl": wl, "ingest_mode": ingest_mode,
+        "roofline": {"kernel": "k_ncc_search", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": ncc_tf / fp32_peak, "traffic": None,
+                     "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
+                     "us_per_launch": ncc_s * 1e6, "macs_per_launch": macs_per_launch,
+                     "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps" % Kp},
+        "kernel_ms_per_step": {"ingest": prof["ingest_ms"] / steps_p, "stats": prof["stats_ms"] / steps_p, "search": prof["ncc_ms"] / steps_p,
+                               "finalize_update": prof["update_ms"] / steps_p},
+        "device_timeline_us": timeline,
+    }
+    if not full:
+        return out
 
-    # ---- leg 3: batch=4 hold semantics (reported beside the headline) ---------------------------------
-    batch4 = None
-    if args.workload == "C2":
+    # ---- leg 3: full-frame ingest (the reference's toGrayF32 on whole frames) against the HBM roofline -------
+    # one launch converts NS frames of this geometry (>= 200 MB per launch, larger than L2), frames from the resident ring
+    hbm_peak, hbm_src = peaks()
+    NS = max(1, min(16, int(240e6 // (W * H * 7))))
+    tri = pvt.Tracker(W, H, tw, th, max_streams=NS, max_tracks=1, device=dev_index, search_radius_x=R, search_radius_y=R, ingest=pvt.INGEST_FULL)
+    tri.init_track(0, pvt.device_frame(dev[0, 0].data_ptr(), W * 3, stream=0), rois_for(wl, scenes[0])[0], stream=0)
+    ring_i = [[pvt.Frame(s2, pvt.FMT_BGR8, pvt.MEM_DEVICE, 0, dev[(s2 + k) % S, (k + s2 // S) % L].data_ptr(), W * 3) for s2 in range(NS)] for k in range(L)]
+    tri.submit_sequence(4, ring_i[1:] + ring_i[:1])
+    tri.profile_enable(True)
+    tri.profile_get(reset=True)
+    tri.submit_sequence(20, ring_i[5 % L:] + ring_i[:5 % L])
+    pf = tri.profile_get(reset=True)
+    tri.profile_enable(False)
+    tri.close()
+    ing_s = pf["ingest_ms"] * 1e-3 / max(pf["ingest_launches"], 1)
+    ing_bytes = pf["ingest_bytes"] / max(pf["ingest_launches"], 1)
+    out["ingest"] = {"kernel": "k_ingest (full frames)", "bound": "hbm", "achieved": ing_bytes / ing_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ing_bytes / ing_s / 1e9 / hbm_peak, "peak_source": hbm_src, "us_per_launch": ing_s * 1e6,
+                     "bytes_per_launch": ing_bytes, "frames_per_launch": NS,
+                     "note": "BGR8 -> f32: 3 B read + 4 B written per pixel; the timed legs use ingest mode '%s'" % ingest_mode}
+
+    # ---- leg 4: batch=4 hold semantics (reported beside the headline) ---------------------------------
+    out["batch4"] = None
+    if wname == "C2":
         trb = make_tracker(mode=pvt.MODE_BATCH, batch_size=4)
         trb.submit_sequence(Wm, shifted(ring_dev, 1))
         trb.sync()
@@ -261,9 +282,9 @@ def run_ours(args):
         trb.submit_sequence(K, shifted(ring_dev, 1 + Wm))
         msb = maxr(trb.timer_stop())
         trb.close()
-        batch4 = {"frames_per_s": world * K / (msb * 1e-3), "searched_frames_per_s": world * (K // 4) / (msb * 1e-3), "ms_per_frame": msb / K}
+        out["batch4"] = {"frames_per_s": world * K / (msb * 1e-3), "searched_frames_per_s": world * (K // 4) / (msb * 1e-3), "ms_per_frame": msb / K}
 
-    # ---- leg 4: end to end through the C ABI with pinned HOST frames ------------------------------------
+    # ---- leg 5: end to end through the C ABI with pinned HOST frames ------------------------------------
     ring_host = ring_descs(pvt, wl, host, False)
     tre = make_tracker()
     ce = 32 if K >= 32 else K
@@ -281,31 +302,72 @@ def run_ours(args):
         if not (res[i][0]["x"] == tx and res[i][0]["y"] == ty):
             raise SystemExit("bench: e2e leg lost the object")
     tre.close()
-    e2e = {"value": world * frames_per_step * Ke / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(S * W * H * 3),
-           "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke, "how": "pvt_submit_sequence over pinned host BGR frames; results read back every %d steps" % ce}
+    roi = ingest_mode.startswith("roi")
+    tile_bytes = n_tracks * (2 * R + 1 + tw + 3) * (2 * R + th) * 3
+    out["e2e"] = {"value": world * S * Ke / e2e_s, "unit": "frames/s",
+                  "h2d_bytes_per_step": int(tile_bytes if roi else S * W * H * 3), "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke,
+                  "how": ("pvt_submit_sequence over pinned host BGR frames; ROI ingest reads the search tiles zero-copy over PCIe "
+                          "(bytes = tiles actually read; whole frames are %d B); results read back every %d steps" % (S * W * H * 3, ce)) if roi else
+                         "pvt_submit_sequence over pinned host BGR frames, staged H2D copy of whole frames; results read back every %d steps" % ce}
+    out["_scene0"], out["_host0"] = scenes[0], host[0].numpy()
+    return out
 
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    pvt = importlib.import_module("parallel-video-object-tracker_b200")
+    pvt.lib()  # fails loudly if libpvt.so is missing: there is no fallback path
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    m = measure(pvt, torch, args.workload, rank, world, K, Wm, barrier, maxr, full=True)
+    wl = m["wl"]
     out = {
-        "metric": "tracked_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [W, H], "template": [tw, th], "radius": R,
-                   "streams_per_gpu": S, "tracks_per_gpu": n_tracks, "ring_frames_per_stream": L,
-                   "l2_policy": "frame ring %.0f MB per GPU > 126 MB L2; no explicit flush" % (S * L * W * H * 3 / 1e6),
+        "metric": "tracked_frames_per_s", "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [wl["W"], wl["H"]], "template": [wl["tw"], wl["th"]], "radius": wl["R"],
+                   "streams_per_gpu": wl["streams"], "tracks_per_gpu": m["n_tracks"], "ring_frames_per_stream": wl["ring"], "ingest": m["ingest_mode"],
+                   "l2_policy": "frame ring %.0f MB per GPU > 126 MB L2; no explicit flush" % (wl["streams"] * wl["ring"] * wl["W"] * wl["H"] * 3 / 1e6),
                    "parallelism": "1 process per GPU, tracks sharded by stream, no data-path collective"},
-        "ncc_gmacs_per_s": world * macs_per_launch * K / (ms * 1e-3) / 1e9,
-        "roofline": {"kernel": "k_ncc_tiled", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": ncc_tf / fp32_peak, "traffic": None,
-                     "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
-                     "us_per_launch": ncc_s * 1e6, "macs_per_launch": macs_per_launch,
-                     "how": "CUDA events around each launch on the library's stream, identical second pass of %d steps" % Kp},
-        "ingest": {"kernel": "k_ingest", "bound": "hbm", "achieved": ing_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ing_gbs / hbm_peak,
-                   "peak_source": hbm_src, "us_per_launch": ing_s * 1e6},
-        "kernel_ms_per_step": {"ingest": prof["ingest_ms"] / max(prof["steps"], 1), "stats": prof["stats_ms"] / max(prof["steps"], 1),
-                               "ncc": prof["ncc_ms"] / max(prof["steps"], 1), "update": prof["update_ms"] / max(prof["steps"], 1),
-                               "sum": step_ms_prof},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "conf_min": conf_min, "batch4": batch4,
+        "ncc_gmacs_per_s": world * m["macs_per_step"] * K / (m["ms_per_step"] * K * 1e-3) / 1e9,
+        "roofline": m["roofline"], "ingest": m["ingest"], "kernel_ms_per_step": m["kernel_ms_per_step"],
+        "device_timeline_us": m["device_timeline_us"], "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": m["clocks"],
+        "conf_min": m["conf_min"], "batch4": m["batch4"],
     }
+    if rank == 0 and world == 1 and args.extra:
+        # the search kernel with the GPU filled: SURVEY.md 8(d) configs C4 (256 ROIs) and C5's per-GPU share (64 streams)
+        out["extra"] = {}
+        for w2 in ("C4", "C5"):
+            if w2 == args.workload:
+                continue
+            e = measure(pvt, torch, w2, 0, 1, 40, 6, barrier, maxr, full=False)
+            out["extra"][w2] = {"workload": WORKLOADS[w2]["desc"], "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
+                                "ncc_gmacs_per_s": e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9, "roofline": e["roofline"],
+                                "kernel_ms_per_step": e["kernel_ms_per_step"], "ingest": e["ingest_mode"]}
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(wl, scenes[0], host[0].numpy(), budget_s=args.cpu_seconds)
+        out["cpu_baseline"] = cpu_baseline(wl, m["_scene0"], m["_host0"], budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -382,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the filled-GPU C4/C5 side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

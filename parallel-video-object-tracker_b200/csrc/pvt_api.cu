@@ -64,7 +64,8 @@ struct pvt_ctx {
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr;   // aux: second branch inside the captured graph
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaGraphExec_t graph = nullptr, graph_hold = nullptr;
+    cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
+    cudaEvent_t pev[4][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class
     bool graph_valid = false;
     std::vector<void*> allocs;
     FrameDesc* h_table = nullptr;  // pinned, [kRing][max_streams]
@@ -228,36 +229,31 @@ int dbg(pvt_ctx* c, const char* what)
     return PVT_OK;
 }
 
-int prof_begin(pvt_ctx* c, int cls, EventPair** out)
+// profiling inside a captured graph: external event-record nodes (GPU-side timestamps, no host launch gaps)
+int pnode(pvt_ctx* c, int cls, int which, cudaStream_t st)
 {
-    if (c->ev_next == c->ev_pool.size()) {
-        EventPair p{};
-        CK(cudaEventCreate(&p.a));
-        CK(cudaEventCreate(&p.b));
-        c->ev_pool.push_back(p);
-    }
-    EventPair* p = &c->ev_pool[c->ev_next++];
-    p->cls = cls;
-    CK(cudaEventRecord(p->a, c->compute));
-    *out = p;
+    CK(cudaEventRecordWithFlags(c->pev[cls][which], st, cudaEventRecordExternal));
     return PVT_OK;
 }
 
-// the kernels of one searched time step, on c->compute (captured into the graph or launched directly)
+// The kernels of one searched time step.  capturing: being recorded into a CUDA graph on c->compute (fork/join allowed).
+// profile (only while capturing): external event-record NODES around each kernel class, so the measured durations are
+// GPU-side and contain no host launch gaps.  Classes: ingest | statistics | search (k_ncc_search [+ tail reduction]) |
+// update (k_ncc_finalize incl. the fused update in K-split mode, else k_update).
 int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
 {
     const Ctx& d = c->d;
-    EventPair* ep = nullptr;
+    profile = profile && capturing;
     const int gpr = (d.W + 3) / 4;
     const long long groups = (long long)gpr * d.H;
-    if (profile) { int r = prof_begin(c, CLS_INGEST, &ep); if (r) return r; }
+    if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
     if (c->roi_ingest) {
         const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
         k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
-        k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+        k_ingest<<<dim3((unsigned)((groups + 256 * kIngestGroups - 1) / (256 * kIngestGroups)), d.max_streams), 256, 0, c->compute>>>(d);
     }
-    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    if (profile) { int r = pnode(c, CLS_INGEST, 1, c->compute); if (r) return r; }
     { int r = dbg(c, "k_ingest"); if (r) return r; }
 
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
@@ -270,33 +266,38 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
         CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
         sstats = c->aux;
     }
-    if (profile) { int r = prof_begin(c, CLS_STATS, &ep); if (r) return r; }
+    if (profile) { int r = pnode(c, CLS_STATS, 0, sstats); if (r) return r; }
     k_colprefix<<<dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, c->colprefix_chunks), 0, sstats>>>(d);
     { int r = dbg(c, "k_colprefix"); if (r) return r; }
     k_rowsum<<<dim3((d.Hmax + c->rowsum_warps - 1) / c->rowsum_warps, d.max_tracks), c->rowsum_warps * 32,
                (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), sstats>>>(d, c->rowsum_pw);
-    if (profile) CK(cudaEventRecord(ep->b, c->compute));
+    if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
-    if (profile) { int r = prof_begin(c, CLS_NCC, &ep); if (r) return r; }
+    if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; }
     if (c->params.kernel == PVT_KERNEL_DIRECT) {
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
+        if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else {
         const int parts = c->tile.pj * c->tile.pd;
         const unsigned nbx = (unsigned)(c->tile.n_full + c->tile.n_tail * std::max(c->tile.tail_ps, 1));
         k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
         if (c->tile.tail_ps > 1) k_ncc_tail_finalize<kCY><<<c->tile.n_tail, kTilesPerCta, 0, c->compute>>>(d, c->tile);
+        if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
-        if (parts > 1) k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, c->tile);
+        if (parts > 1) {
+            if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
+            k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, c->tile);
+            if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
+        }
     }
-    if (profile) CK(cudaEventRecord(ep->b, c->compute));
     { int r = dbg(c, "k_ncc"); if (r) return r; }
 
-    if (c->params.kernel == PVT_KERNEL_DIRECT || c->tile.pj * c->tile.pd == 1) {   // otherwise the update ran inside k_ncc_finalize
-        if (profile) { int r = prof_begin(c, CLS_UPDATE, &ep); if (r) return r; }
+    if (!ksplit) {   // otherwise the update ran inside k_ncc_finalize
+        if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
         k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
-        if (profile) CK(cudaEventRecord(ep->b, c->compute));
+        if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_update"); if (r) return r; }
     }
     CK(cudaGetLastError());
@@ -314,6 +315,14 @@ int build_graphs(pvt_ctx* c)
     if (r) return r;
     CK(e);
     CK(cudaGraphInstantiate(&c->graph, g, 0));
+    CK(cudaGraphDestroy(g));
+    if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
+    CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+    r = launch_step_kernels(c, true, true);
+    e = cudaStreamEndCapture(c->compute, &g);
+    if (r) return r;
+    CK(e);
+    CK(cudaGraphInstantiate(&c->graph_prof, g, 0));
     CK(cudaGraphDestroy(g));
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
     k_hold<<<1, 256, 0, c->compute>>>(c->d);
@@ -398,11 +407,25 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph_hold, c->compute));
         c->launches += 1;
-    } else if (c->profiling || debug_sync()) {
-        int r = launch_step_kernels(c, c->profiling);
+    } else if (debug_sync()) {
+        int r = launch_step_kernels(c, false);
         if (r) return r;
         c->launches += c->kps;
-        if (c->profiling) c->prof.steps += 1;
+    } else if (c->profiling) {
+        // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
+        if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
+        CK(cudaGraphLaunch(c->graph_prof, c->compute));
+        CK(cudaStreamSynchronize(c->compute));
+        c->launches += c->kps;
+        c->prof.steps += 1;
+        double* acc[4] = {&c->prof.ingest_ms, &c->prof.stats_ms, &c->prof.ncc_ms, &c->prof.update_ms};
+        int64_t* cnt[4] = {&c->prof.ingest_launches, &c->prof.stats_launches, &c->prof.ncc_launches, &c->prof.update_launches};
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->pev[k][0], c->pev[k][1]));
+            *acc[k] += ms;
+            *cnt[k] += (k == CLS_STATS) ? 2 : 1;
+        }
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
@@ -498,6 +521,8 @@ int pvt_destroy(pvt_ctx* c)
     if (c->copy) cudaStreamSynchronize(c->copy);
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
+    if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
+    for (int k = 0; k < 4; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_table) cudaFreeHost(c->h_table);
     if (c->h_results) cudaFreeHost(c->h_results);
@@ -610,6 +635,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CKD(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     }
+    for (int k = 0; k < 4; ++k) { CKD(cudaEventCreate(&c->pev[k][0])); CKD(cudaEventCreate(&c->pev[k][1])); }
     CKD(cudaEventCreate(&c->timer_a));
     CKD(cudaEventCreate(&c->timer_b));
     c->stage.assign((size_t)d.max_streams * kStageDepth, nullptr);
@@ -748,7 +774,7 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
     if (e == cudaSuccess) {
         const int gpr = (d.W + 3) / 4;
         const long long groups = (long long)gpr * d.H;
-        k_ingest<<<dim3((unsigned)((groups + 255) / 256), d.max_streams), 256, 0, c->compute>>>(d);
+        k_ingest<<<dim3((unsigned)((groups + 256 * kIngestGroups - 1) / (256 * kIngestGroups)), d.max_streams), 256, 0, c->compute>>>(d);
         c->launches += 1;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);

@@ -1,5 +1,5 @@
 W=${1:-C4}
-for plan in "" "33,1,1" "33,2,1" "33,4,1" "33,1,2" "11,2,1"; do
+for plan in "" "33,1,1"; do
   PVT_PLAN="$plan" PVT_DEBUG_PLAN=1 timeout 300 python bench.py --workload $W --steps 24 --warmup 4 --no-cpu > /tmp/b.json 2> /tmp/b.err
   echo "plan=[$plan] rc=$? $(grep -m1 'plan:' /tmp/b.err)"
   python -c "
