@@ -22,7 +22,9 @@ identical second pass; `ingest` HBM fraction is reported beside it against MEASU
 from __future__ import annotations
 
 import argparse
+import contextlib
 import importlib
+import io
 import json
 import os
 import subprocess
@@ -447,10 +449,25 @@ def main():
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the filled-GPU C4/C5 side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # exactly ONE line may reach stdout (the JSON); libraries print banners there (e.g. "NCCL version ..."), so fd 1 is
+    # pointed at stderr while working and restored for the final print
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
