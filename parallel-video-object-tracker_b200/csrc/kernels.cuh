@@ -436,38 +436,46 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
 
     constexpr int kRingT = 4;  // template slices in flight (full/empty mbarrier ring; no CTA-wide sync in the loop)
     float* s_tile = reinterpret_cast<float*>(sm_raw);
-    float* s_templ = s_tile + (size_t)g.boxW * g.boxH;             // kRingT slices of [mth][8]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_templ + kRingT * (size_t)c.mth * 8);  // [0] tile, [1..4] full, [5..8] empty
+    const size_t sstride = (size_t)c.mth * 8;                      // kRingT slices of [mth][8]
+    float* s_templ = s_tile + (size_t)g.boxW * g.boxH;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_templ + kRingT * sstride);  // [0] tile, [1..4] full, [5..8] empty
     uint64_t* full = bars + 1;
     uint64_t* empty = bars + 1 + kRingT;
     const float* gtempl = c.templc + (size_t)track * c.mth * c.mtp;
     const uint32_t slice_bytes = (uint32_t)nd * 32u;
     const int nj = j1 - j0;
 
+    const int q = q0 + threadIdx.x;
+    const int col = q / g.GB, gl = q - col * g.GB;
+    const int grp = band * g.GB + gl;
+    const bool active = col < g.C && col * 8 < xs + ww && grp * CY < wh;
+    // warps without a single active tile (e.g. half of a track's last CTA) take no part in the template-slice ring and
+    // leave right after setup: left in the loop they would spin on the slice barriers for the CTA's whole lifetime and
+    // take issue slots from the co-resident CTA.  The `empty` barriers count the participating warps only.
+    const bool warp_on = __any_sync(0xffffffffu, active) || threadIdx.x < 32;   // warp 0 hosts the producer thread: always in
+    const int n_part = __syncthreads_count(warp_on && (threadIdx.x & 31) == 0);
+
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
 #pragma unroll
         for (int s = 0; s < kRingT; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], blockDim.x >> 5);
+            mbar_init(&empty[s], n_part);
         }
         fence_mbar_init();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
         tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, t.stream);
         for (int s = 0; s < 2 && s < nj; ++s) {
             mbar_arrive_expect_tx(&full[s], slice_bytes);
-            bulk_load(s_templ + (size_t)s * c.mth * 8, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
+            bulk_load(s_templ + (size_t)s * sstride, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
         }
     }
     __syncthreads();  // barriers initialised before anybody polls them
     if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2] = gtime();
+    if (!warp_on) return;
     mbar_wait(&bars[0], 0);
     if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2 + 1] = gtime();
 
-    const int q = q0 + threadIdx.x;
-    const int col = q / g.GB, gl = q - col * g.GB;
-    const int grp = band * g.GB + gl;
-    const bool active = col < g.C && col * 8 < xs + ww && grp * CY < wh;
     const int P = g.boxW;
     const float* base = s_tile + (size_t)(gl * CY) * P + (col - c_lo) * 8;
 
@@ -484,11 +492,11 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
             const int c2 = it + 2, s2 = c2 & (kRingT - 1);
             if (c2 >= kRingT) mbar_wait(&empty[s2], (uint32_t)((c2 / kRingT) - 1) & 1u);
             mbar_arrive_expect_tx(&full[s2], slice_bytes);
-            bulk_load(s_templ + (size_t)s2 * c.mth * 8, gtempl + ((size_t)(j0 + c2) * th + d0) * 8, slice_bytes, &full[s2]);
+            bulk_load(s_templ + (size_t)s2 * sstride, gtempl + ((size_t)(j0 + c2) * th + d0) * 8, slice_bytes, &full[s2]);
         }
         mbar_wait(&full[slot], (uint32_t)(it / kRingT) & 1u);
         if (active) {
-            const float* st = s_templ + (size_t)slot * c.mth * 8;
+            const float* st = s_templ + (size_t)slot * sstride;
             const float* fb = base + (j - j0) * 8;
             float racc[CY][8], w[CY][16];
 #pragma unroll

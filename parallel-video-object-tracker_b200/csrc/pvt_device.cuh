@@ -166,7 +166,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x2000;\n\t"   // suspend-time hint (ns): sleep in HW, no hot spin
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");

@@ -237,6 +237,173 @@ void run_y(const char* name, int sms, double ghz, const float* gt)
     CK(cudaFree(out));
 }
 
+
+// ---- y-sliding, explicitly software-pipelined: the window row and template values of step dy+1 are loaded into a spare
+// register set before the FMAs of step dy; the chunk totals live in shared memory (frees 8*CY registers for the spare set).
+template <int CY>
+__global__ void __launch_bounds__(128, 2) k_loop_yp(float* out, const float* __restrict__ gt, int reps)
+{
+    extern __shared__ __align__(16) float sm[];
+    float* s_tile = sm;
+    float* s_templ = sm + ROWS * P;
+    float* s_acc = s_templ + TP * TH;                       // [8*CY][128] chunk totals
+    for (int i = threadIdx.x; i < ROWS * P; i += blockDim.x) s_tile[i] = 0.5f + 1e-4f * (float)(i % 977);
+    for (int i = threadIdx.x; i < TP * TH; i += blockDim.x) s_templ[i] = gt[i];
+    for (int i = threadIdx.x; i < 8 * CY * 128; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int q = threadIdx.x, col = q >> 5, g = q & 31;
+    const float* base = s_tile + ((CY * g) % (ROWS - TH - CY)) * P + (col % 3) * 8;
+    for (int rep = 0; rep < reps; ++rep)
+        for (int j = 0; j < TP; j += 8) {
+            float racc[CY][8], w[CY + 1][16], t[2][8];
+#pragma unroll
+            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = 0.f;
+#pragma unroll
+            for (int r = 0; r < CY; ++r) {                  // rows 0 .. CY-1 (the window of step 0 complete)
+                const float* p = base + r * P + j;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * v); w[r][4 * v] = a.x; w[r][4 * v + 1] = a.y; w[r][4 * v + 2] = a.z; w[r][4 * v + 3] = a.w; }
+            }
+            loadt(t[0], s_templ + j);
+            // steps run in groups of CY+1 so that the (CY+1)-slot window ring and the 2-slot template ring rotate through
+            // static register names
+#pragma unroll 1
+            for (int dy0 = 0; dy0 < TH; dy0 += (CY + 1)) {
+#pragma unroll
+                for (int u = 0; u < (CY + 1); ++u) {
+                    const int dy = dy0 + u;
+                    if (dy < TH) {
+                        // prefetch for step dy+1: window row dy+CY into the spare slot, template row dy+1
+                        const float* p = base + (dy + CY) * P + j;
+                        float(&wn)[16] = w[(u + CY) % (CY + 1)];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * v); wn[4 * v] = a.x; wn[4 * v + 1] = a.y; wn[4 * v + 2] = a.z; wn[4 * v + 3] = a.w; }
+                        loadt(t[(u + 1) & 1], s_templ + (dy + 1 < TH ? dy + 1 : dy) * TP + j);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+#pragma unroll
+                            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = fmaf(w[(u + i) % (CY + 1)][k + cx], t[u & 1][k], racc[i][cx]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) s_acc[(i * 8 + cx) * 128 + threadIdx.x] += racc[i][cx];
+        }
+    float s = 0.f;
+    for (int i = 0; i < 8 * CY; ++i) s += s_acc[i * 128 + threadIdx.x];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CY, bool PIPE>
+void run_y2(const char* name, int sms, double ghz, const float* gt, int ctas_per_sm)
+{
+    const int reps = 8, ctas = sms * ctas_per_sm;
+    const size_t smem = (size_t)(ROWS * P + TP * TH + 64 + (PIPE ? 8 * CY * 128 : 0)) * 4;
+    float* out; CK(cudaMalloc(&out, (size_t)ctas * 128 * 4));
+    if (PIPE) CK(cudaFuncSetAttribute(k_loop_yp<CY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(k_loop_y<CY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    auto go = [&](int r) { if (PIPE) k_loop_yp<CY><<<ctas, 128, smem>>>(out, gt, r); else k_loop_y<CY><<<ctas, 128, smem>>>(out, gt, r, 32); };
+    go(1);
+    CK(cudaDeviceSynchronize());
+    float best = 1e9f;
+    for (int r = 0; r < 3; ++r) {
+        CK(cudaEventRecord(a)); go(reps); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+    }
+    const double fma = (double)ctas * 128 * reps * TH * TP * 8.0 * CY;
+    const double tf = 2.0 * fma / (best * 1e-3) / 1e12;
+    printf("Y%s CY=%d %-40s ctas/SM=%d %8.3f ms  %6.2f TFLOP/s  %5.1f%% of nominal (x%d warps per sub-partition)\n", PIPE ? "P" : " ", CY, name, ctas_per_sm, best, tf,
+           100.0 * tf / (sms * 128 * 2 * ghz * 1e-3), ctas_per_sm);
+    CK(cudaFree(out));
+}
+
+
+// ---- y-sliding CY=5, 12 warps per SM in ONE 384-thread CTA: chunk totals in shared memory so the loop fits 168 registers
+template <int CY, int NT>
+__global__ void __launch_bounds__(NT, 1) k_loop_y12(float* out, const float* __restrict__ gt, int reps, int rows)
+{
+    extern __shared__ __align__(16) float sm[];
+    float* s_tile = sm;
+    float* s_templ = sm + rows * P;
+    float* s_acc = s_templ + TP * TH;                       // [8*CY][NT] chunk totals
+    for (int i = threadIdx.x; i < rows * P; i += blockDim.x) s_tile[i] = 0.5f + 1e-4f * (float)(i % 977);
+    for (int i = threadIdx.x; i < TP * TH; i += blockDim.x) s_templ[i] = gt[i];
+    for (int i = threadIdx.x; i < 8 * CY * NT; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int q = threadIdx.x, col = q >> 5, g = q & 31;
+    const float* base = s_tile + ((CY * g) % (rows - TH - CY)) * P + (col % 3) * 8;
+    for (int rep = 0; rep < reps; ++rep)
+        for (int j = 0; j < TP; j += 8) {
+            float racc[CY][8], w[CY][16], t[8];
+#pragma unroll
+            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = 0.f;
+#pragma unroll
+            for (int r = 0; r < CY - 1; ++r) {
+                const float* p = base + r * P + j;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * v); w[r][4 * v] = a.x; w[r][4 * v + 1] = a.y; w[r][4 * v + 2] = a.z; w[r][4 * v + 3] = a.w; }
+            }
+#pragma unroll 1
+            for (int dy0 = 0; dy0 < TH; dy0 += CY) {
+#pragma unroll
+                for (int u = 0; u < CY; ++u) {
+                    const int dy = dy0 + u;
+                    if (dy < TH) {
+                        const float* p = base + (dy + CY - 1) * P + j;
+                        float(&wn)[16] = w[(u + CY - 1) % CY];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * v); wn[4 * v] = a.x; wn[4 * v + 1] = a.y; wn[4 * v + 2] = a.z; wn[4 * v + 3] = a.w; }
+                        loadt(t, s_templ + dy * TP + j);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+#pragma unroll
+                            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                                for (int cx = 0; cx < 8; ++cx) racc[i][cx] = fmaf(w[(u + i) % CY][k + cx], t[k], racc[i][cx]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CY; ++i)
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx) s_acc[(i * 8 + cx) * NT + threadIdx.x] += racc[i][cx];
+        }
+    float s = 0.f;
+    for (int i = 0; i < 8 * CY; ++i) s += s_acc[i * NT + threadIdx.x];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CY, int NT>
+void run_y12(const char* name, int sms, double ghz, const float* gt)
+{
+    const int reps = 8, ctas = sms, rows = 228;
+    const size_t smem = (size_t)(rows * P + TP * TH + 64 + 8 * CY * NT) * 4;
+    float* out; CK(cudaMalloc(&out, (size_t)ctas * NT * 4));
+    CK(cudaFuncSetAttribute(k_loop_y12<CY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    k_loop_y12<CY, NT><<<ctas, NT, smem>>>(out, gt, 1, rows);
+    CK(cudaDeviceSynchronize());
+    float best = 1e9f;
+    for (int r = 0; r < 3; ++r) {
+        CK(cudaEventRecord(a)); k_loop_y12<CY, NT><<<ctas, NT, smem>>>(out, gt, reps, rows); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+    }
+    const double fma = (double)ctas * NT * reps * TH * TP * 8.0 * CY;
+    const double tf = 2.0 * fma / (best * 1e-3) / 1e12;
+    printf("Y12 CY=%d %-40s NT=%d %8.3f ms  %6.2f TFLOP/s  %5.1f%% of nominal (%d warps per sub-partition)\n", CY, name, NT, best, tf,
+           100.0 * tf / (sms * 128 * 2 * ghz * 1e-3), NT / 128);
+    CK(cudaFree(out));
+}
+
 template <int V, int CY>
 void run(const char* name, int sms, double ghz, const float* gt)
 {
@@ -284,6 +451,13 @@ int main()
     run<9, 4>("V0 with every window load issued twice", sms, ghz, gt);
     run<6, 4>("V0 + opaque branch after every k group", sms, ghz, gt);
     run<7, 4>("V0 + opaque branch after every 2 k groups", sms, ghz, gt);
+    run_y2<5, false>("y-sliding", sms, ghz, gt, 1);
+    run_y2<5, false>("y-sliding", sms, ghz, gt, 2);
+    run_y2<5, true>("y-sliding, software-pipelined", sms, ghz, gt, 1);
+    run_y2<5, true>("y-sliding, software-pipelined", sms, ghz, gt, 2);
+    run_y12<5, 256>("chunk totals in smem, 1 CTA/SM", sms, ghz, gt);
+    run_y12<5, 384>("chunk totals in smem, 1 CTA/SM", sms, ghz, gt);
+    run_y12<5, 512>("chunk totals in smem, 1 CTA/SM", sms, ghz, gt);
     run_y<3>("y-sliding", sms, ghz, gt);
     run_y<4>("y-sliding (rows 4 apart: 2-way bank conflicts expected)", sms, ghz, gt);
     run_y<5>("y-sliding", sms, ghz, gt);
