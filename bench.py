@@ -225,17 +225,25 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
     tr.submit_sequence(24, shifted(ring_dev, 1 + Wm + K + extra_steps + Kp))
     T = tr.trace_get(16).astype(np.int64)
     tr.trace_enable(False)
-    names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update"]
+    names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe"]
     timeline = {nm: round(float(np.median(T[:, k, 1] - T[:, k, 0])) / 1e3, 2) for k, nm in enumerate(names) if T[:, k, 0].any()}
+    if T[:, 6, 0].any():   # where the fringe kernel sits relative to the search kernel's start
+        timeline["ncc_fringe_start_after_search_start"] = round(float(np.median(T[:, 6, 0] - T[:, 3, 0])) / 1e3, 2)
+        timeline["ncc_fringe_end_after_search_end"] = round(float(np.median(T[:, 6, 1] - T[:, 3, 1])) / 1e3, 2)
     timeline["step_to_step"] = round(float(np.median(np.diff(T[:, 0, 0]))) / 1e3, 2)
     ingest_mode = "roi" if tr.params.ingest == pvt.INGEST_ROI else "full" if tr.params.ingest == pvt.INGEST_FULL else \
         ("roi (auto)" if n_tracks * (2 * R + 1 + tw) * (2 * R + 1 + th) <= 0.5 * S * W * H else "full (auto)")
     tr.close()
     fmax_ghz = info["sm_clock_khz"] * 1e-6
     fp32_peak = info["sm_count"] * 128 * 2 * fmax_ghz * 1e-3  # TFLOP/s at the max SM clock
-    ncc_s = prof["ncc_ms"] * 1e-3 / max(prof["ncc_launches"], 1)
+    # the search PHASE (k_ncc_search + tail reduction + the concurrent k_ncc_fringe, until all have ended) with ALL MACs,
+    # and the dominant kernel alone (k_ncc_search with the MACs of its own thread-tile grid): the roofline entry
+    phase_s = prof["ncc_ms"] * 1e-3 / max(prof["ncc_launches"], 1)
     macs_per_launch = prof["ncc_macs"] / max(prof["ncc_launches"], 1)
-    ncc_tf = 2.0 * macs_per_launch / ncc_s / 1e12
+    phase_tf = 2.0 * macs_per_launch / phase_s / 1e12
+    ncc_s = prof["search_kernel_ms"] * 1e-3 / max(prof["ncc_launches"], 1)
+    kmacs_per_launch = prof["search_kernel_macs"] / max(prof["ncc_launches"], 1)
+    ncc_tf = 2.0 * kmacs_per_launch / ncc_s / 1e12
     steps_p = max(prof["steps"], 1)
     out = {
         "value": value, "ms_per_step": ms / K, "launches": int(launches), "clocks": clocks, "conf_min": conf_min,
@@ -243,8 +251,12 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
         "roofline": {"kernel": "k_ncc_search", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": ncc_tf / fp32_peak, "traffic": None,
                      "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
-                     "us_per_launch": ncc_s * 1e6, "macs_per_launch": macs_per_launch,
-                     "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps" % Kp},
+                     "us_per_launch": ncc_s * 1e6, "macs_per_launch": kmacs_per_launch,
+                     "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps; "
+                            "MACs = candidates of the kernel's thread-tile grid x tw x th" % Kp,
+                     "search_phase": {"what": "k_ncc_search + tail reduction + concurrent k_ncc_fringe, all MACs of the step",
+                                      "achieved": phase_tf, "frac": phase_tf / fp32_peak, "us": phase_s * 1e6,
+                                      "macs": macs_per_launch}},
         "kernel_ms_per_step": {"ingest": prof["ingest_ms"] / steps_p, "stats": prof["stats_ms"] / steps_p, "search": prof["ncc_ms"] / steps_p,
                                "finalize_update": prof["update_ms"] / steps_p},
         "device_timeline_us": timeline,

@@ -133,6 +133,8 @@ typedef struct pvt_profile {
     int64_t steps;
     double ncc_macs;       /* algorithmic MACs (n_cand * tw * th) summed over the profiled steps */
     double ingest_bytes;   /* algorithmic bytes read + written by the ingest kernel */
+    double search_kernel_ms;   /* k_ncc_search alone (ncc_ms also covers the tail reduction and k_ncc_fringe) */
+    double search_kernel_macs; /* MACs of the candidates k_ncc_search's thread-tile grid computes (the rest: k_ncc_fringe) */
 } pvt_profile;
 
 typedef struct pvt_ctx pvt_ctx;

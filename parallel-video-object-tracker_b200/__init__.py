@@ -73,7 +73,8 @@ assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 32
 class Profile(C.Structure):
     _fields_ = [("ingest_ms", C.c_double), ("stats_ms", C.c_double), ("ncc_ms", C.c_double), ("update_ms", C.c_double),
                 ("ingest_launches", C.c_int64), ("stats_launches", C.c_int64), ("ncc_launches", C.c_int64),
-                ("update_launches", C.c_int64), ("steps", C.c_int64), ("ncc_macs", C.c_double), ("ingest_bytes", C.c_double)]
+                ("update_launches", C.c_int64), ("steps", C.c_int64), ("ncc_macs", C.c_double), ("ingest_bytes", C.c_double),
+                ("search_kernel_ms", C.c_double), ("search_kernel_macs", C.c_double)]
 
 
 class PvtError(RuntimeError):

@@ -379,8 +379,36 @@ __global__ void __launch_bounds__(256) k_ncc_direct(Ctx c)
 // =============================================================================================
 constexpr int kTilesPerCta = 128;
 
+// Shift every row of the shared tile [rows][P] left by S (1..3) floats, in place: row[i] = row[i + S].  Lanes take
+// consecutive rows; P / 4 is odd (P == 4 mod 8), so the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups.
+// The last float4 of a row keeps stale (finite) data: the box is 4 floats wider than anything the loop reads.
+template <int S>
+__device__ __forceinline__ void shift_rows_left(float* tile, int P, int rows)
+{
+    const int nv = P >> 2;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        float4* row = reinterpret_cast<float4*>(tile + (size_t)r * P);
+        float4 cur = row[0];
+        for (int m = 0; m + 1 < nv; ++m) {
+            const float4 nxt = row[m + 1];
+            float4 o;
+            if (S == 1) o = make_float4(cur.y, cur.z, cur.w, nxt.x);
+            else if (S == 2) o = make_float4(cur.z, cur.w, nxt.x, nxt.y);
+            else o = make_float4(cur.w, nxt.x, nxt.y, nxt.z);
+            row[m] = o;
+            cur = nxt;
+        }
+    }
+}
+
+
 struct TileCfg {
-    int G, C;            // row groups per column (ceil(Hmax / CY)), columns (ceil((Wmax + 3) / 8))
+    // Thread-tile grid, relative to the WINDOW ORIGIN: column c = candidates x in [8c, 8c+8), row group g = candidate
+    // rows [CY*g, CY*g + CY).  G = ceil(Hmax / CY) and C = ceil(Wmax / 8) -- except that a remainder of exactly ONE row /
+    // column (2R+1 = 161 = 32*5 + 1 = 20*8 + 1, the reference's default radius) is left out of the grid: a 33rd row
+    // group / 21st column would spend full 8 x CY tiles on 1/5 resp. 1/8 useful candidates.  Those "fringe" candidates
+    // (x >= 8C or y >= CY*G) are computed by k_ncc_fringe in the same accumulation order, concurrently.
+    int G, C;
     int GB, bands;       // row groups per band (a CTA's tiles live in one band), bands = ceil(G / GB)
     int ctas_band;       // CTAs per band (ceil(GB * C / 128))
     int span;            // columns one CTA's 128 tiles can touch
@@ -396,6 +424,10 @@ template <int CY>
 __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char sm_raw[];
+    // programmatic dependent launch: k_ncc_fringe (launched right behind this kernel in the throughput shape, and
+    // independent of its results) may start as soon as every CTA of this grid has been dispatched, i.e. it fills the
+    // SM slots that free up while the last round of search CTAs is still running
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int item = blockIdx.x, part = blockIdx.z, pj = g.pj, pd = g.pd, tail_k = -1;
     if (g.tail_ps > 1 && item >= g.n_full) {           // a part of a tail item
         tail_k = item - g.n_full;
@@ -418,13 +450,15 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     }
     const int ww = win[2], wh = win[3];
     const int th = t.h, nchunk = t.tp >> 3;
-    // the TMA tile must start on a 16-byte boundary in x: the column grid starts at the window origin rounded
-    // DOWN to a multiple of 4 pixels; the xs (0..3) grid columns in front of the window are masked
+    // A TMA tile must start on a 16-byte boundary in x (an unaligned innermost start coordinate raises "illegal
+    // instruction" on sm_100a: tools/tma_align_probe.cu), but the window origin is arbitrary.  The tile is therefore
+    // fetched from the origin rounded DOWN to 4 pixels and, when xs = origin & 3 is not 0, every row is shifted left by
+    // xs floats in shared memory once (~0.7 us of a ~190 us CTA), so that thread-tile columns start at the window origin.
     const int xs = win[0] & 3;
     const int band = blk / g.ctas_band, q0 = (blk - band * g.ctas_band) * kTilesPerCta;
     const int c_lo = q0 / g.GB;
     const int row0 = band * g.GB * CY;  // first candidate row of this band
-    if (c_lo * 8 >= xs + ww || row0 >= wh) return;
+    if (c_lo * 8 >= ww || row0 >= wh) return;
 
     // K-split part -> template chunk range [j0, j1) and row range [d0, d1)
     const int pjx = part % pj, pdx = part / pj;
@@ -448,7 +482,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     const int q = q0 + threadIdx.x;
     const int col = q / g.GB, gl = q - col * g.GB;
     const int grp = band * g.GB + gl;
-    const bool active = col < g.C && col * 8 < xs + ww && grp * CY < wh;
+    const bool active = col < g.C && col * 8 < ww && grp < g.G && grp * CY < wh;
     // warps without a single active tile (e.g. half of a track's last CTA) take no part in the template-slice ring and
     // leave right after setup: left in the loop they would spin on the slice barriers for the CTA's whole lifetime and
     // take issue slots from the co-resident CTA.  The `empty` barriers count the participating warps only.
@@ -471,12 +505,19 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         }
     }
     __syncthreads();  // barriers initialised before anybody polls them
-    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2] = gtime();
-    if (!warp_on) return;
-    mbar_wait(&bars[0], 0);
-    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 6) * 2 + 1] = gtime();
-
     const int P = g.boxW;
+    if (xs) {   // CTA-uniform.  Every warp (also those about to leave) takes its share of rows.
+        mbar_wait(&bars[0], 0);
+        if (xs == 1) shift_rows_left<1>(s_tile, P, g.boxH);
+        else if (xs == 2) shift_rows_left<2>(s_tile, P, g.boxH);
+        else shift_rows_left<3>(s_tile, P, g.boxH);
+        __syncthreads();
+        if (!warp_on) return;
+    } else {
+        if (!warp_on) return;
+        mbar_wait(&bars[0], 0);
+    }
+
     const float* base = s_tile + (size_t)(gl * CY) * P + (col - c_lo) * 8;
 
     float acc[CY][8];
@@ -576,13 +617,13 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
                     double d8[8];
 #pragma unroll
                     for (int cx = 0; cx < 8; ++cx) {
-                        const int x = col * 8 + cx - xs;
-                        d8[cx] = (x >= 0 && x < ww) ? __ldg(dn + y * ww + x) : 0.0;
+                        const int x = col * 8 + cx;
+                        d8[cx] = x < ww ? __ldg(dn + y * ww + x) : 0.0;
                     }
 #pragma unroll
                     for (int cx = 0; cx < 8; ++cx) {
-                        const int x = col * 8 + cx - xs;
-                        if (x >= 0 && x < ww) {
+                        const int x = col * 8 + cx;
+                        if (x < ww) {
                             const unsigned int idx = (unsigned int)(y * ww + x);
                             const float v = ncc_finalize(acc[i][cx], d8[cx], flat);
                             if (mp) mp[idx] = v;
@@ -606,6 +647,208 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     trace_end(c, step, TR_NCC);
 }
 
+// (3c) k_ncc_fringe: the candidates the thread-tile grid leaves out (TileCfg: the single column x = 8C and/or the
+//      single row y = CY*G -- both exist for the default 161 x 161 window), register-blocked like the search itself.
+//      A thread owns 8 consecutive candidates of the fringe row (8 x 1 tile) or of the fringe column (1 x 8 tile) and ONE
+//      template chunk: per template row it fetches the chunk's 8 template values (2 LDS.128) and
+//        row tile:    the 16-float window of that frame row (4 LDS.128)                 -> acc[cx] += w[k + cx] * t[k]
+//        column tile: ONE new 8-float frame row; the other seven stay in registers (2 LDS.128) -> acc[yy] += blk[yy][k] * t[k]
+//      i.e. 64 FMAs for 4 - 6 shared loads, eight independent chains per thread.  Every chain runs dy outer, k inner,
+//      exactly as in k_ncc_search; one thread per candidate finally adds the chunk results in k_ncc_search's order
+//      INCLUDING the K-split part structure (part p = pdx*pj + pjx covers template rows [d0, d1) of chunks [j0, j1);
+//      parts added in part order as k_ncc_finalize does): equal windows get equal scores wherever they are computed.
+//      A CTA takes up to FringeCfg.tpc tiles of one kind and one track; thread = (tile, chunk).  The strip of the gray
+//      plane the tiles cover and the centred template are staged in shared memory with cp.async (4-byte copies: the
+//      window origin has no alignment).  The strip pitch has an odd number of 16-byte groups, so lanes on consecutive
+//      strip rows (column tiles) read vectors without bank conflicts.
+//      Scheduling: in the throughput shape the kernel is launched right behind k_ncc_search with a programmatic
+//      dependency (it needs none of the search's results), so its CTAs start when the last search CTA has been
+//      dispatched and fill the SM slots that free up during the search's ragged last round.  In the latency shape it is
+//      a third graph branch beside the statistics and the search (FringeCfg.defer).
+//      Shared memory: strip | template [nchunk][th * 8 + 4] | chain results [nchunk][8 * tpc].
+__host__ __device__ inline int fringe_pitch(int sw)
+{
+    const int p = (sw + 3) & ~3;
+    return ((p >> 2) & 1) ? p : p + 4;
+}
+
+struct FringeCfg {
+    int tpc;             // tiles (of 8 candidates) per CTA
+    int colg, rowg;      // CTAs per track for the fringe column (ceil(ceil(Hmax / 8) / tpc)) and the fringe row; 0 = none
+    int strip_floats;    // shared floats reserved for the strip
+    int threads;         // tpc * (mtp / 8) rounded up to a warp
+    int defer;           // 1 (K-split / latency shape): grid.z = pd, a CTA computes ONE row part pdx = blockIdx.z and stores the
+                         //    raw partial cross terms of its parts to Ctx.fringe_acc; k_ncc_finalize adds them in part order and
+                         //    normalises, so the kernel needs no window statistics and runs beside them and the search
+};
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void load8(float (&d)[8], const float* p)
+{
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+constexpr int kFringeThreads = 256;
+__global__ void __launch_bounds__(kFringeThreads) k_ncc_fringe(Ctx c, TileCfg g, FringeCfg fc)
+{
+    extern __shared__ __align__(16) float sm_fr[];
+    __shared__ int s_d[34];                                         // K-split row bounds: part pdx covers rows [s_d[pdx], s_d[pdx+1])
+    const int track = blockIdx.y;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    // the window is derived here (not read from t.win): see k_ncc_search
+    int win[4];
+    {
+        const DevParams P = *c.params;
+        search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    }
+    trace_begin(c, step, TR_FRINGE);
+    const int ww = win[2], wh = win[3];
+    const int fx = 8 * g.C, fy = kCY * g.G;                        // the grid covers [0, fx) x [0, fy)
+    const bool is_col = (int)blockIdx.x < fc.colg;
+    const int grp = is_col ? blockIdx.x : blockIdx.x - fc.colg;
+    int n;                                                          // candidates of this kind
+    if (is_col) { if (ww <= fx) return; n = wh; }                   // (fx, y), y = 0 .. wh-1
+    else { if (wh <= fy) return; n = min(ww, fx); }                 // (x, fy), x = 0 .. min(ww, fx)-1
+    const int c0 = grp * fc.tpc * 8;
+    if (c0 >= n) return;
+    const int nc = min(fc.tpc * 8, n - c0), ntile = (nc + 7) >> 3;
+    const int th = t.h, tp = t.tp, nchunk = tp >> 3, pj = g.pj, pd = g.pd;
+    if ((int)threadIdx.x <= pd) s_d[threadIdx.x] = (th * (int)threadIdx.x) / pd;
+    const int pz = fc.defer ? (int)blockIdx.z : 0;                  // the row part this CTA computes (non-deferred: pd == 1)
+    // strip: window-relative origin (sx0, sy0), sw x sh floats; it spans the PADDED template width tp and whole tiles.
+    // Elements outside the frame are stored as 0 (they only meet masked candidates or zero template columns).
+    const int sx0 = is_col ? fx : c0, sy0 = is_col ? c0 : fy;
+    const int sw = is_col ? tp : ntile * 8 + tp, sh = is_col ? ntile * 8 + th - 1 : th;
+    const int SP = fringe_pitch(sw);
+    float* s_strip = sm_fr;
+    float* s_t = sm_fr + fc.strip_floats;
+    const int TS = th * 8 + 4;                                      // template chunk stride: lanes on consecutive chunks read
+                                                                    // consecutive 16-byte bank groups
+    float* s_r = s_t + (size_t)(c.mtp >> 3) * (c.mth * 8 + 4);
+    const int ncand_pad = fc.tpc * 8;
+    {
+        const int ax0 = win[0] + sx0, ay0 = win[1] + sy0;
+        const float* src = c.gray + (size_t)t.stream * c.plane + (size_t)ay0 * c.pitch + ax0;
+        const int nwarp = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        // only what this CTA's row part [d0, d1) touches (everything when there is a single part)
+        const int d0 = (th * pz) / pd, d1 = fc.defer ? (th * (pz + 1)) / pd : th;
+        const int r_lo = d0, r_hi = is_col ? min(sh, ntile * 8 + d1 - 1) : d1;
+        for (int r = r_lo + wid; r < r_hi; r += nwarp)
+            for (int x = lane; x < sw; x += 32) {
+                if (ay0 + r < c.H && ax0 + x < c.W) cp_async4(s_strip + r * SP + x, src + (size_t)r * c.pitch + x);
+                else s_strip[r * SP + x] = 0.f;
+            }
+        const float4* tsrc = reinterpret_cast<const float4*>(c.templc + (size_t)track * c.mth * c.mtp);
+        float4* tdst = reinterpret_cast<float4*>(s_t);
+        const int nq = (d1 - d0) * 2;                               // float4 per chunk
+        for (int i = threadIdx.x; i < nchunk * nq; i += blockDim.x) {
+            const int j = i / nq, q = d0 * 2 + (i - j * nq);
+            cp_async16(tdst + j * (TS >> 2) + q, tsrc + j * th * 2 + q);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    {
+        // thread = (chunk, tile), chunk fastest: neighbouring lanes read neighbouring 32-byte pieces of a strip row
+        const int nchm = c.mtp >> 3, j = threadIdx.x % nchm, tile = threadIdx.x / nchm;
+        if (tile < ntile && j < nchunk) {
+            const float* tj = s_t + (size_t)j * TS;
+            float* out = s_r + (size_t)j * ncand_pad + tile * 8;
+            if (!is_col) {
+                const float* base = s_strip + tile * 8 + j * 8;                  // 16-byte aligned: c0, tile*8, j*8 are multiples of 8
+                {
+                    const int pdx = pz;
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+                    for (int dy = s_d[pdx]; dy < s_d[pdx + 1]; ++dy) {
+                        float w[16], tt[8];
+                        load8(*reinterpret_cast<float(*)[8]>(w), base + dy * SP);
+                        load8(*reinterpret_cast<float(*)[8]>(w + 8), base + dy * SP + 8);
+                        load8(tt, tj + dy * 8);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+#pragma unroll
+                            for (int cx = 0; cx < 8; ++cx) acc[cx] = fmaf(w[k + cx], tt[k], acc[cx]);
+                    }
+                    *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+            } else {
+                const float* base = s_strip + (size_t)(tile * 8) * SP + j * 8;   // rows tile*8 + yy + dy
+                {
+                    const int pdx = pz;
+                    const int d0 = s_d[pdx], nd = s_d[pdx + 1] - d0;
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    float blk[8][8];                                             // ring of 8 frame rows, 8 floats each
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) load8(blk[r], base + (size_t)(d0 + r) * SP);
+#pragma unroll 1
+                    for (int e0 = 0; e0 < nd; e0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int e = e0 + u;
+                            if (e < nd) {
+                                load8(blk[(u + 7) & 7], base + (size_t)(d0 + e + 7) * SP);
+                                float tt[8];
+                                load8(tt, tj + (d0 + e) * 8);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                                    for (int yy = 0; yy < 8; ++yy) acc[yy] = fmaf(blk[(u + yy) & 7][k], tt[k], acc[yy]);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long key = 0ull;
+    for (int l = threadIdx.x; l < nc; l += blockDim.x) {
+        const int x = is_col ? fx : c0 + l, y = is_col ? c0 + l : fy;
+        if (fc.defer) {
+            // the parts (pjx, pz) of this candidate: chunk results added in chunk order, as a K-split search CTA does
+            const bool empty = s_d[pz + 1] <= s_d[pz];
+            for (int pjx = 0; pjx < pj; ++pjx) {
+                const int j0 = (nchunk * pjx) / pj, j1 = empty ? j0 : (nchunk * (pjx + 1)) / pj;
+                float pacc = 0.f;
+                for (int j = j0; j < j1; ++j) pacc += s_r[(size_t)j * ncand_pad + l];
+                c.fringe_acc[((size_t)track * pj * pd + (size_t)pz * pj + pjx) * (c.Hmax + c.Wmax) + (is_col ? y : c.Hmax + x)] = pacc;
+            }
+        } else {
+            float acc = 0.f;
+            for (int j = 0; j < nchunk; ++j) acc += s_r[(size_t)j * ncand_pad + l];
+            const unsigned int idx = (unsigned int)(y * ww + x);
+            const double dn = c.denom[(size_t)track * c.Hmax * c.Wmax + idx];
+            const float v = ncc_finalize(acc, dn, t.flat);
+            if (c.params->keep_maps) c.maps[(size_t)track * c.Hmax * c.Wmax + idx] = v;
+            const unsigned long long k2 = peak_key(v, idx);
+            key = k2 > key ? k2 : key;
+        }
+    }
+    if (!fc.defer) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            unsigned long long o = shfl_xor_u64(key, m);
+            key = o > key ? o : key;
+        }
+        if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+    }
+    trace_end(c, step, TR_FRINGE);
+}
+
 // Tail items' second stage (throughput mode): one CTA per tail item, thread = thread tile of k_ncc_search; adds the
 // tail_ps partial sums of its 8 x CY candidates in part order, then the same FP64 normalisation / peak epilogue.
 template <int CY>
@@ -616,11 +859,11 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
-    const int ww = t.win[2], wh = t.win[3], xs = t.win[0] & 3;
+    const int ww = t.win[2], wh = t.win[3];
     const int band = blk / g.ctas_band, q = (blk - band * g.ctas_band) * kTilesPerCta + threadIdx.x;
     const int col = q / g.GB, grp = band * g.GB + (q - col * g.GB);
     unsigned long long key = 0ull;
-    if (col < g.C && col * 8 < xs + ww && grp * CY < wh) {
+    if (col < g.C && col * 8 < ww && grp < g.G && grp * CY < wh) {
         float acc[CY][8];
 #pragma unroll
         for (int i = 0; i < CY; ++i)
@@ -648,13 +891,13 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
                 double d8[8];
 #pragma unroll
                 for (int cx = 0; cx < 8; ++cx) {
-                    const int x = col * 8 + cx - xs;
-                    d8[cx] = (x >= 0 && x < ww) ? __ldg(dn + y * ww + x) : 0.0;
+                    const int x = col * 8 + cx;
+                    d8[cx] = x < ww ? __ldg(dn + y * ww + x) : 0.0;
                 }
 #pragma unroll
                 for (int cx = 0; cx < 8; ++cx) {
-                    const int x = col * 8 + cx - xs;
-                    if (x >= 0 && x < ww) {
+                    const int x = col * 8 + cx;
+                    if (x < ww) {
                         const unsigned int idx = (unsigned int)(y * ww + x);
                         const float v = ncc_finalize(acc[i][cx], d8[cx], flat);
                         if (mp) mp[idx] = v;
@@ -691,22 +934,31 @@ __global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, TileCfg g)
         const int idx = blockIdx.x * blockDim.x + threadIdx.x;
         unsigned long long key = 0ull;
         if (idx < n) {
-            // candidate -> (thread tile, slot) of k_ncc_search: column-major tiles inside row bands
             const int y = idx / ww, x = idx - y * ww;
-            const int gx = x + (t.win[0] & 3), col = gx >> 3, cx = gx & 7;
-            const int grp = y / kCY, i = y - grp * kCY;
-            const int band = grp / g.GB, gl = grp - band * g.GB;
-            const size_t tile = (size_t)band * g.ctas_band * kTilesPerCta + (size_t)col * g.GB + gl;
-            const size_t tiles_track = (size_t)g.bands * g.ctas_band * kTilesPerCta;
-            const size_t off = ((size_t)track * tiles_track + tile) * (8 * kCY) + i * 8 + cx;
-            const size_t pstride = (size_t)c.max_tracks * tiles_track * (8 * kCY);
+            // where this candidate's partial cross terms are: (a) fringe candidate -> Ctx.fringe_acc, one float per part
+            // (k_ncc_fringe); (b) grid candidate -> (thread tile, slot) of k_ncc_search, column-major tiles inside row
+            // bands.  One common load loop, so that warps holding both kinds do not pay two L2 round trips.
+            const float* src;
+            size_t stride;
+            if (x >= 8 * g.C || y >= kCY * g.G) {
+                stride = (size_t)(c.Hmax + c.Wmax);
+                src = c.fringe_acc + (size_t)track * parts * stride + (x >= 8 * g.C ? y : c.Hmax + x);
+            } else {
+                const int col = x >> 3, cx = x & 7;
+                const int grp = y / kCY, i = y - grp * kCY;
+                const int band = grp / g.GB, gl = grp - band * g.GB;
+                const size_t tile = (size_t)band * g.ctas_band * kTilesPerCta + (size_t)col * g.GB + gl;
+                const size_t tiles_track = (size_t)g.bands * g.ctas_band * kTilesPerCta;
+                stride = (size_t)c.max_tracks * tiles_track * (8 * kCY);
+                src = c.partial + ((size_t)track * tiles_track + tile) * (8 * kCY) + i * 8 + cx;
+            }
             const size_t woff = (size_t)track * c.Hmax * c.Wmax;
             const double dnv = __ldg(c.denom + woff + idx);
             float acc = 0.f;
             for (int p0 = 0; p0 < parts; p0 += 16) {           // 16 independent loads in flight, added in part order
                 float pv[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) pv[k] = (p0 + k < parts) ? __ldg(c.partial + (size_t)(p0 + k) * pstride + off) : 0.f;
+                for (int k = 0; k < 16; ++k) pv[k] = (p0 + k < parts) ? __ldg(src + (size_t)(p0 + k) * stride) : 0.f;
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
                     if (p0 + k < parts) acc += pv[k];
@@ -882,6 +1134,7 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
             atomicAdd(c.macs, (unsigned long long)t.win[2] * t.win[3] * t.w * t.h);
+            atomicAdd(c.macs_grid, (unsigned long long)min(t.win[2], c.gridW) * min(t.win[3], c.gridH) * t.w * t.h);
             res->x = nx; res->y = ny; res->w = t.w; res->h = t.h;
             res->conf = val; res->moved = moved; res->updated = updated; res->searched = 1; res->valid = 1;
             res->track = track; res->step = (int32_t)step;

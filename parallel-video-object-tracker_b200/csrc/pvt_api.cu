@@ -59,13 +59,15 @@ struct pvt_ctx {
     size_t ncc_smem = 0;
     int rowsum_warps = 8, rowsum_pw = 0;
     int kps = 5;               // kernels per searched time step (for pvt_launch_count)
+    FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
+    size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
-    cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr;   // aux: second branch inside the captured graph
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr;   // aux, aux2: further branches inside the captured graph
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
-    cudaEvent_t pev[4][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class
+    cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
     bool graph_valid = false;
     std::vector<void*> allocs;
     FrameDesc* h_table = nullptr;  // pinned, [kRing][max_streams]
@@ -111,29 +113,63 @@ int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
 // CTAs run in rounds of 2 per SM; a round costs ~3 us of fixed latency (launch, TMA tile, partial-sum stores) plus the
 // per-thread FMA count over ~870 FMA/us (two warps per sub-partition) or ~1250 FMA/us (one); K-split adds the
 // second-stage reduction.  Smallest estimate wins; ties go to fewer parts, then taller bands.
-bool choose_plan(int sm_count, int n_tracks, int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
+// k_ncc_fringe geometry: tiles (of 8 candidates) per CTA and the largest K-split row-part count whose chain results
+// still fit its shared memory: strip | template | results [pd][chunks][8 * tpc].  Returns false when nothing fits
+// (then the thread-tile grid keeps the remainder and there is no fringe kernel).
+int fringe_strip_floats(int tpc, int mtp, int mth)
+{
+    const int col = (tpc * 8 + mth - 1) * fringe_pitch(mtp), row = mth * fringe_pitch(tpc * 8 + mtp);
+    return std::max(col, row);
+}
+bool fringe_plan(int mtp, int mth, int* tpc_out, int* pd_cap_out)
+{
+    const int nch = mtp / 8;
+    if (nch > kFringeThreads) return false;
+    const long long budget = 216 * 1024 / 4;
+    const int want[4] = {16, 8, 4, 1};   // prefer many tiles per CTA
+    for (int wi = 0; wi < 4; ++wi)
+        for (int tpc = std::min(kFringeThreads / nch, 24); tpc >= 1; --tpc) {
+            const long long left = budget - fringe_strip_floats(tpc, mtp, mth) - (long long)nch * (mth * 8 + 4);
+            // chain results: [chunks][8 * tpc] (a CTA computes one K-split row part)
+            if (left >= (long long)nch * tpc * 8 && tpc >= std::min(want[wi], 24)) {
+                *tpc_out = tpc;
+                *pd_cap_out = 32;
+                return true;
+            }
+        }
+    return false;
+}
+
+bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax, int Hmax, TileCfg* out, size_t* smem_out)
 {
     const int CY = kCY;
-    const int G = (Hmax + CY - 1) / CY, C = (Wmax + 3 + 7) / 8, nch = mtp / 8;
+    const int nch = mtp / 8;
+    // a remainder of exactly one row / column stays out of the thread-tile grid (k_ncc_fringe takes it): see TileCfg
+    int pd_cap = 0, tpc = 0;
+    (void)mtw;
+    const bool fringe_ok = fringe_plan(mtp, mth, &tpc, &pd_cap);
+    const int G = (fringe_ok && Hmax > CY && Hmax % CY == 1) ? Hmax / CY : (Hmax + CY - 1) / CY;
+    const int C = (fringe_ok && Wmax > 8 && Wmax % 8 == 1) ? Wmax / 8 : (Wmax + 7) / 8;
+    auto span_of = [C](int GB) { return std::min(C, kTilesPerCta % GB == 0 ? kTilesPerCta / GB : (kTilesPerCta - 1) / GB + 2); };
     const long long slots = (long long)sm_count * 2;
     double best = 1e300;
     // does the unsplit plan exist and fill at least one whole round?  then never K-split globally: the partial round at
     // the end is handled by tail splitting (pvt_create), which has none of the K-split's traffic
     bool unsplit_fills = false;
     {
-        const int boxH = G * CY + mth - 1, span = std::min(C, (kTilesPerCta - 1) / G + 2), boxW = 8 * span + mtp + 4;
+        const int boxH = G * CY + mth - 1, span = span_of(G), boxW = 8 * span + mtp + 4;
         const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
         const long long ctas = (long long)n_tracks * ((G * C + kTilesPerCta - 1) / kTilesPerCta);
         unsplit_fills = boxH <= 256 && boxW <= 256 && 2 * (smem + 1024) <= 228u * 1024u && ctas >= slots;
     }
     for (int pj = 1; pj <= (unsplit_fills ? 1 : nch); ++pj)
-        for (int pd = 1; pd <= (unsplit_fills ? 1 : std::min(mth, 32)); ++pd) {
+        for (int pd = 1; pd <= (unsplit_fills ? 1 : std::min(mth, fringe_ok ? pd_cap : 32)); ++pd) {
             const int nchp = (nch + pj - 1) / pj, ndp = (mth + pd - 1) / pd;
             if ((pj > 1 && (pj - 1) * nchp >= nch) || (pd > 1 && (pd - 1) * ndp >= mth)) continue;  // a part would be empty
             for (int GB = G; GB >= 1; --GB) {
                 const int boxH = GB * CY + ndp - 1;
                 if (boxH > 256) continue;
-                const int span = std::min(C, (kTilesPerCta - 1) / GB + 2);
+                const int span = span_of(GB);
                 const int boxW = 8 * span + 8 * nchp + 4;
                 if (boxW > 256) continue;
                 const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
@@ -212,12 +248,18 @@ int validate_params(const pvt_params* p)
     return PVT_OK;
 }
 
-enum { CLS_INGEST = 0, CLS_STATS = 1, CLS_NCC = 2, CLS_UPDATE = 3 };
+enum { CLS_INGEST = 0, CLS_STATS = 1, CLS_NCC = 2, CLS_UPDATE = 3, CLS_SEARCH_KERNEL = 4 };
 
 // PVT_DEBUG_SYNC=1: launch kernels directly (no graph), synchronise after each and name the one that faulted
 bool debug_sync()
 {
     static const bool on = [] { const char* e = getenv("PVT_DEBUG_SYNC"); return e && *e && *e != '0'; }();
+    return on;
+}
+// PVT_FRINGE_BRANCH=1 (experiments): k_ncc_fringe on a parallel low-priority graph branch instead of behind the search kernel
+bool fringe_branch()
+{
+    static const bool on = [] { const char* e = getenv("PVT_FRINGE_BRANCH"); return e && *e && *e != '0'; }();
     return on;
 }
 int dbg(pvt_ctx* c, const char* what)
@@ -273,17 +315,57 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
                (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), sstats>>>(d, c->rowsum_pw);
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
+    // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
+    const bool fringe = c->params.kernel != PVT_KERNEL_DIRECT && c->fringe.colg + c->fringe.rowg > 0;
+    const dim3 fgrid((unsigned)(c->fringe.colg + c->fringe.rowg), (unsigned)d.max_tracks, (unsigned)(c->fringe.defer ? c->tile.pd : 1));
     if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
     if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; }
+    bool join2 = false, fringe_after = false;
+    if (fringe) {
+        if (fork) {
+            // latency shape: a third branch from the same fork point; the cross terms are left in fringe_acc
+            // (FringeCfg.defer) and normalised by k_ncc_finalize, so this branch does not wait for the statistics
+            CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
+            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->aux2>>>(d, c->tile, c->fringe);
+            CK(cudaEventRecord(c->ev_join2, c->aux2));
+            join2 = true;
+        } else if (capturing && fringe_branch()) {
+            // throughput shape, experiment: after the statistics (the kernel normalises its own candidates), on a parallel branch
+            CK(cudaEventRecord(c->ev_fork2, c->compute));
+            CK(cudaStreamWaitEvent(c->aux2, c->ev_fork2, 0));
+            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->aux2>>>(d, c->tile, c->fringe);
+            CK(cudaEventRecord(c->ev_join2, c->aux2));
+            join2 = true;
+        } else if (capturing) {
+            fringe_after = true;   // throughput shape: right behind the search kernel with a programmatic dependency (below)
+        } else {
+            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->compute>>>(d, c->tile, c->fringe);
+            { int r = dbg(c, "k_ncc_fringe"); if (r) return r; }
+        }
+    }
     if (c->params.kernel == PVT_KERNEL_DIRECT) {
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else {
         const int parts = c->tile.pj * c->tile.pd;
         const unsigned nbx = (unsigned)(c->tile.n_full + c->tile.n_tail * std::max(c->tile.tail_ps, 1));
+        if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
         k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
+        if (fringe_after) {
+            // programmatic dependent launch: the fringe kernel may begin once all search CTAs have been dispatched
+            // (k_ncc_search issues griddepcontrol.launch_dependents first thing); it needs none of the search's results
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = fgrid; cfg.blockDim = dim3(c->fringe.threads); cfg.dynamicSmemBytes = c->fringe_smem; cfg.stream = c->compute;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = profile ? 0 : 1;   // the profiling graph times k_ncc_search alone
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, k_ncc_fringe, d, c->tile, c->fringe));
+        }
         if (c->tile.tail_ps > 1) k_ncc_tail_finalize<kCY><<<c->tile.n_tail, kTilesPerCta, 0, c->compute>>>(d, c->tile);
+        if (join2) CK(cudaStreamWaitEvent(c->compute, c->ev_join2, 0));   // the search class ends when the fringe has ended too
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
         if (parts > 1) {
@@ -426,6 +508,11 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             *acc[k] += ms;
             *cnt[k] += (k == CLS_STATS) ? 2 : 1;
         }
+        if (c->params.kernel != PVT_KERNEL_DIRECT) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->pev[CLS_SEARCH_KERNEL][0], c->pev[CLS_SEARCH_KERNEL][1]));
+            c->prof.search_kernel_ms += ms;
+        }
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
@@ -522,7 +609,7 @@ int pvt_destroy(pvt_ctx* c)
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
     if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
-    for (int k = 0; k < 4; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
+    for (int k = 0; k < 5; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_table) cudaFreeHost(c->h_table);
     if (c->h_results) cudaFreeHost(c->h_results);
@@ -534,7 +621,10 @@ int pvt_destroy(pvt_ctx* c)
     for (auto& p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
+    if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->aux2) cudaStreamDestroy(c->aux2);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -605,11 +695,18 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         }                                                                                             \
     } while (0)
 
-    CKD(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    // kernel nodes inherit the priority of the stream they were captured on: the branches that carry the fringe kernel
+    // (and, in the latency shape, the statistics) yield to the search kernel on the main stream
+    int prio_lo = 0, prio_hi = 0;
+    CKD(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CKD(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
     CKD(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-    CKD(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, prio_hi));
+    CKD(cudaStreamCreateWithPriority(&c->aux2, cudaStreamNonBlocking, prio_lo));
     CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     const size_t win = (size_t)d.Wmax * d.Hmax;
     CR(dev_alloc(c, &d.gray, d.plane * d.max_streams));
     CR(dev_alloc(c, &d.templ, (size_t)d.max_tracks * d.mth * d.mtw));
@@ -625,7 +722,8 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     CR(dev_alloc(c, &d.params, 1));
     CR(dev_alloc(c, &d.step, 1));
     CR(dev_alloc(c, &d.ticket, 1));
-    CR(dev_alloc(c, &d.macs, 1));
+    CR(dev_alloc(c, &d.macs, 2));
+    d.macs_grid = d.macs + 1;
     c->d_macs = d.macs;
     CR(dev_alloc(c, &c->d_trace, (size_t)kRing * 16));
     CKD(cudaHostAlloc((void**)&c->h_table, sizeof(FrameDesc) * kRing * d.max_streams, cudaHostAllocDefault));
@@ -635,25 +733,25 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CKD(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 4; ++k) { CKD(cudaEventCreate(&c->pev[k][0])); CKD(cudaEventCreate(&c->pev[k][1])); }
+    for (int k = 0; k < 5; ++k) { CKD(cudaEventCreate(&c->pev[k][0])); CKD(cudaEventCreate(&c->pev[k][1])); }
     CKD(cudaEventCreate(&c->timer_a));
     CKD(cudaEventCreate(&c->timer_b));
     c->stage.assign((size_t)d.max_streams * kStageDepth, nullptr);
     c->stage_bytes = (size_t)d.W * d.H * 4;
     c->track_stream.assign(d.max_tracks, -1);
 
-    if (!choose_plan(prop.multiProcessorCount, d.max_tracks, d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
+    if (!choose_plan(prop.multiProcessorCount, d.max_tracks, d.mtw, d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
         pvt_destroy(c);
         return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
     }
     if (const char* e = getenv("PVT_PLAN")) {  // experiments: "GB,pj,pd" overrides the planner
         int GB = 0, pj = 0, pd = 0;
-        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0) {
+        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
             TileCfg& g = c->tile;
             const int nch = d.mtp / 8, nchp = (nch + pj - 1) / pj, ndp = (d.mth + pd - 1) / pd;
             g.GB = std::min(GB, g.G); g.pj = pj; g.pd = pd;
             g.bands = (g.G + g.GB - 1) / g.GB; g.ctas_band = (g.GB * g.C + kTilesPerCta - 1) / kTilesPerCta;
-            g.span = std::min(g.C, (kTilesPerCta - 1) / g.GB + 2);
+            g.span = std::min(g.C, kTilesPerCta % g.GB == 0 ? kTilesPerCta / g.GB : (kTilesPerCta - 1) / g.GB + 2);
             g.boxW = 8 * g.span + 8 * nchp + 4; g.boxH = g.GB * kCY + ndp - 1;
             c->ncc_smem = (size_t)g.boxW * g.boxH * 4 + (size_t)4 * d.mth * 32 + 128;
             if (g.boxW > 256 || g.boxH > 256 || c->ncc_smem + 1024 > kSmemBudget) {
@@ -681,11 +779,36 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
         c->roi_ingest = params->ingest == PVT_INGEST_ROI || (params->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
     }
-    c->kps = 4 + ((c->tile.pj * c->tile.pd > 1) ? 1 : (c->tile.tail_ps > 1 ? 2 : 1));  // ingest, 2 stats, search, [tail] + update | finalize
+    d.gridW = 8 * c->tile.C;
+    d.gridH = kCY * c->tile.G;
+    {
+        int tpc = 1, pd_cap = 0;
+        const bool ok = fringe_plan(d.mtp, d.mth, &tpc, &pd_cap);
+        const int col_tiles = (d.Hmax + 7) / 8, row_tiles = (std::min(d.Wmax, 8 * c->tile.C) + 7) / 8;
+        tpc = std::max(1, std::min(tpc, std::max(col_tiles, row_tiles)));
+        c->fringe.tpc = tpc;
+        c->fringe.colg = d.Wmax > 8 * c->tile.C ? (col_tiles + tpc - 1) / tpc : 0;
+        c->fringe.rowg = d.Hmax > kCY * c->tile.G ? (row_tiles + tpc - 1) / tpc : 0;
+        c->fringe.strip_floats = fringe_strip_floats(tpc, d.mtp, d.mth);
+        c->fringe.threads = std::min(kFringeThreads, (tpc * (d.mtp / 8) + 31) & ~31);
+        if (c->fringe.colg + c->fringe.rowg > 0 && (!ok || c->tile.pd > pd_cap)) {
+            pvt_destroy(c);
+            return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe plan does not fit shared memory");
+        }
+    }
+    c->fringe.defer = c->tile.pj * c->tile.pd > 1 ? 1 : 0;
+    if (c->fringe.defer && c->fringe.colg + c->fringe.rowg > 0)
+        CR(dev_alloc(c, &d.fringe_acc, (size_t)d.max_tracks * c->tile.pj * c->tile.pd * (d.Hmax + d.Wmax)));
+    c->fringe_smem = ((size_t)c->fringe.strip_floats + (size_t)(d.mtp / 8) * (d.mth * 8 + 4) + (size_t)(d.mtp / 8) * c->fringe.tpc * 8) * sizeof(float);
+    if (c->fringe.colg + c->fringe.rowg > 0) {
+        if (c->fringe_smem > 220u * 1024u) { pvt_destroy(c); return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe does not fit shared memory"); }
+        CKD(cudaFuncSetAttribute(k_ncc_fringe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fringe_smem));
+    }
+    c->kps = 4 + ((c->tile.pj * c->tile.pd > 1) ? 1 : (c->tile.tail_ps > 1 ? 2 : 1)) + (c->fringe.colg + c->fringe.rowg > 0 ? 1 : 0);  // ingest, 2 stats, search, [fringe], [tail] + update | finalize
     if (getenv("PVT_DEBUG_PLAN"))
-        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu | items full=%d tail=%d x%d\n",
+        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu | items full=%d tail=%d x%d | fringe ctas %d+%d x %d thr, %d tiles/cta, smem %zu\n",
                 d.max_tracks, c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH,
-                c->tile.pj, c->tile.pd, c->ncc_smem, c->tile.n_full, c->tile.n_tail, c->tile.tail_ps);
+                c->tile.pj, c->tile.pd, c->ncc_smem, c->tile.n_full, c->tile.n_tail, c->tile.tail_ps, c->fringe.colg, c->fringe.rowg, c->fringe.threads, c->fringe.tpc, c->fringe_smem);
     if (c->tile.tail_ps > 1)           // tail items' partial cross terms: [tail part][128 tiles][8 * kCY]
         CR(dev_alloc(c, &d.partial, (size_t)c->tile.n_tail * c->tile.tail_ps * kTilesPerCta * 8 * kCY, false));
     if (c->tile.pj * c->tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
@@ -703,6 +826,21 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CKD(cudaFuncSetAttribute(k_ncc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
         CKD(cudaFuncSetAttribute(k_track_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
         CKD(cudaFuncSetAttribute(k_track_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+    }
+    // every kernel of the step graph asks for the same (maximum) shared-memory carve-out: an SM has to drain before its
+    // L1 / shared split can change, which would serialise kernels that could otherwise overlap (search || fringe || statistics)
+    {
+        const int mx = (int)cudaSharedmemCarveoutMaxShared;
+        CKD(cudaFuncSetAttribute(k_ingest, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_ingest_roi, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_colprefix, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_ncc_fringe, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_ncc_tail_finalize<kCY>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_ncc_finalize, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_update, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        CKD(cudaFuncSetAttribute(k_hold, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
     }
     CR(encode_tmap(c));
     CR(upload_params(c));
@@ -1111,13 +1249,14 @@ int pvt_profile_get(pvt_ctx* c, pvt_profile* out, int reset)
     CK(cudaSetDevice(c->cfg.device));
     int r = resolve_profile(c);
     if (r) return r;
-    unsigned long long macs = 0;
-    CK(cudaMemcpy(&macs, c->d_macs, sizeof(macs), cudaMemcpyDeviceToHost));
-    c->prof.ncc_macs = (double)macs;
+    unsigned long long macs[2] = {0, 0};
+    CK(cudaMemcpy(macs, c->d_macs, sizeof(macs), cudaMemcpyDeviceToHost));
+    c->prof.ncc_macs = (double)macs[0];
+    c->prof.search_kernel_macs = (double)macs[1];
     *out = c->prof;
     if (reset) {
         c->prof = pvt_profile{};
-        CK(cudaMemsetAsync(c->d_macs, 0, sizeof(unsigned long long), c->compute));
+        CK(cudaMemsetAsync(c->d_macs, 0, 2 * sizeof(unsigned long long), c->compute));
         CK(cudaStreamSynchronize(c->compute));
     }
     return PVT_OK;

@@ -72,6 +72,7 @@ struct Ctx {
     double* denom;
     float* maps;
     float* partial;            // [parts][max_tracks][tiles][8*kCY] K-split partial cross terms, tile-major
+    float* fringe_acc;         // [max_tracks][parts][Hmax + Wmax] partial cross terms of the fringe column (by y) and row (by x), K-split mode
     TrackState* tracks;
     FrameDesc* table;
     SeqDesc* seq;
@@ -80,6 +81,8 @@ struct Ctx {
     unsigned long long* step;  // device-side time-step counter (advanced by the update kernel)
     unsigned int* ticket;      // tracks whose update is done in this step (the last one advances the step counter)
     unsigned long long* macs;  // algorithmic MACs searched so far (n_cand * tw * th per track per step)
+    unsigned long long* macs_grid;  // the share of them inside k_ncc_search's thread-tile grid (gridW x gridH candidates)
+    int gridW, gridH;          // 8 * TileCfg.C, kCY * TileCfg.G
     unsigned long long* trace; // optional [kRing][8 kernels][2] globaltimer stamps (first CTA start, last CTA end); NULL = off
 };
 
@@ -124,7 +127,7 @@ __device__ __forceinline__ unsigned long long peak_key(float v, unsigned int idx
 }
 
 // ---- optional device-side timeline (pvt_trace_enable): first-CTA start and last-CTA end of every kernel, per step
-enum { TR_INGEST = 0, TR_COLPREFIX = 1, TR_ROWSUM = 2, TR_NCC = 3, TR_FINALIZE = 4, TR_UPDATE = 5 };
+enum { TR_INGEST = 0, TR_COLPREFIX = 1, TR_ROWSUM = 2, TR_NCC = 3, TR_FINALIZE = 4, TR_UPDATE = 5, TR_FRINGE = 6 };
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;
