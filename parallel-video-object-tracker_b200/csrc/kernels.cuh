@@ -388,15 +388,22 @@ __device__ __forceinline__ void shift_rows_left(float* tile, int P, int rows)
     const int nv = P >> 2;
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         float4* row = reinterpret_cast<float4*>(tile + (size_t)r * P);
-        float4 cur = row[0];
-        for (int m = 0; m + 1 < nv; ++m) {
-            const float4 nxt = row[m + 1];
-            float4 o;
-            if (S == 1) o = make_float4(cur.y, cur.z, cur.w, nxt.x);
-            else if (S == 2) o = make_float4(cur.z, cur.w, nxt.x, nxt.y);
-            else o = make_float4(cur.w, nxt.x, nxt.y, nxt.z);
-            row[m] = o;
-            cur = nxt;
+        // eight vectors are read before the seven they produce are written: the shared-memory latency is paid once per
+        // batch, not once per vector (the loop is latency-bound otherwise)
+        for (int m0 = 0; m0 + 1 < nv; m0 += 7) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (m0 + k < nv) ? row[m0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                if (m0 + k + 1 < nv) {
+                    float4 o;
+                    if (S == 1) o = make_float4(v[k].y, v[k].z, v[k].w, v[k + 1].x);
+                    else if (S == 2) o = make_float4(v[k].z, v[k].w, v[k + 1].x, v[k + 1].y);
+                    else o = make_float4(v[k].w, v[k + 1].x, v[k + 1].y, v[k + 1].z);
+                    row[m0 + k] = o;
+                }
+            }
         }
     }
 }
@@ -589,7 +596,6 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done with the slice
     }
 
-    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 7) * 2] = gtime();
     unsigned long long key = 0ull;
     if (active) {
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;
@@ -643,7 +649,6 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         }
         if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
     }
-    if (c.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) c.trace[((step % kRing) * 8 + 7) * 2 + 1] = gtime();
     trace_end(c, step, TR_NCC);
 }
 
@@ -859,6 +864,7 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
+    trace_begin(c, step, TR_TAIL);
     const int ww = t.win[2], wh = t.win[3];
     const int band = blk / g.ctas_band, q = (blk - band * g.ctas_band) * kTilesPerCta + threadIdx.x;
     const int col = q / g.GB, grp = band * g.GB + (q - col * g.GB);
@@ -914,6 +920,7 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
         key = o > key ? o : key;
     }
     if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
+    trace_end(c, step, TR_TAIL);
 }
 
 // K-split second stage: add the parts' partial sums in part order, normalise, pick the peak.

@@ -827,21 +827,6 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CKD(cudaFuncSetAttribute(k_track_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
         CKD(cudaFuncSetAttribute(k_track_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
     }
-    // every kernel of the step graph asks for the same (maximum) shared-memory carve-out: an SM has to drain before its
-    // L1 / shared split can change, which would serialise kernels that could otherwise overlap (search || fringe || statistics)
-    {
-        const int mx = (int)cudaSharedmemCarveoutMaxShared;
-        CKD(cudaFuncSetAttribute(k_ingest, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_ingest_roi, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_colprefix, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_ncc_fringe, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_ncc_tail_finalize<kCY>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_ncc_finalize, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_update, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        CKD(cudaFuncSetAttribute(k_hold, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-    }
     CR(encode_tmap(c));
     CR(upload_params(c));
     CR(upload_seq(c, 0, kRing, 0));

@@ -127,7 +127,7 @@ __device__ __forceinline__ unsigned long long peak_key(float v, unsigned int idx
 }
 
 // ---- optional device-side timeline (pvt_trace_enable): first-CTA start and last-CTA end of every kernel, per step
-enum { TR_INGEST = 0, TR_COLPREFIX = 1, TR_ROWSUM = 2, TR_NCC = 3, TR_FINALIZE = 4, TR_UPDATE = 5, TR_FRINGE = 6 };
+enum { TR_INGEST = 0, TR_COLPREFIX = 1, TR_ROWSUM = 2, TR_NCC = 3, TR_FINALIZE = 4, TR_UPDATE = 5, TR_FRINGE = 6, TR_TAIL = 7 };
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;

@@ -19,7 +19,7 @@ tr.trace_enable(True)
 tr.submit_sequence(64, sh(1)); tr.sync()
 tr.timer_start(); tr.submit_sequence(64, sh(65)); ms = tr.timer_stop()
 T = tr.trace_get(64).astype(np.int64)
-names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe"]
+names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe", "ncc_tail_finalize"]
 T = T[8:]                                     # skip the first steps
 t0 = T[:, 0, 0:1]
 print("%s: %.2f us/step (events); step-to-step %.2f us (trace)" % (wname, 1e3 * ms / 64, np.median(np.diff(T[:, 0, 0])) / 1e3))
@@ -29,9 +29,5 @@ for k, nm in enumerate(names):
     st = np.median(T[:, k, 0] - T[:, 0, 0]) / 1e3; en = np.median(T[:, k, 1] - T[:, 0, 0]) / 1e3
     print("  %-13s start %7.2f  end %7.2f  dur %6.2f us  gap-before %6.2f" % (nm, st, en, en - st, st - prev_end if prev_end is not None else 0.0))
     prev_end = en
-if T[:, 7, 0].any():
-    b = T[:, 3, 0]
-    print("  ncc_search CTA(0,0,0): compute-done +%.2f  epilogue-done +%.2f us (from kernel start)" % tuple(
-        np.median(x - b) / 1e3 for x in (T[:, 7, 0], T[:, 7, 1])))
 nxt = np.median(T[1:, 0, 0] - T[:-1, 5, 1]) / 1e3
 print("  gap to next step's ingest: %.2f us" % nxt)
