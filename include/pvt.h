@@ -16,6 +16,7 @@
  *   tracker/src/main.cpp:103-161               NCC -> window clamp -> minMaxLoc -> gates -> addWeighted -> pvt_step / pvt_submit
  *   tracker/src/main.cpp:115-130               --batch=N hold semantics                 -> pvt_params.mode == PVT_MODE_BATCH
  *   tracker/src/baseline_kernel.cu:12-18       checkCuda -> exit(1)                     -> negative return code + pvt_last_error()
+ *   tracker_ghc/src/main.cpp:17-23,183-239     lost-object logic: whole-frame re-acquisition -> pvt_params.lost_frame_threshold / ncc_global_confidence
  *
  * Results follow the reference's `--cpu` path (cv::matchTemplate TM_CCOEFF_NORMED, OpenCV 4.13.0):
  * identical peak per frame (ties -> lowest row-major index), scores within 1e-4, identical bbox
@@ -40,7 +41,7 @@ extern "C" {
 #define PVT_API
 #endif
 
-#define PVT_VERSION 100
+#define PVT_VERSION 101
 
 /* return codes */
 #define PVT_OK               0
@@ -88,7 +89,14 @@ typedef struct pvt_params {
     int kernel;                   /* pvt_kernel */
     int keep_maps;                /* != 0: keep every track's last window map for pvt_get_window_map (tests) */
     int ingest;                   /* pvt_ingest */
-    int reserved[3];
+    /* lost-object re-acquisition, tracker_ghc/src/main.cpp:17-23,143-144,183-239 (the second tracker of the reference).
+     * 0 = off (tracker/src/main.cpp semantics).  > 0: after that many consecutive frames below the confidence
+     * threshold the track is searched over the WHOLE frame (global arg-max of the full NCC map) and only accepted
+     * at ncc_global_confidence; once found it returns to the local window.  Must be chosen at pvt_create (it sizes
+     * the whole-frame scratch: ~53 MB per track at 1080p); the value may be changed later while it stays > 0. */
+    int lost_frame_threshold;     /* LOST_FRAME_THRESHOLD = 50 in tracker_ghc */
+    int reserved[2];
+    double ncc_global_confidence; /* NCC_GLOBAL_CONFIDENCE = 0.60 in tracker_ghc */
 } pvt_params;
 
 typedef struct pvt_config {
@@ -120,7 +128,7 @@ typedef struct pvt_result {
     float conf;         /* bestVal of main.cpp:150 (NaN when the frame was held in batch mode) */
     uint8_t moved;      /* conf >= ncc_min_confidence    (main.cpp:153) */
     uint8_t updated;    /* conf >= ncc_strong_confidence (main.cpp:157): template EMA applied */
-    uint8_t searched;   /* 0 for frames held by batch mode */
+    uint8_t searched;   /* 0 for frames held by batch mode, 1 local window search, 2 whole-frame search (lost-object mode) */
     uint8_t valid;      /* track was active and its stream had a frame */
     int32_t track;
     int32_t step;       /* time-step index since creation */
@@ -146,6 +154,7 @@ PVT_API int pvt_device_count(void);       /* >= 0, or PVT_ERR_CUDA */
 PVT_API int pvt_device_info(int device, int* sm_count, int* sm_clock_khz, int* mem_clock_khz, size_t* mem_bytes, int* cc);
 
 PVT_API void pvt_default_params(pvt_params* p); /* the constants of main.cpp:6-20 */
+PVT_API void pvt_default_params_ghc(pvt_params* p); /* the constants of tracker_ghc/src/main.cpp:9-23 (radius 60, lost-object mode on) */
 PVT_API int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* config);
 PVT_API int pvt_destroy(pvt_ctx* ctx);
 PVT_API int pvt_set_params(pvt_ctx* ctx, const pvt_params* params); /* radii must stay <= the creation maxima */
@@ -178,6 +187,9 @@ PVT_API int pvt_sync(pvt_ctx* ctx);
 /* tracker state = {bbox, template} (the reference keeps it in host variables, main.cpp:63-71) */
 PVT_API int pvt_get_state(pvt_ctx* ctx, int track, int32_t bbox[4], float* templ, size_t templ_step_bytes);
 PVT_API int pvt_set_state(pvt_ctx* ctx, int track, const int32_t bbox[4], const float* templ, size_t templ_step_bytes);
+/* lost-object state of a track (tracker_ghc/src/main.cpp:143-144 lost_frame_count, use_global_search), for checkpoint / resume */
+PVT_API int pvt_get_lost_state(pvt_ctx* ctx, int track, int* lost_frame_count, int* use_global_search);
+PVT_API int pvt_set_lost_state(pvt_ctx* ctx, int track, int lost_frame_count, int use_global_search);
 /* last window map of a track (needs params.keep_maps): win = {minTx, minTy, width, height} (main.cpp:143-147) */
 PVT_API int pvt_get_window_map(pvt_ctx* ctx, int track, float* out, size_t out_step_bytes, int32_t win[4]);
 
@@ -199,7 +211,7 @@ PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA eve
 PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);
 /* device-side timeline: with tracing on, every kernel stamps %globaltimer (ns) at its first CTA's start and last
  * CTA's end; pvt_trace_get copies the stamps of the last <= 64 steps: out[step][8 kernel slots][2], slots =
- * ingest, colprefix, rowsum, ncc_search, ncc_finalize, update.  Returns the number of steps written. */
+ * ingest, colprefix, rowsum, ncc_search, ncc_finalize, update, ncc_fringe, ncc_tail_finalize.  Returns the number of steps written. */
 PVT_API int pvt_trace_enable(pvt_ctx* ctx, int on);
 PVT_API int pvt_trace_get(pvt_ctx* ctx, uint64_t* out, int max_steps);
 PVT_API int64_t pvt_launch_count(pvt_ctx* ctx); /* kernels launched by this context so far (graph nodes counted per launch) */

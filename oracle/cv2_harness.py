@@ -12,6 +12,7 @@ OpenCV's; only the driver loop is restated:
     minMaxLoc on the ROI tracker/src/main.cpp:147-151
     gates + EMA          tracker/src/main.cpp:153-161
     batch hold semantics tracker/src/main.cpp:115-130  (only the N-th frame is searched)
+    lost-object logic    tracker_ghc/src/main.cpp:145-239 (track_clip_ghc: whole-frame re-acquisition)
 
 Uses: (1) generating the golden fixtures in tests/golden/ (make_golden.py),
 (2) the `cpu_baseline` / `--impl reference` legs of bench.py, timed on the
@@ -115,3 +116,61 @@ def track_clip(frames, roi, rx=SEARCH_RADIUS_X, ry=SEARCH_RADIUS_Y,
         timing["t_gray"] = t_gray        # toGrayF32, outside t_tot in the reference
         timing["frames"] = len(frames) - 1
     return {"records": np.array(recs, dtype=np.float64), "maps": maps, "templ": templ}
+
+
+# tracker_ghc/src/main.cpp:9-23
+GHC_SEARCH_RADIUS = 60
+NCC_GLOBAL_CONFIDENCE = 0.60
+LOST_FRAME_THRESHOLD = 50
+
+
+def _bbox_outside(x, y, w, h, fw, fh):
+    """tracker_ghc/src/main.cpp:49-55 isBboxOutsideFrame."""
+    cx, cy = x + w // 2, y + h // 2
+    return (cx < 0 or cx >= fw or cy < 0 or cy >= fh) or (x + w < 0 or x >= fw or y + h < 0 or y >= fh)
+
+
+def track_clip_ghc(frames, roi, rx=GHC_SEARCH_RADIUS, ry=GHC_SEARCH_RADIUS, min_conf=NCC_MIN_CONFIDENCE,
+                   global_conf=NCC_GLOBAL_CONFIDENCE, strong_conf=NCC_STRONG_CONFIDENCE, lr=TEMPLATE_UPDATE_LR,
+                   lost_threshold=LOST_FRAME_THRESHOLD):
+    """tracker_ghc/src/main.cpp:145-239 (mode "cpu") with cv2: full-frame matchTemplate, then either the local window
+    or the whole map.  records = [n-1, 10]: x y w h conf moved updated searched(1 local, 2 whole map) lost_count use_global."""
+    x, y, w, h = roi
+    g = to_gray_f32(frames[0])
+    templ = g[y:y + h, x:x + w].copy()
+    lost, use_global, recs = 0, False, []
+    for k in range(1, len(frames)):
+        g = to_gray_f32(frames[k])
+        fh, fw = g.shape
+        ncc = cv2.matchTemplate(g, templ, cv2.TM_CCOEFF_NORMED)
+        outH, outW = ncc.shape
+        if _bbox_outside(x, y, w, h, fw, fh) or lost >= lost_threshold:
+            use_global = True
+        if use_global:
+            _, bestVal, _, bestLoc = cv2.minMaxLoc(ncc)
+            bx, by = bestLoc
+        else:
+            minTx, minTy, ww, wh = search_window(x, y, w, h, outW, outH, rx, ry)
+            if ww > 0 and wh > 0:
+                _, bestVal, _, bestLoc = cv2.minMaxLoc(ncc[minTy:minTy + wh, minTx:minTx + ww])
+                bx, by = bestLoc[0] + minTx, bestLoc[1] + minTy
+            else:
+                _, bestVal, _, bestLoc = cv2.minMaxLoc(ncc)
+                bx, by = bestLoc
+        searched = 2 if use_global else 1
+        thr = global_conf if use_global else min_conf
+        moved = updated = 0
+        if bestVal >= thr:
+            x, y = bx, by
+            moved = 1
+            lost = 0
+            if not _bbox_outside(x, y, w, h, fw, fh):
+                use_global = False
+            if bestVal >= strong_conf:
+                patch = g[y:y + h, x:x + w].copy()
+                cv2.addWeighted(templ, 1 - lr, patch, lr, 0.0, templ)
+                updated = 1
+        else:
+            lost += 1
+        recs.append((x, y, w, h, bestVal, moved, updated, searched, lost, int(use_global)))
+    return {"records": np.array(recs, dtype=np.float64), "templ": templ}

@@ -10,6 +10,7 @@
  *     baseline::ncc_match_cpu           /root/reference/tracker/src/ncc_cpu.cpp:5-13
  *     window clamp / peak / gate / EMA  /root/reference/tracker/src/main.cpp:135-161
  *     batch hold semantics              /root/reference/tracker/src/main.cpp:115-130
+ *     lost-object re-acquisition        /root/reference/tracker_ghc/src/main.cpp:17-23,143-144,183-239 (orc_track_clip_ghc)
  * and every arithmetic call on it lands in a THIRD-PARTY dependency that is not vendored under
  * /root/reference: OpenCV (imgproc/core), pinned at 4.13.0 by tracker/Makefile:19-27
  * (opencv_core4130.lib ...).  The functions below restate OpenCV 4.13.0's published algorithms
@@ -366,6 +367,86 @@ ORC_API int orc_track_clip(const uint8_t* frames, int n, int fw, int fh,
         rc = orc_track_step(gray, fw, fh, templ, tw, th, &x, &y, rx, ry, min_conf, strong_conf, lr, rec, NULL, NULL);
     }
     if (templ_out) memcpy(templ_out, templ, sizeof(float) * (size_t)tw * th);
+    free(gray);
+    free(templ);
+    return rc;
+}
+
+/* ---- tracker_ghc: the second tracker of the reference, with lost-object re-acquisition ---------
+ * tracker_ghc/src/main.cpp:145-239 (demo loop; the record loop :330-410 is the same logic), mode "cpu".
+ * State: lost_frame_count, use_global_search (:143-144).  Per frame:
+ *   :181   bbox_outside = isBboxOutsideFrame(curr_bbox) (:49-55) -- the box always comes from a position of the NCC map,
+ *          so its centre is inside the frame; evaluated anyway, as the reference does
+ *   :183   if (bbox_outside || lost_frame_count >= LOST_FRAME_THRESHOLD) use_global_search = true
+ *   :186   global: minMaxLoc over the WHOLE map; else the local window (:195-203) -- same clamp as tracker/
+ *   :217   threshold = use_global_search ? NCC_GLOBAL_CONFIDENCE : NCC_MIN_CONFIDENCE
+ *   :218   found: move, lost_frame_count = 0, use_global_search = false (box inside), EMA if >= NCC_STRONG_CONFIDENCE
+ *   :236   else lost_frame_count++
+ * searched = 1 local window, 2 whole map. */
+typedef struct orc_record_ghc {
+    int x, y, w, h;
+    float conf;
+    int moved, updated, searched, lost_count, use_global;
+} orc_record_ghc;
+
+static int bbox_outside_frame(int x, int y, int w, int h, int fw, int fh)
+{
+    int cx = x + w / 2, cy = y + h / 2;
+    return (cx < 0 || cx >= fw || cy < 0 || cy >= fh) || (x + w < 0 || x >= fw || y + h < 0 || y >= fh);
+}
+
+ORC_API int orc_track_clip_ghc(const uint8_t* frames, int n, int fw, int fh,
+                               int x, int y, int tw, int th, int rx, int ry,
+                               double min_conf, double global_conf, double strong_conf, double lr, int lost_threshold,
+                               orc_record_ghc* recs, float* templ_out)
+{
+    size_t fbytes = (size_t)fw * fh * 3;
+    int outW = fw - tw + 1, outH = fh - th + 1;
+    if (outW <= 0 || outH <= 0) return -1;
+    float* gray = (float*)malloc(sizeof(float) * (size_t)fw * fh);
+    float* templ = (float*)malloc(sizeof(float) * (size_t)tw * th);
+    float* map = (float*)malloc(sizeof(float) * (size_t)outW * outH);
+    orc_to_gray_f32(frames, fw, fh, (size_t)fw * 3, gray, sizeof(float) * (size_t)fw);
+    for (int r = 0; r < th; ++r) memcpy(templ + (size_t)r * tw, gray + (size_t)(y + r) * fw + x, sizeof(float) * tw);
+    int lost = 0, use_global = 0, rc = 0;
+    for (int k = 1; k < n && !rc; ++k) {
+        orc_record_ghc* rec = recs + (k - 1);
+        orc_to_gray_f32(frames + fbytes * k, fw, fh, (size_t)fw * 3, gray, sizeof(float) * (size_t)fw);
+        if (bbox_outside_frame(x, y, tw, th, fw, fh) || lost >= lost_threshold) use_global = 1;
+        int win[4] = {0, 0, outW, outH};
+        if (!use_global) {
+            orc_search_window(x, y, tw, th, outW, outH, rx, ry, win);
+            if (win[2] <= 0 || win[3] <= 0) { win[0] = 0; win[1] = 0; win[2] = outW; win[3] = outH; }   /* :204-210 fallback */
+        }
+        /* only the searched part of the map is needed: every cell of the map is independent of the others */
+        rc = orc_ncc_window(gray, fw, fh, sizeof(float) * (size_t)fw, templ, tw, th, sizeof(float) * (size_t)tw,
+                            win[0], win[1], win[2], win[3], map, sizeof(float) * (size_t)win[2]);
+        if (rc) break;
+        double best; int lx, ly;
+        orc_max_loc(map, win[2], win[3], sizeof(float) * (size_t)win[2], &best, &lx, &ly);
+        const int searched = use_global ? 2 : 1;
+        const double thr = use_global ? global_conf : min_conf;
+        int moved = 0, updated = 0;
+        if (best >= thr) {
+            x = lx + win[0]; y = ly + win[1];
+            moved = 1;
+            lost = 0;
+            if (!bbox_outside_frame(x, y, tw, th, fw, fh)) use_global = 0;
+            if (best >= strong_conf) {
+                float* patch = (float*)malloc(sizeof(float) * (size_t)tw * th);
+                for (int r = 0; r < th; ++r) memcpy(patch + (size_t)r * tw, gray + (size_t)(y + r) * fw + x, sizeof(float) * tw);
+                orc_add_weighted(templ, patch, tw * th, 1 - lr, lr);
+                free(patch);
+                updated = 1;
+            }
+        } else {
+            lost++;
+        }
+        rec->x = x; rec->y = y; rec->w = tw; rec->h = th; rec->conf = (float)best;
+        rec->moved = moved; rec->updated = updated; rec->searched = searched; rec->lost_count = lost; rec->use_global = use_global;
+    }
+    if (templ_out) memcpy(templ_out, templ, sizeof(float) * (size_t)tw * th);
+    free(map);
     free(gray);
     free(templ);
     return rc;

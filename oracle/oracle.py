@@ -145,3 +145,26 @@ def track_clip(frames: np.ndarray, roi, rx=80, ry=80, min_conf=0.40, strong_conf
         raise ValueError(f"orc_track_clip rc={rc}")
     out = np.array([(r.x, r.y, r.w, r.h, r.conf, r.moved, r.updated, r.searched) for r in recs], np.float64)
     return out, templ
+
+
+class RecordGhc(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int), ("conf", C.c_float),
+                ("moved", C.c_int), ("updated", C.c_int), ("searched", C.c_int), ("lost_count", C.c_int), ("use_global", C.c_int)]
+
+
+def track_clip_ghc(frames: np.ndarray, roi, rx=60, ry=60, min_conf=0.40, global_conf=0.60, strong_conf=0.70, lr=0.10,
+                   lost_threshold=50):
+    """tracker_ghc/src/main.cpp:145-239 over a whole clip; returns (records[n-1,10] float64: x y w h conf moved updated
+    searched(1 local, 2 whole map) lost_count use_global, final template)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, fh, fw, _ = frames.shape
+    x, y, tw, th = roi
+    recs = (RecordGhc * (n - 1))()
+    templ = np.empty((th, tw), np.float32)
+    rc = lib().orc_track_clip_ghc(_p(frames), C.c_int(n), C.c_int(fw), C.c_int(fh), C.c_int(x), C.c_int(y), C.c_int(tw), C.c_int(th),
+                                  C.c_int(rx), C.c_int(ry), C.c_double(min_conf), C.c_double(global_conf), C.c_double(strong_conf),
+                                  C.c_double(lr), C.c_int(lost_threshold), recs, _p(templ))
+    if rc:
+        raise ValueError(f"orc_track_clip_ghc rc={rc}")
+    out = np.array([(r.x, r.y, r.w, r.h, r.conf, r.moved, r.updated, r.searched, r.lost_count, r.use_global) for r in recs], np.float64)
+    return out, templ

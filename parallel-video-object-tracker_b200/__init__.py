@@ -37,6 +37,7 @@ SYMBOLS = [
     "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
+    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state",
 ]
 
 
@@ -44,7 +45,8 @@ class Params(C.Structure):
     _fields_ = [("search_radius_x", C.c_int), ("search_radius_y", C.c_int),
                 ("ncc_min_confidence", C.c_double), ("ncc_strong_confidence", C.c_double),
                 ("template_update_lr", C.c_double), ("batch_size", C.c_int), ("mode", C.c_int),
-                ("kernel", C.c_int), ("keep_maps", C.c_int), ("ingest", C.c_int), ("reserved", C.c_int * 3)]
+                ("kernel", C.c_int), ("keep_maps", C.c_int), ("ingest", C.c_int), ("lost_frame_threshold", C.c_int),
+                ("reserved", C.c_int * 2), ("ncc_global_confidence", C.c_double)]
 
 
 class Config(C.Structure):
@@ -112,6 +114,8 @@ def lib():
     L.pvt_submit_sequence.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Frame), C.c_int, C.c_int, C.c_void_p]
     L.pvt_get_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t]
     L.pvt_set_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t]
+    L.pvt_get_lost_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pvt_set_lost_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.pvt_get_window_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
     L.pvt_to_gray_f32.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_size_t, C.c_int]
     L.pvt_ncc_match.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
@@ -136,9 +140,10 @@ def _ck(rc):
     return rc
 
 
-def default_params(**kw) -> Params:
+def default_params(ghc=False, **kw) -> Params:
+    """tracker/src/main.cpp:6-20 constants, or (ghc=True) those of tracker_ghc/src/main.cpp:9-23 (lost-object mode on)."""
     p = Params()
-    lib().pvt_default_params(C.byref(p))
+    (lib().pvt_default_params_ghc if ghc else lib().pvt_default_params)(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -287,6 +292,15 @@ class Tracker:
 
     def sync(self):
         _ck(lib().pvt_sync(self._h))
+
+    def get_lost_state(self, track=0):
+        """(lost_frame_count, use_global_search) of tracker_ghc/src/main.cpp:143-144."""
+        a, b = C.c_int(), C.c_int()
+        _ck(lib().pvt_get_lost_state(self._h, track, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_lost_state(self, track, lost_frame_count, use_global_search):
+        _ck(lib().pvt_set_lost_state(self._h, track, int(lost_frame_count), int(use_global_search)))
 
     def get_state(self, track=0):
         bbox = (C.c_int32 * 4)()

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
 {
     const unsigned long long step = *c.step;
     const int stream = blockIdx.y;
+    if (c.global_pass && !c.stream_need[stream]) return;   // whole-frame pass: only streams with a lost track
     const FrameDesc d = c.table[table_row(c, step) + stream];
     if (!d.valid) return;
     trace_begin(c, step, TR_INGEST);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     const int track = blockIdx.y;
     const TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
-    if (!t.active) return;
+    if (!t.active || !track_owned(c, t, step)) return;
     const FrameDesc d = c.table[table_row(c, step) + t.stream];
     if (!d.valid) return;
     trace_begin(c, step, TR_INGEST);
@@ -1018,6 +1019,7 @@ __global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream
     }
     if (threadIdx.x == 0) {
         t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull; t.ticket = 0u;
+        t.lost_count = 0; t.use_global = 0; t.global_since = 0ull;
         t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
     }
     __syncthreads();
@@ -1098,6 +1100,9 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
 {
     TrackState& t = c.tracks[track];
     pvt_result* res = c.results + (step % kRing) * c.max_tracks + track;
+    // tracker_ghc semantics (Ctx.lost_mode): a step is a local pass followed by a whole-frame pass; a track is reported
+    // by the pass that owns it (read before this call changes the track's mode)
+    const bool owned = track_owned(c, t, step);
     if (stepped) {
         const DevParams P = *c.params;
         const unsigned long long key = *((volatile unsigned long long*)&t.peak);
@@ -1140,19 +1145,30 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         }
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
+            if (c.lost_mode) {
+                // tracker_ghc/src/main.cpp:213-239: found -> reset the counter and go back to the local search (the box
+                // comes from a map position, so it is never outside the frame); else count the frame as lost.
+                // :183-185: from LOST_FRAME_THRESHOLD consecutive lost frames on, the NEXT frames search the whole map
+                // with NCC_GLOBAL_CONFIDENCE as the acceptance threshold (P.min_conf of the global pass)
+                if (moved) { t.lost_count = 0; t.use_global = 0; }
+                else t.lost_count += 1;
+                if (!t.use_global && t.lost_count >= P.lost_threshold) { t.use_global = 1; t.global_since = step + 1ull; }
+            }
             atomicAdd(c.macs, (unsigned long long)t.win[2] * t.win[3] * t.w * t.h);
             atomicAdd(c.macs_grid, (unsigned long long)min(t.win[2], c.gridW) * min(t.win[3], c.gridH) * t.w * t.h);
             res->x = nx; res->y = ny; res->w = t.w; res->h = t.h;
-            res->conf = val; res->moved = moved; res->updated = updated; res->searched = 1; res->valid = 1;
+            res->conf = val; res->moved = moved; res->updated = updated; res->searched = c.global_pass ? 2 : 1; res->valid = 1;
             res->track = track; res->step = (int32_t)step;
         }
-    } else if (threadIdx.x == 0) {
+    } else if (owned && threadIdx.x == 0) {
         res->x = t.x; res->y = t.y; res->w = t.w; res->h = t.h;
         res->conf = __int_as_float(0x7fc00000);
         res->moved = 0; res->updated = 0; res->searched = 0; res->valid = (uint8_t)(t.active != 0);
         res->track = track; res->step = (int32_t)step;
     }
-    // last track done -> advance the time step (every kernel of this step has read *c.step already)
+    // last track done -> advance the time step (every kernel of this step has read *c.step already).
+    // With two passes per step only the second (whole-frame) pass counts arrivals: one per track, owned or not.
+    if (c.lost_mode && !c.global_pass) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -1174,6 +1190,18 @@ __global__ void __launch_bounds__(256) k_update(Ctx c)
     trace_begin(c, step, TR_UPDATE);
     track_update(c, track, step, track_stepped(c, c.tracks[track], step), sm_f, red);
     trace_end(c, step, TR_UPDATE);
+}
+
+// whole-frame pass, first kernel: which streams carry a track that is searched over the whole frame this step
+__global__ void k_global_mark(Ctx c)
+{
+    const unsigned long long step = *c.step;
+    for (int s = threadIdx.x; s < c.max_streams; s += blockDim.x) c.stream_need[s] = 0;
+    __syncthreads();
+    for (int track = threadIdx.x; track < c.max_tracks; track += blockDim.x) {
+        const TrackState& t = c.tracks[track];
+        if (track_global(t, step)) c.stream_need[t.stream] = 1;
+    }
 }
 
 // hold step (batch mode, main.cpp:118-123): no NCC, no update; emit the stale box and advance

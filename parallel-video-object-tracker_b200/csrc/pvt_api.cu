@@ -48,6 +48,21 @@ struct EventPair {
     int cls;
 };
 
+// Everything the kernels of one pass over the tracks need.  A time step is ONE pass (the local search window of
+// tracker/src/main.cpp) or, in lost-object mode (tracker_ghc/src/main.cpp), that pass followed by a whole-frame pass
+// over the tracks that are currently lost: same kernels, window == the whole NCC map, its own plan and scratch.
+struct Pass {
+    Ctx d{};                   // by-value kernel argument
+    TileCfg tile{};
+    CUtensorMap tmap{};
+    size_t ncc_smem = 0;
+    int rowsum_warps = 8, rowsum_pw = 0;
+    int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
+    FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
+    size_t fringe_smem = 0;
+    bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
+};
+
 }  // namespace
 
 struct pvt_ctx {
@@ -59,6 +74,10 @@ struct pvt_ctx {
     size_t ncc_smem = 0;
     int rowsum_warps = 8, rowsum_pw = 0;
     int kps = 5;               // kernels per searched time step (for pvt_launch_count)
+    bool lost_mode = false;    // params.lost_frame_threshold > 0 at creation: every searched step also runs the whole-frame pass
+    Pass G{};                  // the whole-frame pass (lost-object re-acquisition)
+    int kps_global = 0;
+    cudaGraphExec_t graph_global = nullptr;
     FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
@@ -194,21 +213,145 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
     return best < 1e300;
 }
 
-int encode_tmap(pvt_ctx* c)
+int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out)
 {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
-    const Ctx& d = c->d;
     cuuint64_t dims[3] = {(cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.max_streams};
     cuuint64_t strides[2] = {(cuuint64_t)d.pitch * 4, (cuuint64_t)d.plane * 4};
-    cuuint32_t box[3] = {(cuuint32_t)c->tile.boxW, (cuuint32_t)c->tile.boxH, 1};
+    cuuint32_t box[3] = {(cuuint32_t)tile.boxW, (cuuint32_t)tile.boxH, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ((EncodeTiledFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.gray, dims, strides, box, estr,
+    CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.gray, dims, strides, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+    return PVT_OK;
+}
+
+// process-wide: the dynamic shared-memory limit of a kernel is only ever raised (several contexts may coexist)
+int raise_smem(const void* fn, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<const void*, size_t> cur;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& v = cur[fn];
+    if (bytes > v) {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        v = bytes;
+    }
+    return PVT_OK;
+}
+
+int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
+
+// kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
+int pass_kernels(const TileCfg& t, const FringeCfg& f)
+{
+    return 4 + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
+}
+
+// Plan one pass: p.d holds the geometry (W, H, templates, Wmax, Hmax, VW) and the shared pointers on entry; on return the
+// plan (tile grid, K-split / tail split, fringe, shared-memory sizes, TMA descriptor) and the pass's own scratch.
+int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
+{
+    Ctx& d = p.d;
+    if (!choose_plan(sm_count, d.max_tracks, d.mtw, d.mtp, d.mth, d.Wmax, d.Hmax, &p.tile, &p.ncc_smem)) { return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
+    }
+    if (const char* e = allow_env ? getenv("PVT_PLAN") : nullptr) {  // experiments: "GB,pj,pd" overrides the planner
+        int GB = 0, pj = 0, pd = 0;
+        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
+            TileCfg& g = p.tile;
+            const int nch = d.mtp / 8, nchp = (nch + pj - 1) / pj, ndp = (d.mth + pd - 1) / pd;
+            g.GB = std::min(GB, g.G); g.pj = pj; g.pd = pd;
+            g.bands = (g.G + g.GB - 1) / g.GB; g.ctas_band = (g.GB * g.C + kTilesPerCta - 1) / kTilesPerCta;
+            g.span = std::min(g.C, kTilesPerCta % g.GB == 0 ? kTilesPerCta / g.GB : (kTilesPerCta - 1) / g.GB + 2);
+            g.boxW = 8 * g.span + 8 * nchp + 4; g.boxH = g.GB * kCY + ndp - 1;
+            p.ncc_smem = (size_t)g.boxW * g.boxH * 4 + (size_t)4 * d.mth * 32 + 128;
+            if (g.boxW > 256 || g.boxH > 256 || p.ncc_smem + 1024 > kSmemBudget) { return fail(PVT_ERR_INVALID, "PVT_PLAN does not fit the TMA box / shared memory");
+            }
+        }
+    }
+    {   // item grid + tail splitting (see TileCfg)
+        TileCfg& g = p.tile;
+        g.cpt = g.bands * g.ctas_band;
+        const long long items = (long long)d.max_tracks * g.cpt, slots = (long long)sm_count * 2;
+        g.n_full = (int)items; g.n_tail = 0; g.tail_ps = 0;
+        const char* no_tail = getenv("PVT_NO_TAIL_SPLIT");
+        if (g.pj * g.pd == 1 && items > slots && !(no_tail && *no_tail == '1')) {
+            const long long rem = items % slots;
+            const int nch = d.mtp / 8;
+            const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
+            if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) {
+                g.n_tail = (int)rem; g.n_full = (int)(items - rem); g.tail_ps = ps;
+            }
+        }
+    }
+    {
+        const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
+        p.roi_ingest = !d.global_pass && (ingest == PVT_INGEST_ROI || (ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px));
+    }
+    d.gridW = 8 * p.tile.C;
+    d.gridH = kCY * p.tile.G;
+    {
+        int tpc = 1, pd_cap = 0;
+        const bool ok = fringe_plan(d.mtp, d.mth, &tpc, &pd_cap);
+        const int col_tiles = (d.Hmax + 7) / 8, row_tiles = (std::min(d.Wmax, 8 * p.tile.C) + 7) / 8;
+        tpc = std::max(1, std::min(tpc, std::max(col_tiles, row_tiles)));
+        p.fringe.tpc = tpc;
+        p.fringe.colg = d.Wmax > 8 * p.tile.C ? (col_tiles + tpc - 1) / tpc : 0;
+        p.fringe.rowg = d.Hmax > kCY * p.tile.G ? (row_tiles + tpc - 1) / tpc : 0;
+        p.fringe.strip_floats = fringe_strip_floats(tpc, d.mtp, d.mth);
+        p.fringe.threads = std::min(kFringeThreads, (tpc * (d.mtp / 8) + 31) & ~31);
+        if (p.fringe.colg + p.fringe.rowg > 0 && (!ok || p.tile.pd > pd_cap)) { return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe plan does not fit shared memory");
+        }
+    }
+    p.fringe.defer = p.tile.pj * p.tile.pd > 1 ? 1 : 0;
+    if (p.fringe.defer && p.fringe.colg + p.fringe.rowg > 0)
+        { int r_ = dev_alloc(c, &d.fringe_acc, (size_t)d.max_tracks * p.tile.pj * p.tile.pd * (d.Hmax + d.Wmax)); if (r_) return r_; }
+    p.fringe_smem = ((size_t)p.fringe.strip_floats + (size_t)(d.mtp / 8) * (d.mth * 8 + 4) + (size_t)(d.mtp / 8) * p.fringe.tpc * 8) * sizeof(float);
+    if (p.fringe.colg + p.fringe.rowg > 0) {
+        if (p.fringe_smem > 220u * 1024u) { return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe does not fit shared memory"); }
+        { int r_ = raise_smem((const void*)k_ncc_fringe, p.fringe_smem); if (r_) return r_; }
+    }
+    if (getenv("PVT_DEBUG_PLAN"))
+        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu | items full=%d tail=%d x%d | fringe ctas %d+%d x %d thr, %d tiles/cta, smem %zu\n",
+                d.max_tracks, p.tile.G, p.tile.C, p.tile.GB, p.tile.bands, p.tile.ctas_band, p.tile.span, p.tile.boxW, p.tile.boxH,
+                p.tile.pj, p.tile.pd, p.ncc_smem, p.tile.n_full, p.tile.n_tail, p.tile.tail_ps, p.fringe.colg, p.fringe.rowg, p.fringe.threads, p.fringe.tpc, p.fringe_smem);
+    if (p.tile.tail_ps > 1)           // tail items' partial cross terms: [tail part][128 tiles][8 * kCY]
+        { int r_ = dev_alloc(c, &d.partial, (size_t)p.tile.n_tail * p.tile.tail_ps * kTilesPerCta * 8 * kCY, false); if (r_) return r_; }
+    if (p.tile.pj * p.tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
+        { int r_ = dev_alloc(c, &d.partial, (size_t)p.tile.pj * p.tile.pd * d.max_tracks * p.tile.bands * p.tile.ctas_band * kTilesPerCta * 8 * kCY, false); if (r_) return r_; }
+    { int r_ = raise_smem((const void*)k_ncc_search<kCY>, p.ncc_smem); if (r_) return r_; }
+    p.rowsum_pw = d.VW + 8;
+    p.rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * p.rowsum_pw * sizeof(double))));
+    { int r_ = raise_smem((const void*)k_rowsum, (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double)); if (r_) return r_; }
+    // k_colprefix: ~28 rows per thread (8 chunks for a 224-row tracker tile, up to 32 for full-frame maps)
+    p.colprefix_chunks = std::max(1, std::min(32, (d.Hmax + d.mth - 1 + 27) / 28));
+    return encode_tmap(p.d, p.tile, &p.tmap);
+}
+
+// Lost-object mode: the whole-frame pass.  Same kernels, window == the whole NCC map (its DevParams copy carries
+// rx = W, ry = H and NCC_GLOBAL_CONFIDENCE as the acceptance threshold), own plan and scratch sized for the full frame.
+int build_global_pass(pvt_ctx* c, int sm_count)
+{
+    Pass& g = c->G;
+    g.d = c->d;
+    Ctx& d = g.d;
+    d.global_pass = 1;
+    d.Wmax = d.W; d.Hmax = d.H;                         // upper bounds of the map (W - tw + 1) x (H - th + 1)
+    d.VW = (d.Wmax + d.mtw - 1 + 7) & ~7;
+    d.maps = nullptr; d.partial = nullptr; d.fringe_acc = nullptr; d.trace = nullptr;
+    const size_t win = (size_t)d.Wmax * d.Hmax;
+    { int r = dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
+    { int r = dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
+    { int r = dev_alloc(c, &d.denom, (size_t)d.max_tracks * win, false); if (r) return r; }
+    { int r = dev_alloc(c, &d.params, 1); if (r) return r; }
+    { int r = dev_alloc(c, &d.stream_need, (size_t)d.max_streams); if (r) return r; }
+    int r = build_plan(c, g, sm_count, PVT_INGEST_FULL, false);
+    if (r) return r;
+    c->kps_global = 1 + pass_kernels(g.tile, g.fringe);
     return PVT_OK;
 }
 
@@ -221,8 +364,16 @@ int upload_params(pvt_ctx* c)
     p.strong_conf = c->params.ncc_strong_confidence;
     p.lr = c->params.template_update_lr;
     p.keep_maps = c->params.keep_maps;
+    p.lost_threshold = c->params.lost_frame_threshold;
     CK(cudaMemcpyAsync(c->d.params, &p, sizeof(p), cudaMemcpyHostToDevice, c->compute));
     CK(cudaStreamSynchronize(c->compute));
+    if (c->lost_mode && c->G.d.params) {
+        p.rx = c->d.W; p.ry = c->d.H;                       // window == the whole map (tracker_ghc/src/main.cpp:188-193)
+        p.min_conf = c->params.ncc_global_confidence;       // :217
+        p.keep_maps = 0;
+        CK(cudaMemcpyAsync(c->G.d.params, &p, sizeof(p), cudaMemcpyHostToDevice, c->compute));
+        CK(cudaStreamSynchronize(c->compute));
+    }
     return PVT_OK;
 }
 
@@ -245,6 +396,7 @@ int validate_params(const pvt_params* p)
     if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
     if (!(p->template_update_lr >= 0.0 && p->template_update_lr <= 1.0)) return fail(PVT_ERR_INVALID, "template_update_lr outside [0,1]");
+    if (p->lost_frame_threshold < 0) return fail(PVT_ERR_INVALID, "negative lost_frame_threshold");
     return PVT_OK;
 }
 
@@ -278,18 +430,34 @@ int pnode(pvt_ctx* c, int cls, int which, cudaStream_t st)
     return PVT_OK;
 }
 
+// the local pass as the kernels see it (the context's own fields are the master copy)
+Pass local_pass(const pvt_ctx* c)
+{
+    Pass p;
+    p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
+    p.colprefix_chunks = c->colprefix_chunks; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
+    return p;
+}
+Pass global_pass(const pvt_ctx* c)
+{
+    Pass p = c->G;
+    p.d.trace = nullptr;   // the device timeline describes the local pass
+    return p;
+}
+
 // The kernels of one searched time step.  capturing: being recorded into a CUDA graph on c->compute (fork/join allowed).
 // profile (only while capturing): external event-record NODES around each kernel class, so the measured durations are
 // GPU-side and contain no host launch gaps.  Classes: ingest | statistics | search (k_ncc_search [+ tail reduction]) |
 // update (k_ncc_finalize incl. the fused update in K-split mode, else k_update).
-int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
+int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing = false)
 {
-    const Ctx& d = c->d;
+    const Ctx& d = p.d;
     profile = profile && capturing;
     const int gpr = (d.W + 3) / 4;
     const long long groups = (long long)gpr * d.H;
     if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
-    if (c->roi_ingest) {
+    if (d.global_pass) k_global_mark<<<1, 256, 0, c->compute>>>(d);   // whole-frame pass: which streams need a whole-frame ingest
+    if (p.roi_ingest) {
         const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
         k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
@@ -300,7 +468,7 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
 
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
-    const bool ksplit = c->params.kernel != PVT_KERNEL_DIRECT && c->tile.pj * c->tile.pd > 1;
+    const bool ksplit = c->params.kernel != PVT_KERNEL_DIRECT && p.tile.pj * p.tile.pd > 1;
     const bool fork = capturing && ksplit;
     cudaStream_t sstats = c->compute;
     if (fork) {
@@ -309,15 +477,15 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
         sstats = c->aux;
     }
     if (profile) { int r = pnode(c, CLS_STATS, 0, sstats); if (r) return r; }
-    k_colprefix<<<dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, c->colprefix_chunks), 0, sstats>>>(d);
+    k_colprefix<<<dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats>>>(d);
     { int r = dbg(c, "k_colprefix"); if (r) return r; }
-    k_rowsum<<<dim3((d.Hmax + c->rowsum_warps - 1) / c->rowsum_warps, d.max_tracks), c->rowsum_warps * 32,
-               (size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double), sstats>>>(d, c->rowsum_pw);
+    k_rowsum<<<dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), p.rowsum_warps * 32,
+               (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats>>>(d, p.rowsum_pw);
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
-    const bool fringe = c->params.kernel != PVT_KERNEL_DIRECT && c->fringe.colg + c->fringe.rowg > 0;
-    const dim3 fgrid((unsigned)(c->fringe.colg + c->fringe.rowg), (unsigned)d.max_tracks, (unsigned)(c->fringe.defer ? c->tile.pd : 1));
+    const bool fringe = c->params.kernel != PVT_KERNEL_DIRECT && p.fringe.colg + p.fringe.rowg > 0;
+    const dim3 fgrid((unsigned)(p.fringe.colg + p.fringe.rowg), (unsigned)d.max_tracks, (unsigned)(p.fringe.defer ? p.tile.pd : 1));
     if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
     if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; }
@@ -327,20 +495,20 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
             // latency shape: a third branch from the same fork point; the cross terms are left in fringe_acc
             // (FringeCfg.defer) and normalised by k_ncc_finalize, so this branch does not wait for the statistics
             CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
-            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->aux2>>>(d, c->tile, c->fringe);
+            k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->aux2>>>(d, p.tile, p.fringe);
             CK(cudaEventRecord(c->ev_join2, c->aux2));
             join2 = true;
         } else if (capturing && fringe_branch()) {
             // throughput shape, experiment: after the statistics (the kernel normalises its own candidates), on a parallel branch
             CK(cudaEventRecord(c->ev_fork2, c->compute));
             CK(cudaStreamWaitEvent(c->aux2, c->ev_fork2, 0));
-            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->aux2>>>(d, c->tile, c->fringe);
+            k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->aux2>>>(d, p.tile, p.fringe);
             CK(cudaEventRecord(c->ev_join2, c->aux2));
             join2 = true;
         } else if (capturing) {
             fringe_after = true;   // throughput shape: right behind the search kernel with a programmatic dependency (below)
         } else {
-            k_ncc_fringe<<<fgrid, c->fringe.threads, c->fringe_smem, c->compute>>>(d, c->tile, c->fringe);
+            k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->compute>>>(d, p.tile, p.fringe);
             { int r = dbg(c, "k_ncc_fringe"); if (r) return r; }
         }
     }
@@ -348,29 +516,29 @@ int launch_step_kernels(pvt_ctx* c, bool profile, bool capturing = false)
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else {
-        const int parts = c->tile.pj * c->tile.pd;
-        const unsigned nbx = (unsigned)(c->tile.n_full + c->tile.n_tail * std::max(c->tile.tail_ps, 1));
+        const int parts = p.tile.pj * p.tile.pd;
+        const unsigned nbx = (unsigned)(p.tile.n_full + p.tile.n_tail * std::max(p.tile.tail_ps, 1));
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
-        k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, c->ncc_smem, c->compute>>>(d, c->tile, c->tmap);
+        k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, p.ncc_smem, c->compute>>>(d, p.tile, p.tmap);
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (fringe_after) {
             // programmatic dependent launch: the fringe kernel may begin once all search CTAs have been dispatched
             // (k_ncc_search issues griddepcontrol.launch_dependents first thing); it needs none of the search's results
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = fgrid; cfg.blockDim = dim3(c->fringe.threads); cfg.dynamicSmemBytes = c->fringe_smem; cfg.stream = c->compute;
+            cfg.gridDim = fgrid; cfg.blockDim = dim3(p.fringe.threads); cfg.dynamicSmemBytes = p.fringe_smem; cfg.stream = c->compute;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = profile ? 0 : 1;   // the profiling graph times k_ncc_search alone
             cfg.attrs = at; cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, k_ncc_fringe, d, c->tile, c->fringe));
+            CK(cudaLaunchKernelEx(&cfg, k_ncc_fringe, d, p.tile, p.fringe));
         }
-        if (c->tile.tail_ps > 1) k_ncc_tail_finalize<kCY><<<c->tile.n_tail, kTilesPerCta, 0, c->compute>>>(d, c->tile);
+        if (p.tile.tail_ps > 1) k_ncc_tail_finalize<kCY><<<p.tile.n_tail, kTilesPerCta, 0, c->compute>>>(d, p.tile);
         if (join2) CK(cudaStreamWaitEvent(c->compute, c->ev_join2, 0));   // the search class ends when the fringe has ended too
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
         if (parts > 1) {
             if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
-            k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, c->tile);
+            k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, p.tile);
             if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         }
     }
@@ -392,7 +560,8 @@ int build_graphs(pvt_ctx* c)
     if (c->graph_hold) { cudaGraphExecDestroy(c->graph_hold); c->graph_hold = nullptr; }
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-    int r = launch_step_kernels(c, false, true);
+    const Pass lp = local_pass(c);
+    int r = launch_step_kernels(c, lp, false, true);
     cudaError_t e = cudaStreamEndCapture(c->compute, &g);
     if (r) return r;
     CK(e);
@@ -400,12 +569,22 @@ int build_graphs(pvt_ctx* c)
     CK(cudaGraphDestroy(g));
     if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-    r = launch_step_kernels(c, true, true);
+    r = launch_step_kernels(c, lp, true, true);
     e = cudaStreamEndCapture(c->compute, &g);
     if (r) return r;
     CK(e);
     CK(cudaGraphInstantiate(&c->graph_prof, g, 0));
     CK(cudaGraphDestroy(g));
+    if (c->graph_global) { cudaGraphExecDestroy(c->graph_global); c->graph_global = nullptr; }
+    if (c->lost_mode) {
+        CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+        r = launch_step_kernels(c, global_pass(c), false, true);
+        e = cudaStreamEndCapture(c->compute, &g);
+        if (r) return r;
+        CK(e);
+        CK(cudaGraphInstantiate(&c->graph_global, g, 0));
+        CK(cudaGraphDestroy(g));
+    }
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
     k_hold<<<1, 256, 0, c->compute>>>(c->d);
     CK(cudaStreamEndCapture(c->compute, &g));
@@ -490,13 +669,19 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         CK(cudaGraphLaunch(c->graph_hold, c->compute));
         c->launches += 1;
     } else if (debug_sync()) {
-        int r = launch_step_kernels(c, false);
+        int r = launch_step_kernels(c, local_pass(c), false);
         if (r) return r;
         c->launches += c->kps;
+        if (c->lost_mode) {
+            r = launch_step_kernels(c, global_pass(c), false);
+            if (r) return r;
+            c->launches += c->kps_global;
+        }
     } else if (c->profiling) {
         // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph_prof, c->compute));
+        if (c->lost_mode) { CK(cudaGraphLaunch(c->graph_global, c->compute)); c->launches += c->kps_global; }
         CK(cudaStreamSynchronize(c->compute));
         c->launches += c->kps;
         c->prof.steps += 1;
@@ -517,6 +702,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
         CK(cudaGraphLaunch(c->graph, c->compute));
         c->launches += c->kps;
+        if (c->lost_mode) { CK(cudaGraphLaunch(c->graph_global, c->compute)); c->launches += c->kps_global; }
     }
     if (copied) {
         CK(cudaEventRecord(c->ev_done[sd], c->compute));
@@ -586,6 +772,21 @@ void pvt_default_params(pvt_params* p)
     p->batch_size = 4;                 // main.cpp:11
     p->mode = PVT_MODE_NAIVE;          // main.cpp:8
     p->kernel = PVT_KERNEL_AUTO;
+    p->lost_frame_threshold = 0;       // tracker/src/main.cpp has no lost-object logic
+    p->ncc_global_confidence = 0.60;   // tracker_ghc/src/main.cpp:17
+}
+
+void pvt_default_params_ghc(pvt_params* p)
+{
+    if (!p) return;
+    pvt_default_params(p);
+    p->search_radius_x = 60;           // tracker_ghc/src/main.cpp:9
+    p->search_radius_y = 60;           // :10
+    p->ncc_min_confidence = 0.40;      // :15
+    p->ncc_global_confidence = 0.60;   // :17
+    p->ncc_strong_confidence = 0.70;   // :19
+    p->template_update_lr = 0.10;      // :21
+    p->lost_frame_threshold = 50;      // :23
 }
 
 int pvt_alloc_pinned(void** out, size_t bytes)
@@ -609,6 +810,7 @@ int pvt_destroy(pvt_ctx* c)
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
     if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
+    if (c->graph_global) cudaGraphExecDestroy(c->graph_global);
     for (int k = 0; k < 5; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_table) cudaFreeHost(c->h_table);
@@ -663,7 +865,10 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         delete c;
         return fail(PVT_ERR_INVALID, "search radius exceeds config.max_radius");
     }
+    c->lost_mode = params->lost_frame_threshold > 0;
     Ctx& d = c->d;
+    d.lost_mode = c->lost_mode ? 1 : 0;
+    d.global_pass = 0;
     d.W = cfg->frame_w;
     d.H = cfg->frame_h;
     d.pitch = (d.W + 3) & ~3;
@@ -740,94 +945,23 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     c->stage_bytes = (size_t)d.W * d.H * 4;
     c->track_stream.assign(d.max_tracks, -1);
 
-    if (!choose_plan(prop.multiProcessorCount, d.max_tracks, d.mtw, d.mtp, d.mth, d.Wmax, d.Hmax, &c->tile, &c->ncc_smem)) {
-        pvt_destroy(c);
-        return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
-    }
-    if (const char* e = getenv("PVT_PLAN")) {  // experiments: "GB,pj,pd" overrides the planner
-        int GB = 0, pj = 0, pd = 0;
-        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
-            TileCfg& g = c->tile;
-            const int nch = d.mtp / 8, nchp = (nch + pj - 1) / pj, ndp = (d.mth + pd - 1) / pd;
-            g.GB = std::min(GB, g.G); g.pj = pj; g.pd = pd;
-            g.bands = (g.G + g.GB - 1) / g.GB; g.ctas_band = (g.GB * g.C + kTilesPerCta - 1) / kTilesPerCta;
-            g.span = std::min(g.C, kTilesPerCta % g.GB == 0 ? kTilesPerCta / g.GB : (kTilesPerCta - 1) / g.GB + 2);
-            g.boxW = 8 * g.span + 8 * nchp + 4; g.boxH = g.GB * kCY + ndp - 1;
-            c->ncc_smem = (size_t)g.boxW * g.boxH * 4 + (size_t)4 * d.mth * 32 + 128;
-            if (g.boxW > 256 || g.boxH > 256 || c->ncc_smem + 1024 > kSmemBudget) {
-                pvt_destroy(c);
-                return fail(PVT_ERR_INVALID, "PVT_PLAN does not fit the TMA box / shared memory");
-            }
-        }
-    }
-    {   // item grid + tail splitting (see TileCfg)
-        TileCfg& g = c->tile;
-        g.cpt = g.bands * g.ctas_band;
-        const long long items = (long long)d.max_tracks * g.cpt, slots = (long long)prop.multiProcessorCount * 2;
-        g.n_full = (int)items; g.n_tail = 0; g.tail_ps = 0;
-        const char* no_tail = getenv("PVT_NO_TAIL_SPLIT");
-        if (g.pj * g.pd == 1 && items > slots && !(no_tail && *no_tail == '1')) {
-            const long long rem = items % slots;
-            const int nch = d.mtp / 8;
-            const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
-            if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) {
-                g.n_tail = (int)rem; g.n_full = (int)(items - rem); g.tail_ps = ps;
-            }
-        }
-    }
     {
-        const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
-        c->roi_ingest = params->ingest == PVT_INGEST_ROI || (params->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
+        Pass lp;
+        lp.d = c->d;
+        CR(build_plan(c, lp, prop.multiProcessorCount, params->ingest, true));
+        c->d = lp.d; c->tile = lp.tile; c->tmap = lp.tmap; c->ncc_smem = lp.ncc_smem; c->rowsum_warps = lp.rowsum_warps;
+        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
+        c->roi_ingest = lp.roi_ingest;
     }
-    d.gridW = 8 * c->tile.C;
-    d.gridH = kCY * c->tile.G;
-    {
-        int tpc = 1, pd_cap = 0;
-        const bool ok = fringe_plan(d.mtp, d.mth, &tpc, &pd_cap);
-        const int col_tiles = (d.Hmax + 7) / 8, row_tiles = (std::min(d.Wmax, 8 * c->tile.C) + 7) / 8;
-        tpc = std::max(1, std::min(tpc, std::max(col_tiles, row_tiles)));
-        c->fringe.tpc = tpc;
-        c->fringe.colg = d.Wmax > 8 * c->tile.C ? (col_tiles + tpc - 1) / tpc : 0;
-        c->fringe.rowg = d.Hmax > kCY * c->tile.G ? (row_tiles + tpc - 1) / tpc : 0;
-        c->fringe.strip_floats = fringe_strip_floats(tpc, d.mtp, d.mth);
-        c->fringe.threads = std::min(kFringeThreads, (tpc * (d.mtp / 8) + 31) & ~31);
-        if (c->fringe.colg + c->fringe.rowg > 0 && (!ok || c->tile.pd > pd_cap)) {
-            pvt_destroy(c);
-            return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe plan does not fit shared memory");
-        }
-    }
-    c->fringe.defer = c->tile.pj * c->tile.pd > 1 ? 1 : 0;
-    if (c->fringe.defer && c->fringe.colg + c->fringe.rowg > 0)
-        CR(dev_alloc(c, &d.fringe_acc, (size_t)d.max_tracks * c->tile.pj * c->tile.pd * (d.Hmax + d.Wmax)));
-    c->fringe_smem = ((size_t)c->fringe.strip_floats + (size_t)(d.mtp / 8) * (d.mth * 8 + 4) + (size_t)(d.mtp / 8) * c->fringe.tpc * 8) * sizeof(float);
-    if (c->fringe.colg + c->fringe.rowg > 0) {
-        if (c->fringe_smem > 220u * 1024u) { pvt_destroy(c); return fail(PVT_ERR_UNSUPPORTED, "internal: k_ncc_fringe does not fit shared memory"); }
-        CKD(cudaFuncSetAttribute(k_ncc_fringe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fringe_smem));
-    }
-    c->kps = 4 + ((c->tile.pj * c->tile.pd > 1) ? 1 : (c->tile.tail_ps > 1 ? 2 : 1)) + (c->fringe.colg + c->fringe.rowg > 0 ? 1 : 0);  // ingest, 2 stats, search, [fringe], [tail] + update | finalize
-    if (getenv("PVT_DEBUG_PLAN"))
-        fprintf(stderr, "[pvt] plan: tracks=%d G=%d C=%d GB=%d bands=%d ctas/band=%d span=%d box=%dx%d pj=%d pd=%d smem=%zu | items full=%d tail=%d x%d | fringe ctas %d+%d x %d thr, %d tiles/cta, smem %zu\n",
-                d.max_tracks, c->tile.G, c->tile.C, c->tile.GB, c->tile.bands, c->tile.ctas_band, c->tile.span, c->tile.boxW, c->tile.boxH,
-                c->tile.pj, c->tile.pd, c->ncc_smem, c->tile.n_full, c->tile.n_tail, c->tile.tail_ps, c->fringe.colg, c->fringe.rowg, c->fringe.threads, c->fringe.tpc, c->fringe_smem);
-    if (c->tile.tail_ps > 1)           // tail items' partial cross terms: [tail part][128 tiles][8 * kCY]
-        CR(dev_alloc(c, &d.partial, (size_t)c->tile.n_tail * c->tile.tail_ps * kTilesPerCta * 8 * kCY, false));
-    if (c->tile.pj * c->tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
-        CR(dev_alloc(c, &d.partial, (size_t)c->tile.pj * c->tile.pd * d.max_tracks * c->tile.bands * c->tile.ctas_band * kTilesPerCta * 8 * kCY, false));
-    CKD(cudaFuncSetAttribute(k_ncc_search<kCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ncc_smem));
-    c->rowsum_pw = d.VW + 8;
-    c->rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * c->rowsum_pw * sizeof(double))));
-    CKD(cudaFuncSetAttribute(k_rowsum, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)((size_t)c->rowsum_warps * 2 * c->rowsum_pw * sizeof(double))));
-    // k_colprefix: ~28 rows per thread (8 chunks for a 224-row tracker tile, up to 32 for full-frame maps)
-    c->colprefix_chunks = std::max(1, std::min(32, (d.Hmax + d.mth - 1 + 27) / 28));
+    c->kps = pass_kernels(c->tile, c->fringe);
     c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
     if (c->templ_smem > 48u * 1024u) {
-        CKD(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
-        CKD(cudaFuncSetAttribute(k_ncc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
-        CKD(cudaFuncSetAttribute(k_track_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
-        CKD(cudaFuncSetAttribute(k_track_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->templ_smem));
+        CR(raise_smem((const void*)k_update, c->templ_smem));
+        CR(raise_smem((const void*)k_ncc_finalize, c->templ_smem));
+        CR(raise_smem((const void*)k_track_init, c->templ_smem));
+        CR(raise_smem((const void*)k_track_refresh, c->templ_smem));
     }
-    CR(encode_tmap(c));
+    if (c->lost_mode) CR(build_global_pass(c, prop.multiProcessorCount));
     CR(upload_params(c));
     CR(upload_seq(c, 0, kRing, 0));
     CKD(cudaDeviceSynchronize());  // the zero-fills above ran on the default stream; kernels use non-blocking streams
@@ -845,6 +979,7 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
     if (p->search_radius_x > c->cfg.max_radius_x || p->search_radius_y > c->cfg.max_radius_y)
         return fail(PVT_ERR_INVALID, "search radius exceeds the maxima the context was created with");
     if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
+    if ((p->lost_frame_threshold > 0) != c->lost_mode) return fail(PVT_ERR_INVALID, "lost-object mode (lost_frame_threshold > 0) must be chosen at pvt_create");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->compute));
     const bool regraph = p->kernel != c->params.kernel || p->ingest != c->params.ingest;
@@ -1015,6 +1150,7 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
             CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
             c->launches += hold ? 1 : c->kps;
+            if (!hold && c->lost_mode) { CK(cudaGraphLaunch(c->graph_global, c->compute)); c->launches += c->kps_global; }
             c->submitted += 1;
             if (collect_every > 0 && (s + 1) % collect_every == 0) {
                 const unsigned long long first = c->submitted - collect_every;
@@ -1116,6 +1252,40 @@ int pvt_set_state(pvt_ctx* c, int track, const int32_t bbox[4], const float* tem
     c->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->compute));
+    return PVT_OK;
+}
+
+int pvt_get_lost_state(pvt_ctx* c, int track, int* lost_frame_count, int* use_global_search)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    TrackState t;
+    CK(cudaMemcpy(&t, &c->d.tracks[track], sizeof(t), cudaMemcpyDeviceToHost));
+    if (!t.active) return fail(PVT_ERR_STATE, "track is not initialised");
+    if (lost_frame_count) *lost_frame_count = t.lost_count;
+    if (use_global_search) *use_global_search = t.use_global;
+    return PVT_OK;
+}
+
+int pvt_set_lost_state(pvt_ctx* c, int track, int lost_frame_count, int use_global_search)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    if (track < 0 || track >= c->cfg.max_tracks) return fail(PVT_ERR_INVALID, "track out of range");
+    if (lost_frame_count < 0) return fail(PVT_ERR_INVALID, "negative lost_frame_count");
+    if (use_global_search && !c->lost_mode) return fail(PVT_ERR_STATE, "context was created without lost-object mode");
+    CK(cudaSetDevice(c->cfg.device));
+    int r = pvt_sync(c);
+    if (r) return r;
+    TrackState t;
+    CK(cudaMemcpy(&t, &c->d.tracks[track], sizeof(t), cudaMemcpyDeviceToHost));
+    if (!t.active) return fail(PVT_ERR_STATE, "track is not initialised");
+    t.lost_count = lost_frame_count;
+    t.use_global = use_global_search ? 1 : 0;
+    t.global_since = 0ull;   // applies from the next submitted step on
+    CK(cudaMemcpy(&c->d.tracks[track], &t, sizeof(t), cudaMemcpyHostToDevice));
     return PVT_OK;
 }
 

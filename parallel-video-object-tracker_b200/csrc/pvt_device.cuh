@@ -47,18 +47,24 @@ struct TrackState {
     unsigned long long peak;   // packed (ordered score << 32 | ~index); 0 = empty
     int win[4];                // minTx, minTy, width, height of the current search window
     unsigned int ticket;       // CTAs of k_ncc_finalize that are done with this track (last one runs the update)
-    int pad;
+    // lost-object re-acquisition (tracker_ghc/src/main.cpp:143-144, 183-239); only used when Ctx.lost_mode != 0
+    int lost_count;            // consecutive frames below the confidence threshold (lost_frame_count)
+    int use_global;            // use_global_search: the track is searched over the whole frame ...
+    unsigned long long global_since;   // ... from this time step on (the flag is set by the PREVIOUS step's update)
 };
 
 struct DevParams {
-    int rx, ry;
-    double min_conf, strong_conf, lr;
+    int rx, ry;                // the global pass has its own copy with rx = W, ry = H (window == whole map) ...
+    double min_conf, strong_conf, lr;   // ... and min_conf = NCC_GLOBAL_CONFIDENCE
     int keep_maps;
-    int pad;
+    int lost_threshold;        // LOST_FRAME_THRESHOLD (tracker_ghc/src/main.cpp:23)
 };
 
 // geometry + pointers every kernel needs; passed by value (fits in the parameter bank)
 struct Ctx {
+    int lost_mode;             // != 0: tracker_ghc semantics; a time step = local pass (global_pass 0) + global pass (1)
+    int global_pass;           // which pass this launch belongs to: a track is handled by exactly one pass per step
+    int* stream_need;          // global pass: streams with at least one whole-frame track this step (whole-frame ingest)
     int W, H, pitch;           // frame geometry, gray-plane pitch in floats
     size_t plane;              // floats per gray plane
     int max_streams, max_tracks;
@@ -102,9 +108,19 @@ __device__ __forceinline__ size_t table_row(const Ctx& c, unsigned long long ste
     const SeqDesc q = *c.seq;
     return (size_t)(q.row0 + (int)((step - q.step0) % (unsigned long long)q.ring_len)) * c.max_streams;
 }
+// whole-frame (global) search applies to this track at this step (decided by the previous step's update)
+__device__ __forceinline__ bool track_global(const TrackState& t, unsigned long long step)
+{
+    return t.active && t.use_global && t.global_since <= step;
+}
+// does this pass own the track at this step?  (inactive tracks belong to the local pass, which reports them)
+__device__ __forceinline__ bool track_owned(const Ctx& c, const TrackState& t, unsigned long long step)
+{
+    return !c.lost_mode || (track_global(t, step) == (c.global_pass != 0));
+}
 __device__ __forceinline__ bool track_stepped(const Ctx& c, const TrackState& t, unsigned long long step)
 {
-    if (!t.active) return false;
+    if (!t.active || !track_owned(c, t, step)) return false;
     return c.table[table_row(c, step) + t.stream].valid != 0;
 }
 

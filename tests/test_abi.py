@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = pvt.lib()
     for s in _declared_symbols():
         assert hasattr(L, s), f"libpvt.so does not export {s}"
-    assert L.pvt_version() == 100
+    assert L.pvt_version() == 101
 
 
 def test_default_params_are_the_reference_constants():
@@ -33,12 +33,16 @@ def test_default_params_are_the_reference_constants():
     assert (p.search_radius_x, p.search_radius_y) == (80, 80)
     assert (p.ncc_min_confidence, p.ncc_strong_confidence, p.template_update_lr) == (0.40, 0.70, 0.10)
     assert p.batch_size == 4 and p.mode == pvt.MODE_NAIVE and p.kernel == pvt.KERNEL_AUTO
+    assert p.lost_frame_threshold == 0                                    # tracker/ has no lost-object logic
+    g = pvt.default_params(ghc=True)  # tracker_ghc/src/main.cpp:9-23
+    assert (g.search_radius_x, g.search_radius_y, g.lost_frame_threshold) == (60, 60, 50)
+    assert (g.ncc_min_confidence, g.ncc_global_confidence, g.ncc_strong_confidence, g.template_update_lr) == (0.40, 0.60, 0.70, 0.10)
 
 
 def test_struct_layouts():
     assert C.sizeof(pvt.Result) == 32 and pvt.RESULT_DTYPE.itemsize == 32
     assert C.sizeof(pvt.Frame) == 32
-    assert C.sizeof(pvt.Params) == 8 + 24 + 4 * 4 + 16
+    assert C.sizeof(pvt.Params) == 8 + 24 + 5 * 4 + 4 + 8 + 8   # + lost_frame_threshold, reserved[2], ncc_global_confidence
     assert C.sizeof(pvt.Config) == 16 * 4
 
 
