@@ -385,6 +385,7 @@ def run_ours(args):
             out["extra"][w2] = {"workload": WORKLOADS[w2]["desc"], "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
                                 "ncc_gmacs_per_s": e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9, "roofline": e["roofline"],
                                 "kernel_ms_per_step": e["kernel_ms_per_step"], "ingest": e["ingest_mode"]}
+        out["extra"]["whole_frame_search"] = whole_frame_leg(pvt, torch, m)
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, m["_scene0"], m["_host0"], budget_s=args.cpu_seconds)
     if rank == 0:
@@ -392,6 +393,40 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def whole_frame_leg(pvt, torch, m, steps=40):
+    """the lost-object mode's whole-frame search (tracker_ghc/src/main.cpp:186-193), one 1080p stream,
+    64x64 template, the track held in the lost state (acceptance threshold 2.0 is never met), so every step computes the
+    full 1857 x 1017 NCC map's arg-max: 7.74 GMAC per frame.  Step time by CUDA events; TFLOP/s from the step time (a lower
+    bound for the search kernel: ingest, statistics and update are inside)."""
+    wl = dict(WORKLOADS["C2"])
+    W, H, tw, th, L = wl["W"], wl["H"], wl["tw"], wl["th"], wl["ring"]
+    scenes, host, dev = build_rings(wl, 0, torch)
+    info = pvt.device_info(torch.cuda.current_device())
+    ring = ring_descs(pvt, wl, dev, True)
+    res = {}
+    for lost in (False, True):
+        tr = pvt.Tracker(W, H, tw, th, search_radius_x=wl["R"], search_radius_y=wl["R"], lost_frame_threshold=50, ncc_global_confidence=2.0)
+        tr.init_track(0, pvt.device_frame(dev[0, 0].data_ptr(), W * 3, stream=0), rois_for(wl, scenes[0])[0], stream=0)
+        if lost:
+            tr.set_lost_state(0, 1000, 1)
+        tr.submit_sequence(6, ring[1:] + ring[:1])
+        tr.sync()
+        tr.timer_start()
+        tr.submit_sequence(steps, ring[7 % L:] + ring[:7 % L])
+        ms = tr.timer_stop() / steps
+        last = tr.collect(1)[0][0]
+        assert int(last["searched"]) == (2 if lost else 1)
+        res[lost] = ms
+        tr.close()
+    macs = float((W - tw + 1) * (H - th + 1) * tw * th)
+    peak = info["sm_count"] * 128 * 2 * info["sm_clock_khz"] * 1e-6 * 1e-3
+    return {"workload": "one 1920x1080 stream, 64x64 template, track lost: arg-max of the full 1857x1017 NCC map every frame",
+            "frames_per_s": 1e3 / res[True], "ms_per_step": res[True], "macs_per_step": macs,
+            "tflops_from_step_time": 2 * macs / (res[True] * 1e-3) / 1e12, "frac_of_fp32_peak_from_step_time": 2 * macs / (res[True] * 1e-3) / 1e12 / peak,
+            "local_step_ms_with_lost_mode_on": res[False], "local_step_ms_headline": m["ms_per_step"],
+            "note": "lost-object mode adds an (empty) whole-frame pass to every step of a track that is not lost"}
 
 
 def cpu_baseline(wl, scene, frames, budget_s=15.0, max_frames=100000):

@@ -187,7 +187,8 @@ PVT_API int pvt_sync(pvt_ctx* ctx);
 /* tracker state = {bbox, template} (the reference keeps it in host variables, main.cpp:63-71) */
 PVT_API int pvt_get_state(pvt_ctx* ctx, int track, int32_t bbox[4], float* templ, size_t templ_step_bytes);
 PVT_API int pvt_set_state(pvt_ctx* ctx, int track, const int32_t bbox[4], const float* templ, size_t templ_step_bytes);
-/* lost-object state of a track (tracker_ghc/src/main.cpp:143-144 lost_frame_count, use_global_search), for checkpoint / resume */
+/* lost-object state of a track (tracker_ghc/src/main.cpp:143-144 lost_frame_count, use_global_search), for checkpoint / resume.
+ * use_global_search is reported as the NEXT frame will evaluate it (:183-185 raises it at the start of a frame). */
 PVT_API int pvt_get_lost_state(pvt_ctx* ctx, int track, int* lost_frame_count, int* use_global_search);
 PVT_API int pvt_set_lost_state(pvt_ctx* ctx, int track, int lost_frame_count, int use_global_search);
 /* last window map of a track (needs params.keep_maps): win = {minTx, minTy, width, height} (main.cpp:143-147) */

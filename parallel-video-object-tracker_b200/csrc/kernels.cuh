@@ -1167,8 +1167,8 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         res->track = track; res->step = (int32_t)step;
     }
     // last track done -> advance the time step (every kernel of this step has read *c.step already).
-    // With two passes per step only the second (whole-frame) pass counts arrivals: one per track, owned or not.
-    if (c.lost_mode && !c.global_pass) return;
+    // With two passes per step (lost-object mode) k_step_advance does it after both.
+    if (c.lost_mode) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -1192,16 +1192,28 @@ __global__ void __launch_bounds__(256) k_update(Ctx c)
     trace_end(c, step, TR_UPDATE);
 }
 
-// whole-frame pass, first kernel: which streams carry a track that is searched over the whole frame this step
-__global__ void k_global_mark(Ctx c)
+// Lost-object mode, after the local pass: which streams carry a track that is searched over the whole frame this step --
+// and whether there is any.  The whole-frame pass is the body of a CUDA-graph CONDITIONAL node: this kernel sets the
+// condition on the device (no host round trip), so a step in which no track is lost pays for two tiny kernels only.
+__global__ void k_global_mark(Ctx c, cudaGraphConditionalHandle cond, int use_cond)
 {
+    __shared__ int any;
     const unsigned long long step = *c.step;
+    if (threadIdx.x == 0) any = 0;
     for (int s = threadIdx.x; s < c.max_streams; s += blockDim.x) c.stream_need[s] = 0;
     __syncthreads();
     for (int track = threadIdx.x; track < c.max_tracks; track += blockDim.x) {
         const TrackState& t = c.tracks[track];
-        if (track_global(t, step)) c.stream_need[t.stream] = 1;
+        if (track_global(t, step)) { c.stream_need[t.stream] = 1; any = 1; }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && use_cond) cudaGraphSetConditional(cond, any ? 1u : 0u);
+}
+
+// Lost-object mode, last kernel of a step: both passes have reported their tracks; advance the device time step.
+__global__ void k_step_advance(Ctx c)
+{
+    if (threadIdx.x == 0) { *c.ticket = 0u; *c.step = *c.step + 1ull; }
 }
 
 // hold step (batch mode, main.cpp:118-123): no NCC, no update; emit the stale box and advance

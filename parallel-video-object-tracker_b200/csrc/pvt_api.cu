@@ -61,6 +61,7 @@ struct Pass {
     FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
+    bool pdl = true;           // k_ncc_fringe behind the search with a programmatic dependency (plain stream order otherwise)
 };
 
 }  // namespace
@@ -351,7 +352,7 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     { int r = dev_alloc(c, &d.stream_need, (size_t)d.max_streams); if (r) return r; }
     int r = build_plan(c, g, sm_count, PVT_INGEST_FULL, false);
     if (r) return r;
-    c->kps_global = 1 + pass_kernels(g.tile, g.fringe);
+    c->kps_global = 2;   // k_global_mark + k_step_advance; the conditional body's kernels (they only run while a track is lost) are not counted
     return PVT_OK;
 }
 
@@ -442,6 +443,7 @@ Pass global_pass(const pvt_ctx* c)
 {
     Pass p = c->G;
     p.d.trace = nullptr;   // the device timeline describes the local pass
+    p.pdl = false;         // body of a conditional graph node: plain stream order
     return p;
 }
 
@@ -456,7 +458,6 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     const int gpr = (d.W + 3) / 4;
     const long long groups = (long long)gpr * d.H;
     if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
-    if (d.global_pass) k_global_mark<<<1, 256, 0, c->compute>>>(d);   // whole-frame pass: which streams need a whole-frame ingest
     if (p.roi_ingest) {
         const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
         k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
@@ -505,7 +506,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
             k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->aux2>>>(d, p.tile, p.fringe);
             CK(cudaEventRecord(c->ev_join2, c->aux2));
             join2 = true;
-        } else if (capturing) {
+        } else if (capturing && p.pdl) {
             fringe_after = true;   // throughput shape: right behind the search kernel with a programmatic dependency (below)
         } else {
             k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->compute>>>(d, p.tile, p.fringe);
@@ -554,17 +555,72 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     return PVT_OK;
 }
 
+// Lost-object mode: append  k_global_mark -> IF (any track lost) { the whole-frame pass } -> k_step_advance  to graph g behind
+// `deps`.  The condition is set on the device by k_global_mark, so nothing returns to the host between the passes.
+int add_global_tail(pvt_ctx* c, cudaGraph_t g, const cudaGraphNode_t* deps, size_t n_deps)
+{
+    const Pass gp = global_pass(c);
+    Ctx gd = gp.d;
+    cudaGraphConditionalHandle cond;
+    CK(cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
+    int use_cond = 1;
+    void* margs[3] = {&gd, &cond, &use_cond};
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)k_global_mark; kp.gridDim = dim3(1); kp.blockDim = dim3(256); kp.sharedMemBytes = 0; kp.kernelParams = margs;
+    cudaGraphNode_t n_mark, n_if, n_adv;
+    CK(cudaGraphAddKernelNode(&n_mark, g, deps, n_deps, &kp));
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = cond; cp.conditional.type = cudaGraphCondTypeIf; cp.conditional.size = 1;
+    CK(cudaGraphAddNode(&n_if, g, &n_mark, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(c->compute, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int r = launch_step_kernels(c, gp, false, true);
+    cudaError_t e = cudaStreamEndCapture(c->compute, nullptr);
+    if (r) return r;
+    CK(e);
+    void* aargs[1] = {&gd};
+    cudaKernelNodeParams ka{};
+    ka.func = (void*)k_step_advance; ka.gridDim = dim3(1); ka.blockDim = dim3(32); ka.sharedMemBytes = 0; ka.kernelParams = aargs;
+    CK(cudaGraphAddKernelNode(&n_adv, g, &n_if, 1, &ka));
+    return PVT_OK;
+}
+
 int build_graphs(pvt_ctx* c)
 {
     if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
     if (c->graph_hold) { cudaGraphExecDestroy(c->graph_hold); c->graph_hold = nullptr; }
     cudaGraph_t g = nullptr;
-    CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
     const Pass lp = local_pass(c);
-    int r = launch_step_kernels(c, lp, false, true);
-    cudaError_t e = cudaStreamEndCapture(c->compute, &g);
-    if (r) return r;
-    CK(e);
+    int r;
+    cudaError_t e;
+    if (!c->lost_mode) {
+        CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+        r = launch_step_kernels(c, lp, false, true);
+        e = cudaStreamEndCapture(c->compute, &g);
+        if (r) return r;
+        CK(e);
+    } else {
+        // one graph per step: the local pass, then (behind its leaves) the conditional whole-frame pass
+        CK(cudaGraphCreate(&g, 0));
+        CK(cudaStreamBeginCaptureToGraph(c->compute, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        r = launch_step_kernels(c, lp, false, true);
+        e = cudaStreamEndCapture(c->compute, nullptr);
+        if (r) return r;
+        CK(e);
+        size_t nn = 0, ne = 0;
+        CK(cudaGraphGetNodes(g, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        CK(cudaGraphGetNodes(g, nodes.data(), &nn));
+        CK(cudaGraphGetEdges(g, nullptr, nullptr, &ne));
+        std::vector<cudaGraphNode_t> from(ne), to(ne);
+        if (ne) CK(cudaGraphGetEdges(g, from.data(), to.data(), &ne));
+        std::vector<cudaGraphNode_t> leaves;
+        for (cudaGraphNode_t n : nodes)
+            if (std::find(from.begin(), from.end(), n) == from.end()) leaves.push_back(n);
+        r = add_global_tail(c, g, leaves.data(), leaves.size());
+        if (r) return r;
+    }
     CK(cudaGraphInstantiate(&c->graph, g, 0));
     CK(cudaGraphDestroy(g));
     if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
@@ -577,11 +633,10 @@ int build_graphs(pvt_ctx* c)
     CK(cudaGraphDestroy(g));
     if (c->graph_global) { cudaGraphExecDestroy(c->graph_global); c->graph_global = nullptr; }
     if (c->lost_mode) {
-        CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-        r = launch_step_kernels(c, global_pass(c), false, true);
-        e = cudaStreamEndCapture(c->compute, &g);
+        // stand-alone copy of the whole-frame tail, launched behind the profiling graph
+        CK(cudaGraphCreate(&g, 0));
+        r = add_global_tail(c, g, nullptr, 0);
         if (r) return r;
-        CK(e);
         CK(cudaGraphInstantiate(&c->graph_global, g, 0));
         CK(cudaGraphDestroy(g));
     }
@@ -673,9 +728,13 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         if (r) return r;
         c->launches += c->kps;
         if (c->lost_mode) {
-            r = launch_step_kernels(c, global_pass(c), false);
+            const Pass gp = global_pass(c);
+            k_global_mark<<<1, 256, 0, c->compute>>>(gp.d, 0, 0);
+            r = launch_step_kernels(c, gp, false);
             if (r) return r;
-            c->launches += c->kps_global;
+            k_step_advance<<<1, 32, 0, c->compute>>>(gp.d);
+            { int r2 = dbg(c, "k_step_advance"); if (r2) return r2; }
+            c->launches += c->kps_global + pass_kernels(gp.tile, gp.fringe);
         }
     } else if (c->profiling) {
         // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
@@ -700,9 +759,8 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
         }
     } else {
         if (!c->graph_valid) { int r = build_graphs(c); if (r) return r; }
-        CK(cudaGraphLaunch(c->graph, c->compute));
-        c->launches += c->kps;
-        if (c->lost_mode) { CK(cudaGraphLaunch(c->graph_global, c->compute)); c->launches += c->kps_global; }
+        CK(cudaGraphLaunch(c->graph, c->compute));   // lost-object mode: includes the conditional whole-frame pass
+        c->launches += c->kps + (c->lost_mode ? c->kps_global : 0);
     }
     if (copied) {
         CK(cudaEventRecord(c->ev_done[sd], c->compute));
@@ -1149,8 +1207,7 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             bool hold = false;
             if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
             CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
-            c->launches += hold ? 1 : c->kps;
-            if (!hold && c->lost_mode) { CK(cudaGraphLaunch(c->graph_global, c->compute)); c->launches += c->kps_global; }
+            c->launches += hold ? 1 : c->kps + (c->lost_mode ? c->kps_global : 0);
             c->submitted += 1;
             if (collect_every > 0 && (s + 1) % collect_every == 0) {
                 const unsigned long long first = c->submitted - collect_every;

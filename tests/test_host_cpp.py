@@ -56,6 +56,45 @@ def test_cli_trajectory_matches_golden(built, tmp_path, name, flags):
     Hp.check_records(got, g, f"cli {name} {flags}")
 
 
+def test_ghc_cli_builds_and_rejects(built, tmp_path):
+    exe = os.path.join(built, "tracker_ghc")
+    r = subprocess.run([exe, "nothing.bgr", "--cpu"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU path" in r.stderr
+    r = subprocess.run([exe, str(tmp_path / "missing.bgr")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Cannot open video:" in r.stderr         # tracker_ghc/src/main.cpp:84
+    (c, _) = Hp.clip("small")
+    write_clip(tmp_path / "c.bgr", c["frames"][:2])
+    r = subprocess.run([exe, str(tmp_path / "c.bgr"), "--first"], capture_output=True, text=True)
+    assert r.returncode != 0 and "No template selected" in r.stderr        # :117-120
+
+
+@pytest.mark.gpu
+def test_ghc_cli_reacquires_like_the_golden(built, tmp_path):
+    """tracker_ghc twin: local search -> lost -> whole-frame search -> re-acquired, as cv2 4.13.0 does it."""
+    import json
+    import zlib
+    from tools import synth
+    with open(os.path.join(Hp.GOLD, "meta_ghc.json")) as fh:
+        m = json.load(fh)["clips"]["reacquire"]
+    c = synth.make_clip(synth.ClipSpec(**m["spec"]))
+    assert zlib.crc32(np.ascontiguousarray(c["frames"]).tobytes()) & 0xFFFFFFFF == m["frames_crc"]
+    want = np.load(os.path.join(Hp.GOLD, "ghc_reacquire.npz"))["records"]
+    write_clip(tmp_path / "c.bgr", c["frames"])
+    roi = ",".join(str(v) for v in c["roi"])
+    tk = m["track"]
+    r = subprocess.run([os.path.join(built, "tracker_ghc"), str(tmp_path / "c.bgr"), "--first", "--roi", roi, "--out", str(tmp_path / "o.csv"),
+                        "--radius", str(tk["rx"]), "--lost", str(tk["lost_threshold"])], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Tracking mode: cuda" in r.stdout and f"Interactive tracking summary: frames={len(c['frames']) - 1}," in r.stdout
+    rows = np.genfromtxt(tmp_path / "o.csv", delimiter=",", skip_header=1)
+    assert np.array_equal(rows[:, 1:5], want[:, :4]) and np.array_equal(rows[:, 6:10], want[:, 5:9])
+    # use_global_search: the reference raises the flag at the START of the next frame (tracker_ghc/src/main.cpp:183-185), the
+    # library reports it as it will be evaluated there -- so it leads the golden's end-of-frame value by one frame
+    assert np.array_equal(rows[:-1, 10], np.maximum(want[:-1, 9], (want[1:, 7] == 2)))
+    assert np.abs(rows[:, 5] - want[:, 4]).max() <= Hp.TOL_SCORE
+    assert (rows[:, 8] == 2).sum() == m["global_frames"]
+
+
 @pytest.mark.gpu
 def test_cpp_operators_match_golden(built, tmp_path):
     g = Hp.golden("maps.npz")
