@@ -197,9 +197,15 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
                 const int bands = (G + GB - 1) / GB, ctas_band = (GB * C + kTilesPerCta - 1) / kTilesPerCta;
                 const long long ctas = (long long)n_tracks * bands * ctas_band * pj * pd;
                 const double work = 8.0 * CY * 8.0 * nchp * ndp;  // FMAs per thread
-                const long long rounds = (ctas + slots - 1) / slots;
-                const double rate = ctas > sm_count ? 870.0 : 1250.0;
+                double rounds = (double)((ctas + slots - 1) / slots);
                 const int parts = pj * pd;
+                if (parts == 1 && ctas > slots) {
+                    // the partial last round of an unsplit plan is cut along the template chunks (tail splitting, build_plan)
+                    const long long rem = ctas % slots;
+                    const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
+                    if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) rounds = (double)(ctas / slots) + 1.0 / ps + 0.03;
+                }
+                const double rate = ctas > sm_count ? 870.0 : 1250.0;
                 // the second stage reads parts*4+8 bytes and the first writes parts*4 bytes per candidate and track
                 const double split_us = parts > 1 ? 3.0 + 0.05 * parts + 1.5e-5 * (double)n_tracks * Wmax * Hmax * parts : 0.0;
                 const double us = rounds * (3.0 + work / rate) + split_us;
