@@ -330,3 +330,57 @@ def test_roi_ingest_equals_full_ingest(name):
         got = tr.collect(n - 1)
     assert np.array_equal(records_of(got[:, 0]), full[0])
     pin.free()
+
+
+# ---- window origin / clamp / fringe sweep -------------------------------------------------------------
+# k_ncc_search lays its thread tiles out from the window origin: the TMA tile is fetched from the origin rounded down to
+# 4 pixels and shifted in shared memory (all four alignments must give the same map), a remainder of exactly one row /
+# column of the window is computed by k_ncc_fringe (present only when the window is not clamped), and the K-split shape
+# (one track) and the throughput shape (many tracks) sum in different places.  Every position is checked against the
+# oracle's window map, in both shapes.
+@pytest.mark.parametrize("R,tw,th", [(40, 32, 32), (20, 24, 19), (12, 37, 29)])
+def test_window_origin_clamp_and_fringe_sweep(R, tw, th):
+    W, H = 333, 251
+    rng = np.random.default_rng(R * 1000 + tw)
+    base = rng.integers(0, 256, (H + 16, W + 16), dtype=np.uint8)
+    frame = np.stack([np.roll(base, s, axis=(0, 1))[:H, :W] for s in (0, 1, 2)], -1).copy()
+    nxt = np.clip(frame.astype(np.int16) + rng.integers(-3, 4, frame.shape), 0, 255).astype(np.uint8)
+    gray = O.to_gray_f32(nxt)
+    outW, outH = W - tw + 1, H - th + 1
+    xs = [0, 1, 2, 3, R - 1, R, R + 1, R + 2, R + 3, 150, 151, 152, 153, outW - 1 - R, outW - R, outW - 1]
+    ys = [0, 3, R, R + 1, 100, outH - 1 - R, outH - R + 5, outH - 1]
+    pos = [(x, y) for x in xs for y in ys if 0 <= x < outW and 0 <= y < outH]
+    n = len(pos)
+
+    def run(max_tracks, chunk):
+        maps = []
+        with pvt.Tracker(W, H, tw, th, max_streams=1, max_tracks=max_tracks, keep_maps=1, search_radius_x=R, search_radius_y=R) as tr:
+            for i0 in range(0, n, chunk):
+                grp = pos[i0:i0 + chunk]
+                for t, (x, y) in enumerate(grp):
+                    tr.init_track(t, frame if t == 0 else None, (x, y, tw, th))
+                for t in range(len(grp), max_tracks):
+                    if i0:
+                        tr.remove_track(t)
+                tr.step([nxt])
+                for t in range(len(grp)):
+                    maps.append(tr.window_map(t))
+        return maps
+
+    single = run(1, 1)          # latency shape (K-split, deferred fringe)
+    many = run(48, 48)          # throughput shape (unsplit, fringe behind the search)
+    templ_of = lambda x, y: O.to_gray_f32(frame)[y:y + th, x:x + tw].copy()
+    seen_fringe = seen_clamped = 0
+    for (x, y), (m1, w1), (m2, w2) in zip(pos, single, many):
+        win = O.search_window(x, y, tw, th, outW, outH, R, R)
+        assert w1 == win and w2 == win
+        want = O.ncc_window(gray, templ_of(x, y), *win)
+        sig = Hp.window_sigma(gray, tw, th, win)
+        for m in (m1, m2):
+            d = np.abs(m - want)
+            assert d[sig >= 0.002].max(initial=0) <= Hp.TOL_SCORE, (x, y)
+            assert np.argmax(m) == np.argmax(want), (x, y)
+        assert np.abs(m1 - m2).max() <= 2e-5
+        seen_fringe += win[2] == 2 * R + 1 and win[3] == 2 * R + 1
+        seen_clamped += win[2] < 2 * R + 1 or win[3] < 2 * R + 1
+    assert seen_fringe >= 4 and seen_clamped >= 20
