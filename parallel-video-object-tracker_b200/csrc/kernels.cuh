@@ -1088,11 +1088,18 @@ __device__ void finish_template(const Ctx& c, int track, TrackState& t, const fl
         t.templ_norm = sqrt(norm2) / sqrt(scale);
         t.tp = tpad;
     }
-    // centred template, CHUNK-MAJOR: tc[(x / 8) * th * 8 + y * 8 + (x % 8)], columns >= tw are zero
+    // centred template, CHUNK-MAJOR: tc[(x / 8) * th * 8 + y * 8 + (x % 8)], columns >= tw are zero.
+    // A thread writes whole 8-float rows (two 16-byte stores): one division per row instead of one per element.
     float* tc = c.templc + (size_t)track * c.mth * c.mtp;
-    for (int i = tid; i < th * tpad; i += blockDim.x) {
-        const int ch = i / (th * 8), r = i - ch * th * 8, y = r >> 3, x = ch * 8 + (r & 7);
-        tc[i] = x < tw ? (float)((double)s_t[y * tw + x] - mean) : 0.f;
+    for (int row = tid; row < th * (tpad >> 3); row += blockDim.x) {
+        const int ch = row / th, y = row - ch * th;
+        const float* src = s_t + y * tw + ch * 8;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ch * 8 + k < tw ? (float)((double)src[k] - mean) : 0.f;
+        float4* dst = reinterpret_cast<float4*>(tc + (size_t)row * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
 }
 
@@ -1120,18 +1127,23 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
             const double alpha = 1.0 - P.lr, beta = P.lr;
             float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
             const float* g = c.gray + (size_t)t.stream * c.plane + (size_t)ny * c.pitch + nx;
-            for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {   // 16 loads in flight per thread, then the EMA
-                float pv[8], tv[8];
+            // one batch of 32 loads per thread covers a 64 x 64 template with 256 threads: one L2 round trip, then the EMA.
+            // (row, column) of pixel i advance incrementally: no division per element
+            const int stride = blockDim.x, dq = stride / tw, dr = stride - dq * tw;
+            int r = threadIdx.x / tw, col = threadIdx.x - r * tw;
+            for (int i0 = threadIdx.x; i0 < n; i0 += 16 * stride) {
+                float pv[16], tv[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + k * blockDim.x;
-                    const int r = i / tw, col = i - r * tw;
+                for (int k = 0; k < 16; ++k) {
+                    const int i = i0 + k * stride;
                     pv[k] = i < n ? g[(size_t)r * c.pitch + col] : 0.f;
                     tv[k] = i < n ? tp_[i] : 0.f;
+                    col += dr; r += dq;
+                    if (col >= tw) { col -= tw; r += 1; }
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + k * blockDim.x;
+                for (int k = 0; k < 16; ++k) {
+                    const int i = i0 + k * stride;
                     if (i < n) {
                         const double pb = __dmul_rn((double)pv[k], beta);
                         const float v = (float)fma((double)tv[k], alpha, pb);

@@ -29,5 +29,8 @@ for k, nm in enumerate(names):
     st = np.median(T[:, k, 0] - T[:, 0, 0]) / 1e3; en = np.median(T[:, k, 1] - T[:, 0, 0]) / 1e3
     print("  %-13s start %7.2f  end %7.2f  dur %6.2f us  gap-before %6.2f" % (nm, st, en, en - st, st - prev_end if prev_end is not None else 0.0))
     prev_end = en
+if T[:, 7, 0].any():
+    b = T[:, 5, 0]
+    print("  DBGU update: EMA-done +%.2f  finish_template-done +%.2f (from update start)" % tuple(np.median(x - b) / 1e3 for x in (T[:, 7, 0], T[:, 7, 1])))
 nxt = np.median(T[1:, 0, 0] - T[:-1, 5, 1]) / 1e3
 print("  gap to next step's ingest: %.2f us" % nxt)
