@@ -67,6 +67,7 @@ __device__ __forceinline__ float4 ingest_group(const FrameDesc& d, const unsigne
 constexpr int kIngestGroups = 4;
 __global__ void __launch_bounds__(256) k_ingest(Ctx c)
 {
+    pdl_trigger();
     const unsigned long long step = *c.step;
     const int stream = blockIdx.y;
     if (c.global_pass && !c.stream_need[stream]) return;   // whole-frame pass: only streams with a lost track
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) k_ingest(Ctx c)
 // path reads them: every consumer (k_colprefix, the TMA tile's useful part, the EMA patch) stays inside the tile.
 __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
 {
+    pdl_trigger();
     const int track = blockIdx.y;
     const TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
 __global__ void __launch_bounds__(1024) k_colprefix(Ctx c)
 {
     __shared__ double tot[2][32][33];
+    pdl_trigger();
     const int track = blockIdx.y;
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     const TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
+    pdl_wait();   // k_colprefix (the window it stored in t.win, the column prefix sums) has completed
     trace_begin(c, step, TR_ROWSUM);
     const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * warps + w;
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
     // programmatic dependent launch: k_ncc_fringe (launched right behind this kernel in the throughput shape, and
     // independent of its results) may start as soon as every CTA of this grid has been dispatched, i.e. it fills the
     // SM slots that free up while the last round of search CTAs is still running
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_trigger();
     int item = blockIdx.x, part = blockIdx.z, pj = g.pj, pd = g.pd, tail_k = -1;
     if (g.tail_ps > 1 && item >= g.n_full) {           // a part of a tail item
         tail_k = item - g.n_full;
@@ -505,6 +509,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
             mbar_init(&empty[s], n_part);
         }
         fence_mbar_init();
+        pdl_wait();   // launched behind the ingest with a programmatic dependency (K-split shape): the gray plane is complete
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
         tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, t.stream);
         for (int s = 0; s < 2 && s < nj; ++s) {
@@ -936,6 +941,7 @@ __global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, TileCfg g)
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     const bool stepped = track_stepped(c, t, step);
+    pdl_wait();   // launched behind the search with a programmatic dependency (K-split shape): the partial sums are complete
     trace_begin(c, step, TR_FINALIZE);
     if (stepped) {
         const int ww = t.win[2], n = ww * t.win[3];

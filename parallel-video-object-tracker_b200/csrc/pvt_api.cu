@@ -36,6 +36,7 @@ int fail(int code, const std::string& msg)
                                           ":" + std::to_string(__LINE__) + ")");                            \
     } while (0)
 
+constexpr int kMultiStep = 4;   // steps per launch of graph_multi: a graph-to-graph boundary costs ~4 us on the device, an edge inside a graph ~1.5 us
 constexpr int kStageDepth = 3;  // host frames in flight per stream (H2D overlaps the previous step's kernels)
 constexpr size_t kSmemBudget = 227u * 1024u;
 
@@ -87,6 +88,7 @@ struct pvt_ctx {
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr;   // aux, aux2: further branches inside the captured graph
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
+    cudaGraphExec_t graph_multi = nullptr;   // kMultiStep consecutive time steps in one launch (resident frame rings)
     cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
     bool graph_valid = false;
     std::vector<void*> allocs;
@@ -196,7 +198,9 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
                 if (2 * (smem + 1024) > 228u * 1024u) continue;   // two CTAs per SM
                 const int bands = (G + GB - 1) / GB, ctas_band = (GB * C + kTilesPerCta - 1) / kTilesPerCta;
                 const long long ctas = (long long)n_tracks * bands * ctas_band * pj * pd;
-                const double work = 8.0 * CY * 8.0 * nchp * ndp;  // FMAs per thread
+                // FMAs per thread, plus the CY-1 window rows every template chunk preloads before its first row (they weigh
+                // in when a K-split part holds only a few template rows)
+                const double work = 8.0 * CY * 8.0 * nchp * (ndp + (pj * pd > 1 ? CY - 1 : 0));
                 double rounds = (double)((ctas + slots - 1) / slots);
                 const int parts = pj * pd;
                 if (parts == 1 && ctas > slots) {
@@ -207,7 +211,7 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
                 }
                 const double rate = ctas > sm_count ? 870.0 : 1250.0;
                 // the second stage reads parts*4+8 bytes and the first writes parts*4 bytes per candidate and track
-                const double split_us = parts > 1 ? 3.0 + 0.05 * parts + 1.5e-5 * (double)n_tracks * Wmax * Hmax * parts : 0.0;
+                const double split_us = parts > 1 ? 3.0 + 0.12 * parts + 2.5e-6 * (double)n_tracks * Wmax * Hmax * parts : 0.0;
                 const double us = rounds * (3.0 + work / rate) + split_us;
                 const double key = us * (1.0 + 1e-4 * parts) - 1e-6 * GB;
                 if (key < best) {
@@ -453,6 +457,23 @@ Pass global_pass(const pvt_ctx* c)
     return p;
 }
 
+// Launch with a programmatic dependency on the previous kernel of the stream (PDL): the kernel's CTAs may start while
+// that kernel is still draining (it has issued griddepcontrol.launch_dependents), run their preamble, and block in
+// griddepcontrol.wait until it has completed -- the launch latency of every such edge (~1.5 us on B200) leaves the
+// critical path of a time step.  pdl == false: plain stream order.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, args...));
+    return PVT_OK;
+}
+
 // The kernels of one searched time step.  capturing: being recorded into a CUDA graph on c->compute (fork/join allowed).
 // profile (only while capturing): external event-record NODES around each kernel class, so the measured durations are
 // GPU-side and contain no host launch gaps.  Classes: ingest | statistics | search (k_ncc_search [+ tail reduction]) |
@@ -486,8 +507,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     if (profile) { int r = pnode(c, CLS_STATS, 0, sstats); if (r) return r; }
     k_colprefix<<<dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats>>>(d);
     { int r = dbg(c, "k_colprefix"); if (r) return r; }
-    k_rowsum<<<dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), p.rowsum_warps * 32,
-               (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats>>>(d, p.rowsum_pw);
+    const bool pdl = capturing && !profile && p.pdl;   // programmatic edges: ingest ~> search, colprefix ~> rowsum, search ~> finalize
+    { int r = launch_pdl(k_rowsum, dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), dim3(p.rowsum_warps * 32),
+                         (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats, pdl, d, p.rowsum_pw); if (r) return r; }
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
@@ -526,7 +548,8 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         const int parts = p.tile.pj * p.tile.pd;
         const unsigned nbx = (unsigned)(p.tile.n_full + p.tile.n_tail * std::max(p.tile.tail_ps, 1));
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
-        k_ncc_search<kCY><<<dim3(nbx, 1, parts), kTilesPerCta, p.ncc_smem, c->compute>>>(d, p.tile, p.tmap);
+        // (in the K-split shape the search directly follows the ingest on this stream; otherwise the statistics, which it needs complete)
+        { int r = launch_pdl(k_ncc_search<kCY>, dim3(nbx, 1, parts), dim3(kTilesPerCta), p.ncc_smem, c->compute, pdl && fork, d, p.tile, p.tmap); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (fringe_after) {
             // programmatic dependent launch: the fringe kernel may begin once all search CTAs have been dispatched
@@ -545,7 +568,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
         if (parts > 1) {
             if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
-            k_ncc_finalize<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, c->templ_smem, c->compute>>>(d, p.tile);
+            { int r = launch_pdl(k_ncc_finalize, dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), dim3(256), c->templ_smem, c->compute, pdl && fork, d, p.tile); if (r) return r; }
             if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         }
     }
@@ -618,9 +641,10 @@ int build_graphs(pvt_ctx* c)
         CK(cudaGraphGetNodes(g, nullptr, &nn));
         std::vector<cudaGraphNode_t> nodes(nn);
         CK(cudaGraphGetNodes(g, nodes.data(), &nn));
-        CK(cudaGraphGetEdges(g, nullptr, nullptr, &ne));
+        CK(cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &ne));   // _v2: the graph has programmatic edges
         std::vector<cudaGraphNode_t> from(ne), to(ne);
-        if (ne) CK(cudaGraphGetEdges(g, from.data(), to.data(), &ne));
+        std::vector<cudaGraphEdgeData> ed(ne);
+        if (ne) CK(cudaGraphGetEdges_v2(g, from.data(), to.data(), ed.data(), &ne));
         std::vector<cudaGraphNode_t> leaves;
         for (cudaGraphNode_t n : nodes)
             if (std::find(from.begin(), from.end(), n) == from.end()) leaves.push_back(n);
@@ -629,6 +653,18 @@ int build_graphs(pvt_ctx* c)
     }
     CK(cudaGraphInstantiate(&c->graph, g, 0));
     CK(cudaGraphDestroy(g));
+    if (c->graph_multi) { cudaGraphExecDestroy(c->graph_multi); c->graph_multi = nullptr; }
+    if (!c->lost_mode) {
+        // every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
+        CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+        r = PVT_OK;
+        for (int k = 0; k < kMultiStep && !r; ++k) r = launch_step_kernels(c, lp, false, true);
+        e = cudaStreamEndCapture(c->compute, &g);
+        if (r) return r;
+        CK(e);
+        CK(cudaGraphInstantiate(&c->graph_multi, g, 0));
+        CK(cudaGraphDestroy(g));
+    }
     if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
     r = launch_step_kernels(c, lp, true, true);
@@ -874,6 +910,7 @@ int pvt_destroy(pvt_ctx* c)
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
     if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
+    if (c->graph_multi) cudaGraphExecDestroy(c->graph_multi);
     if (c->graph_global) cudaGraphExecDestroy(c->graph_global);
     for (int k = 0; k < 5; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
@@ -1210,11 +1247,22 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
         if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }
         const bool batch = c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1;
         for (int s = 0; s < n_steps; ++s) {
+            // several steps per launch while no result read-back falls inside the group
+            const bool multi_ok = !batch && c->graph_multi && s + kMultiStep <= n_steps &&
+                                  (collect_every <= 0 || (s % collect_every) + kMultiStep <= collect_every);
+            if (multi_ok) {
+                CK(cudaGraphLaunch(c->graph_multi, c->compute));
+                c->launches += (int64_t)kMultiStep * c->kps;
+                c->submitted += kMultiStep;
+                s += kMultiStep - 1;
+                if (collect_every <= 0 || (s + 1) % collect_every != 0) continue;
+            } else {
             bool hold = false;
             if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
             CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
             c->launches += hold ? 1 : c->kps + (c->lost_mode ? c->kps_global : 0);
             c->submitted += 1;
+            }
             if (collect_every > 0 && (s + 1) % collect_every == 0) {
                 const unsigned long long first = c->submitted - collect_every;
                 for (int k = 0; k < collect_every; ++k) {

@@ -160,6 +160,12 @@ __device__ __forceinline__ void trace_end(const Ctx& c, unsigned long long step,
     if (c.trace && threadIdx.x == 0 && threadIdx.y == 0) atomicMax(&c.trace[((step % kRing) * 8 + k) * 2 + 1], gtime());
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// pdl_trigger: kernels launched behind this one with the programmatic attribute may start now (they still block in
+// pdl_wait until this grid has completed and its writes are visible).  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- PTX helpers: mbarrier, TMA tensor load, bulk copy -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
