@@ -170,28 +170,34 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
     int pd_cap = 0, tpc = 0;
     (void)mtw;
     const bool fringe_ok = fringe_plan(mtp, mth, &tpc, &pd_cap);
-    const int G = (fringe_ok && Hmax > CY && Hmax % CY == 1) ? Hmax / CY : (Hmax + CY - 1) / CY;
-    const int C = (fringe_ok && Wmax > 8 && Wmax % 8 == 1) ? Wmax / 8 : (Wmax + 7) / 8;
-    auto span_of = [C](int GB) { return std::min(C, kTilesPerCta % GB == 0 ? kTilesPerCta / GB : (kTilesPerCta - 1) / GB + 2); };
+    // ... in UNSPLIT plans (the throughput shape, where every SM slot counts).  K-split plans (few tracks: the GPU is not
+    // full, what counts is the critical path of the step) keep the remainder in the grid as masked lanes: a sixth CTA per
+    // part runs beside the other five on an idle SM, and the step has one kernel and one graph branch less.
+    const int Gf = (fringe_ok && Hmax > CY && Hmax % CY == 1) ? Hmax / CY : (Hmax + CY - 1) / CY;
+    const int Cf = (fringe_ok && Wmax > 8 && Wmax % 8 == 1) ? Wmax / 8 : (Wmax + 7) / 8;
+    const int Gc = (Hmax + CY - 1) / CY, Cc = (Wmax + 7) / 8;
+    auto span_of = [](int C, int GB) { return std::min(C, kTilesPerCta % GB == 0 ? kTilesPerCta / GB : (kTilesPerCta - 1) / GB + 2); };
     const long long slots = (long long)sm_count * 2;
     double best = 1e300;
     // does the unsplit plan exist and fill at least one whole round?  then never K-split globally: the partial round at
     // the end is handled by tail splitting (pvt_create), which has none of the K-split's traffic
     bool unsplit_fills = false;
     {
-        const int boxH = G * CY + mth - 1, span = span_of(G), boxW = 8 * span + mtp + 4;
+        const int G = Gf, C = Cf;
+        const int boxH = G * CY + mth - 1, span = span_of(C, G), boxW = 8 * span + mtp + 4;
         const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
         const long long ctas = (long long)n_tracks * ((G * C + kTilesPerCta - 1) / kTilesPerCta);
         unsplit_fills = boxH <= 256 && boxW <= 256 && 2 * (smem + 1024) <= 228u * 1024u && ctas >= slots;
     }
     for (int pj = 1; pj <= (unsplit_fills ? 1 : nch); ++pj)
-        for (int pd = 1; pd <= (unsplit_fills ? 1 : std::min(mth, fringe_ok ? pd_cap : 32)); ++pd) {
+        for (int pd = 1; pd <= (unsplit_fills ? 1 : std::min(mth, 32)); ++pd) {
             const int nchp = (nch + pj - 1) / pj, ndp = (mth + pd - 1) / pd;
             if ((pj > 1 && (pj - 1) * nchp >= nch) || (pd > 1 && (pd - 1) * ndp >= mth)) continue;  // a part would be empty
+            const int G = pj * pd > 1 ? Gc : Gf, C = pj * pd > 1 ? Cc : Cf;
             for (int GB = G; GB >= 1; --GB) {
                 const int boxH = GB * CY + ndp - 1;
                 if (boxH > 256) continue;
-                const int span = span_of(GB);
+                const int span = span_of(C, GB);
                 const int boxW = 8 * span + 8 * nchp + 4;
                 if (boxW > 256) continue;
                 const size_t smem = (size_t)boxW * boxH * 4 + (size_t)4 * mth * 32 + 128;
@@ -212,7 +218,11 @@ bool choose_plan(int sm_count, int n_tracks, int mtw, int mtp, int mth, int Wmax
                 const double rate = ctas > sm_count ? 870.0 : 1250.0;
                 // the second stage reads parts*4+8 bytes and the first writes parts*4 bytes per candidate and track
                 const double split_us = parts > 1 ? 3.0 + 0.12 * parts + 2.5e-6 * (double)n_tracks * Wmax * Hmax * parts : 0.0;
-                const double us = rounds * (3.0 + work / rate) + split_us;
+                // K-split shape: the window statistics run beside the search (k_colprefix CTAs are 1024 threads wide and
+                // cannot share an SM with two search CTAs).  A search grid that fills every SM slot starves them and the
+                // statistics become the critical path (measured on C3: rowsum 58 us instead of 20): leave 8 SMs free.
+                const double starve_us = (parts > 1 && ctas > slots - 16 && ctas <= slots) ? 0.5 * (work / rate) : 0.0;
+                const double us = rounds * (3.0 + work / rate) + split_us + starve_us;
                 const double key = us * (1.0 + 1e-4 * parts) - 1e-6 * GB;
                 if (key < best) {
                     best = key;
@@ -270,10 +280,14 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
     Ctx& d = p.d;
     if (!choose_plan(sm_count, d.max_tracks, d.mtw, d.mtp, d.mth, d.Wmax, d.Hmax, &p.tile, &p.ncc_smem)) { return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
     }
-    if (const char* e = allow_env ? getenv("PVT_PLAN") : nullptr) {  // experiments: "GB,pj,pd" overrides the planner
-        int GB = 0, pj = 0, pd = 0;
-        if (sscanf(e, "%d,%d,%d", &GB, &pj, &pd) == 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
+    if (const char* e = allow_env ? getenv("PVT_PLAN") : nullptr) {  // experiments / tests: "GB,pj,pd[,f]" overrides the planner
+        int GB = 0, pj = 0, pd = 0, f = -1;                              // f = 1 / 0: remainder row / column out of / in the grid
+        if (sscanf(e, "%d,%d,%d,%d", &GB, &pj, &pd, &f) >= 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
             TileCfg& g = p.tile;
+            if (f >= 0) {
+                g.G = (f && d.Hmax > kCY && d.Hmax % kCY == 1) ? d.Hmax / kCY : (d.Hmax + kCY - 1) / kCY;
+                g.C = (f && d.Wmax > 8 && d.Wmax % 8 == 1) ? d.Wmax / 8 : (d.Wmax + 7) / 8;
+            }
             const int nch = d.mtp / 8, nchp = (nch + pj - 1) / pj, ndp = (d.mth + pd - 1) / pd;
             g.GB = std::min(GB, g.G); g.pj = pj; g.pd = pd;
             g.bands = (g.G + g.GB - 1) / g.GB; g.ctas_band = (g.GB * g.C + kTilesPerCta - 1) / kTilesPerCta;

@@ -367,16 +367,23 @@ def test_window_origin_clamp_and_fringe_sweep(R, tw, th):
                     maps.append(tr.window_map(t))
         return maps
 
-    single = run(1, 1)          # latency shape (K-split, deferred fringe)
-    many = run(48, 48)          # throughput shape (unsplit, fringe behind the search)
+    import os
+    single = run(1, 1)          # latency shape (K-split, the remainder stays in the grid as masked lanes)
+    os.environ["PVT_PLAN"] = "%d,1,1,1" % ((2 * R + 1) // 5)   # throughput shape as planned for a filled GPU: unsplit, remainder
+    try:                                                        # row / column in k_ncc_fringe behind the search (PDL)
+        many = run(48, 48)
+        os.environ["PVT_PLAN"] = "%d,2,3,1" % ((2 * R + 1) // 5)   # K-split ON TOP of the fringe geometry (deferred fringe)
+        forced = run(48, 48)
+    finally:
+        del os.environ["PVT_PLAN"]
     templ_of = lambda x, y: O.to_gray_f32(frame)[y:y + th, x:x + tw].copy()
     seen_fringe = seen_clamped = 0
-    for (x, y), (m1, w1), (m2, w2) in zip(pos, single, many):
+    for (x, y), (m1, w1), (m2, w2), (m3, w3) in zip(pos, single, many, forced):
         win = O.search_window(x, y, tw, th, outW, outH, R, R)
-        assert w1 == win and w2 == win
+        assert w1 == win and w2 == win and w3 == win
         want = O.ncc_window(gray, templ_of(x, y), *win)
         sig = Hp.window_sigma(gray, tw, th, win)
-        for m in (m1, m2):
+        for m in (m1, m2, m3):
             d = np.abs(m - want)
             assert d[sig >= 0.002].max(initial=0) <= Hp.TOL_SCORE, (x, y)
             assert np.argmax(m) == np.argmax(want), (x, y)
