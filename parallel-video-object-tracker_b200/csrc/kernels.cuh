@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     const int track = blockIdx.y;
     const TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
+    pdl_trigger();
     if (!track_stepped(c, t, step)) return;
     pdl_wait();   // k_colprefix (the window it stored in t.win, the column prefix sums) has completed
     trace_begin(c, step, TR_ROWSUM);
@@ -509,7 +510,9 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
             mbar_init(&empty[s], n_part);
         }
         fence_mbar_init();
-        pdl_wait();   // launched behind the ingest with a programmatic dependency (K-split shape): the gray plane is complete
+        // K-split shape: launched behind the ingest with a programmatic dependency -> the gray plane must be complete before
+        // the tile is fetched.  (Unsplit shape: launched behind k_rowsum, whose output only the epilogue needs: see below.)
+        if (split) pdl_wait();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
         tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, t.stream);
         for (int s = 0; s < 2 && s < nj; ++s) {
@@ -618,6 +621,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
                 po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
             }
         } else {
+            pdl_wait();   // unsplit shape: the window statistics (k_rowsum, the programmatic predecessor) are complete
             const double* dn = c.denom + woff;
             float* mp = c.params->keep_maps ? c.maps + woff : nullptr;
             const int flat = t.flat;

@@ -562,7 +562,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         const int parts = p.tile.pj * p.tile.pd;
         const unsigned nbx = (unsigned)(p.tile.n_full + p.tile.n_tail * std::max(p.tile.tail_ps, 1));
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
-        // (in the K-split shape the search directly follows the ingest on this stream; otherwise the statistics, which it needs complete)
+        // (K-split shape: the search directly follows the ingest on this stream and waits for it before fetching its tile.
+        //  Unsplit shape: a plain dependency on k_rowsum -- starting the search during the statistics' tail was measured and
+        //  lost 4 % on C4: k_ncc_fringe then has to wait for the whole search grid before it may read the normalisers)
         { int r = launch_pdl(k_ncc_search<kCY>, dim3(nbx, 1, parts), dim3(kTilesPerCta), p.ncc_smem, c->compute, pdl && fork, d, p.tile, p.tmap); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (fringe_after) {
@@ -1233,10 +1235,18 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
     if (n_steps < 0 || n_frames <= 0 || ring_len <= 0 || !frames) return fail(PVT_ERR_INVALID, "bad sequence arguments");
     if (collect_every > kRing) return fail(PVT_ERR_INVALID, "collect_every exceeds the 64-step results ring");
     const int mt = c->cfg.max_tracks;
-    // Resident ring fast path: every frame is device memory and the ring fits the table -> upload the ring's rows and a
-    // SeqDesc ONCE; after that a time step is a bare graph launch (no H2D, no host-side bookkeeping per frame).
+    // Resident ring fast path: every frame is device memory -- or PINNED host memory that the ROI ingest reads in place
+    // over PCIe (zero-copy: each step's tiles cross the bus inside k_ingest_roi) -- and the ring fits the table -> upload
+    // the ring's rows and a SeqDesc ONCE; after that a time step is a bare graph launch (no host-side bookkeeping per frame).
     bool resident = ring_len <= kRing && !c->profiling && !debug_sync() && n_steps > 0;
-    for (int i = 0; resident && i < ring_len * n_frames; ++i) resident = frames[i].memory == PVT_MEM_DEVICE;
+    std::vector<const void*> dptr((size_t)std::max(ring_len * n_frames, 0), nullptr);
+    for (int i = 0; resident && i < ring_len * n_frames; ++i) {
+        if (frames[i].memory == PVT_MEM_DEVICE) { dptr[i] = frames[i].data; continue; }
+        cudaPointerAttributes pa{};
+        if (c->roi_ingest && frames[i].data && cudaPointerGetAttributes(&pa, frames[i].data) == cudaSuccess &&
+            pa.type == cudaMemoryTypeHost && pa.devicePointer) dptr[i] = pa.devicePointer;
+        else { cudaGetLastError(); resident = false; }
+    }
     if (resident) {
         CK(cudaSetDevice(c->cfg.device));
         const int ms = c->cfg.max_streams;
@@ -1250,7 +1260,7 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
                 int r = check_frame(c, f);
                 if (r) return r;
                 if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
-                row[f->stream] = FrameDesc{f->data, (unsigned long long)f->step, f->format, 1};
+                row[f->stream] = FrameDesc{dptr[(size_t)k * n_frames + i], (unsigned long long)f->step, f->format, 1};
             }
         }
         CK(cudaMemcpyAsync(c->d.table, c->h_table, sizeof(FrameDesc) * (size_t)ring_len * ms, cudaMemcpyHostToDevice, c->compute));
