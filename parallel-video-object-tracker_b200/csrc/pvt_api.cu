@@ -86,7 +86,7 @@ struct pvt_ctx {
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr;   // aux, aux2: further branches inside the captured graph
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
     cudaGraphExec_t graph_multi = nullptr;   // kMultiStep consecutive time steps in one launch (resident frame rings)
     cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
@@ -433,12 +433,6 @@ bool debug_sync()
     static const bool on = [] { const char* e = getenv("PVT_DEBUG_SYNC"); return e && *e && *e != '0'; }();
     return on;
 }
-// PVT_FRINGE_BRANCH=1 (experiments): k_ncc_fringe on a parallel low-priority graph branch instead of behind the search kernel
-bool fringe_branch()
-{
-    static const bool on = [] { const char* e = getenv("PVT_FRINGE_BRANCH"); return e && *e && *e != '0'; }();
-    return on;
-}
 int dbg(pvt_ctx* c, const char* what)
 {
     if (!debug_sync()) return PVT_OK;
@@ -538,13 +532,6 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
             // latency shape: a third branch from the same fork point; the cross terms are left in fringe_acc
             // (FringeCfg.defer) and normalised by k_ncc_finalize, so this branch does not wait for the statistics
             CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
-            k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->aux2>>>(d, p.tile, p.fringe);
-            CK(cudaEventRecord(c->ev_join2, c->aux2));
-            join2 = true;
-        } else if (capturing && fringe_branch()) {
-            // throughput shape, experiment: after the statistics (the kernel normalises its own candidates), on a parallel branch
-            CK(cudaEventRecord(c->ev_fork2, c->compute));
-            CK(cudaStreamWaitEvent(c->aux2, c->ev_fork2, 0));
             k_ncc_fringe<<<fgrid, p.fringe.threads, p.fringe_smem, c->aux2>>>(d, p.tile, p.fringe);
             CK(cudaEventRecord(c->ev_join2, c->aux2));
             join2 = true;
@@ -940,7 +927,6 @@ int pvt_destroy(pvt_ctx* c)
     for (auto& p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->aux2) cudaStreamDestroy(c->aux2);
@@ -1027,7 +1013,6 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     CKD(cudaStreamCreateWithPriority(&c->aux2, cudaStreamNonBlocking, prio_lo));
     CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    CKD(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     const size_t win = (size_t)d.Wmax * d.Hmax;
     CR(dev_alloc(c, &d.gray, d.plane * d.max_streams));
