@@ -254,6 +254,40 @@ def test_device_resident_frames():
     assert np.array_equal(records_of(got[:, 0]), want)
 
 
+@pytest.mark.parametrize("memory,collect_every", [("device", 0), ("device", 5), ("device", 23), ("pinned", 0), ("pinned", 6), ("pageable", 4)])
+def test_submit_sequence_fast_paths_equal_step_by_step(memory, collect_every):
+    """pvt_submit_sequence over a frame ring: device-resident and pinned-host rings take the bare-graph-launch path (several
+    time steps per launch, pinned frames read zero-copy by the ROI ingest), pageable frames the staged path; read-backs may
+    fall anywhere relative to the multi-step launches.  All must reproduce the step-by-step records."""
+    torch = pytest.importorskip("torch")
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi)[0]
+    n, H, W, _ = frames.shape
+    if memory == "device":
+        buf = torch.from_numpy(frames).cuda()
+        torch.cuda.synchronize()
+    elif memory == "pinned":
+        buf = torch.from_numpy(frames).pin_memory()
+    else:
+        buf = torch.from_numpy(frames.copy())
+    mem = pvt.MEM_DEVICE if memory == "device" else pvt.MEM_HOST
+    ring = [[pvt.Frame(0, pvt.FMT_BGR8, mem, 0, buf[k].data_ptr(), W * 3)] for k in range(1, n)]
+    with pvt.Tracker(W, H, 32, 32, ingest=pvt.INGEST_ROI) as tr:
+        tr.init_track(0, frames[0], roi)
+        if collect_every:
+            k = ((n - 1) // collect_every) * collect_every
+            res = tr.submit_sequence(k, ring, collect_every=collect_every, want_results=True)
+            assert np.array_equal(records_of(res[:, 0]), want[:k])
+            if k < n - 1:
+                tr.submit_sequence(n - 1 - k, ring[k:] + ring[:k])
+        else:
+            tr.submit_sequence(n - 1, ring)
+        got = tr.collect(n - 1)
+    assert np.array_equal(records_of(got[:, 0]), want)
+    assert list(got[:, 0]["step"]) == list(range(n - 1))
+
+
 def test_state_roundtrip_and_errors():
     (c, _) = Hp.clip("small")
     frames, roi = c["frames"], c["roi"]
