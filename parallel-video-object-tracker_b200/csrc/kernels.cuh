@@ -246,23 +246,44 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     const double* cq0 = c.vsq + ((size_t)track * rows + y) * c.VW;
     const double* cs1 = cs0 + (size_t)th * c.VW;
     const double* cq1 = cq0 + (size_t)th * c.VW;
+    // Prefix row P[0 .. tileW] of this candidate row in shared memory, element i at PH(i) = i + (i >> 3): one double of
+    // padding per 8, so that lanes owning 8 consecutive elements (stride 9 doubles) and lanes reading consecutive
+    // elements are both bank-conflict-free.
+#define PH(i) ((i) + ((i) >> 3))
     double carry_s = 0.0, carry_q = 0.0;
     for (int base = 0; base < tileW; base += 256) {
-        const int i0 = base + lane * 8;
-        double a0[8], a1[8], b0[8], b1[8];
+        // (1) COALESCED global loads: lane reads elements base + lane + 32 m of the four prefix rows (a warp instruction
+        // touches 256 contiguous bytes; the lane-owns-8-consecutive pattern cost 8x the L1 tag lookups and made the kernel
+        // L1TEX-bound at 80 %), vertical box sums D = C[y+th] - C[y] staged through shared memory
+        {
+            double a0[8], a1[8], b0[8], b1[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {                       // 32 independent loads in flight per lane
-            const bool ok = i0 + k < tileW;
-            a0[k] = ok ? __ldg(cs0 + i0 + k) : 0.0;
-            a1[k] = ok ? __ldg(cs1 + i0 + k) : 0.0;
-            b0[k] = ok ? __ldg(cq0 + i0 + k) : 0.0;
-            b1[k] = ok ? __ldg(cq1 + i0 + k) : 0.0;
+            for (int m = 0; m < 8; ++m) {                       // 32 independent loads in flight per lane
+                const int i = base + lane + 32 * m;
+                const bool ok = i < tileW;
+                a0[m] = ok ? __ldg(cs0 + i) : 0.0;
+                a1[m] = ok ? __ldg(cs1 + i) : 0.0;
+                b0[m] = ok ? __ldg(cq0 + i) : 0.0;
+                b1[m] = ok ? __ldg(cq1 + i) : 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int i = base + lane + 32 * m;
+                if (i < tileW) {
+                    Ps[PH(i + 1)] = a1[m] - a0[m];              // vertical box sum of column i
+                    Pq[PH(i + 1)] = b1[m] - b0[m];
+                }
+            }
         }
+        __syncwarp();
+        // (2) inclusive prefix along x: every lane scans its 8 consecutive elements, then a warp scan of the lane totals
+        const int i0 = base + lane * 8;
         double ls[8], lq[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            ls[k] = a1[k] - a0[k];                          // vertical box sum of column i0+k
-            lq[k] = b1[k] - b0[k];
+            const bool ok = i0 + k < tileW;
+            ls[k] = ok ? Ps[PH(i0 + k + 1)] : 0.0;
+            lq[k] = ok ? Pq[PH(i0 + k + 1)] : 0.0;
         }
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
@@ -279,8 +300,8 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (i0 + k < tileW) {
-                Ps[i0 + k + 1] = off_s + ls[k];
-                Pq[i0 + k + 1] = off_q + lq[k];
+                Ps[PH(i0 + k + 1)] = off_s + ls[k];
+                Pq[PH(i0 + k + 1)] = off_q + lq[k];
             }
         carry_s += shfl_f64(is, 31);
         carry_q += shfl_f64(iq, 31);
@@ -291,8 +312,8 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     const double tn = t.templ_norm;
     double* dn = c.denom + (size_t)track * c.Hmax * c.Wmax + (size_t)y * ww;
     for (int x = lane; x < ww; x += 32) {
-        const double wsum = Ps[x + tw] - Ps[x];
-        const double wsq = Pq[x + tw] - Pq[x];
+        const double wsum = Ps[PH(x + tw)] - Ps[PH(x)];
+        const double wsq = Pq[PH(x + tw)] - Pq[PH(x)];
         // exactly OpenCV's operation order, no contraction: wndMean2 = t*t; wndMean2 *= invArea
         const double wm2 = __dmul_rn(__dmul_rn(wsum, wsum), invArea);
         double diff2 = __dsub_rn(wsq, wm2);
@@ -303,6 +324,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     }
     if (lane == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
+#undef PH
 
 // OpenCV's final rule for TM_CCOEFF_NORMED (common_matchTemplate): never NaN, always in [-1, 1]
 __device__ __forceinline__ float ncc_finalize(float num_f32, double t, int flat_templ)
@@ -885,15 +907,25 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
         for (int i = 0; i < CY; ++i)
 #pragma unroll
             for (int cx = 0; cx < 8; ++cx) acc[i][cx] = 0.f;
-        for (int p = 0; p < g.tail_ps; ++p) {
-            const float4* pi = reinterpret_cast<const float4*>(c.partial + (((size_t)blockIdx.x * g.tail_ps + p) * kTilesPerCta + threadIdx.x) * (8 * CY));
-            float4 v[2 * CY];
+        // four parts' partial sums are fetched per batch (40 independent 16-byte loads in flight: one L2 round trip per
+        // batch instead of one per part), then added in part order
+        for (int p0 = 0; p0 < g.tail_ps; p0 += 4) {
+            float4 v[4][2 * CY];
 #pragma unroll
-            for (int i = 0; i < 2 * CY; ++i) v[i] = __ldg(pi + i);
+            for (int b = 0; b < 4; ++b) {
+                const float4* pi = reinterpret_cast<const float4*>(c.partial + (((size_t)blockIdx.x * g.tail_ps + min(p0 + b, g.tail_ps - 1)) * kTilesPerCta + threadIdx.x) * (8 * CY));
 #pragma unroll
-            for (int i = 0; i < CY; ++i) {
-                acc[i][0] += v[2 * i].x; acc[i][1] += v[2 * i].y; acc[i][2] += v[2 * i].z; acc[i][3] += v[2 * i].w;
-                acc[i][4] += v[2 * i + 1].x; acc[i][5] += v[2 * i + 1].y; acc[i][6] += v[2 * i + 1].z; acc[i][7] += v[2 * i + 1].w;
+                for (int i = 0; i < 2 * CY; ++i) v[b][i] = __ldg(pi + i);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (p0 + b < g.tail_ps) {
+#pragma unroll
+                    for (int i = 0; i < CY; ++i) {
+                        acc[i][0] += v[b][2 * i].x; acc[i][1] += v[b][2 * i].y; acc[i][2] += v[b][2 * i].z; acc[i][3] += v[b][2 * i].w;
+                        acc[i][4] += v[b][2 * i + 1].x; acc[i][5] += v[b][2 * i + 1].y; acc[i][6] += v[b][2 * i + 1].z; acc[i][7] += v[b][2 * i + 1].w;
+                    }
+                }
             }
         }
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;

@@ -349,7 +349,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
     if (p.tile.pj * p.tile.pd > 1)   // tile-major partial cross terms: [parts][tracks][CTAs per track * 128 tiles][8 * kCY]
         { int r_ = dev_alloc(c, &d.partial, (size_t)p.tile.pj * p.tile.pd * d.max_tracks * p.tile.bands * p.tile.ctas_band * kTilesPerCta * 8 * kCY, false); if (r_) return r_; }
     { int r_ = raise_smem((const void*)k_ncc_search<kCY>, p.ncc_smem); if (r_) return r_; }
-    p.rowsum_pw = d.VW + 8;
+    p.rowsum_pw = (d.VW + 8) + ((d.VW + 8) >> 3) + 2;   // prefix row incl. one padding double per 8 (k_rowsum PH())
     p.rowsum_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / ((size_t)2 * p.rowsum_pw * sizeof(double))));
     { int r_ = raise_smem((const void*)k_rowsum, (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double)); if (r_) return r_; }
     // k_colprefix: ~28 rows per thread (8 chunks for a 224-row tracker tile, up to 32 for full-frame maps)
