@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(1024) k_colprefix(Ctx c)
     const int r0 = min(ch * rc, tileH), r1 = min(r0 + rc, tileH);
     const bool okx = X < tileW;
     const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)win[1] * c.pitch + win[0] + X;
+    pdl_wait();   // K-split shape: launched behind the ingest with a programmatic dependency; the gray plane is complete now
     double s = 0.0, q = 0.0;
     if (okx) {
         // loads are issued in batches of 16 before any is consumed: one L2 round trip per batch instead of one per row
@@ -1005,12 +1006,12 @@ __global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, TileCfg g)
             const size_t woff = (size_t)track * c.Hmax * c.Wmax;
             const double dnv = __ldg(c.denom + woff + idx);
             float acc = 0.f;
-            for (int p0 = 0; p0 < parts; p0 += 16) {           // 16 independent loads in flight, added in part order
-                float pv[16];
+            for (int p0 = 0; p0 < parts; p0 += 32) {           // 32 independent loads in flight, added in part order
+                float pv[32];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) pv[k] = (p0 + k < parts) ? __ldg(src + (size_t)(p0 + k) * stride) : 0.f;
+                for (int k = 0; k < 32; ++k) pv[k] = (p0 + k < parts) ? __ldg(src + (size_t)(p0 + k) * stride) : 0.f;
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
+                for (int k = 0; k < 32; ++k)
                     if (p0 + k < parts) acc += pv[k];
             }
             const float v = ncc_finalize(acc, dnv, t.flat);
@@ -1223,14 +1224,17 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
     // last track done -> advance the time step (every kernel of this step has read *c.step already).
     // With two passes per step (lost-object mode) k_step_advance does it after both.
     if (c.lost_mode) return;
-    __syncthreads();
+    // No fences: the counter is only read by the kernels of the NEXT step, which start after this kernel has completed
+    // (nobody in this launch reads it again), and a context with a single track needs no arrival count either.
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int n = atomicAdd(c.ticket, 1u);
-        if (n == (unsigned int)c.max_tracks - 1u) {
-            *c.ticket = 0u;
+        if (c.max_tracks == 1) {
             *c.step = step + 1ull;
-            __threadfence();
+        } else {
+            const unsigned int n = atomicAdd(c.ticket, 1u);
+            if (n == (unsigned int)c.max_tracks - 1u) {
+                *c.ticket = 0u;
+                *c.step = step + 1ull;
+            }
         }
     }
 }
