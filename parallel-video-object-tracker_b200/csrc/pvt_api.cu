@@ -280,7 +280,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
     Ctx& d = p.d;
     if (!choose_plan(sm_count, d.max_tracks, d.mtw, d.mtp, d.mth, d.Wmax, d.Hmax, &p.tile, &p.ncc_smem)) { return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
     }
-    if (const char* e = allow_env ? getenv("PVT_PLAN") : nullptr) {  // experiments / tests: "GB,pj,pd[,f]" overrides the planner
+    if (const char* e = allow_env ? getenv("PVT_PLAN") : getenv("PVT_PLAN_GLOBAL")) {  // experiments / tests: "GB,pj,pd[,f]" overrides the planner
         int GB = 0, pj = 0, pd = 0, f = -1;                              // f = 1 / 0: remainder row / column out of / in the grid
         if (sscanf(e, "%d,%d,%d,%d", &GB, &pj, &pd, &f) >= 3 && GB > 0 && pj > 0 && pd > 0 && pd <= 32) {
             TileCfg& g = p.tile;
