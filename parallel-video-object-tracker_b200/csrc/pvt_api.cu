@@ -98,6 +98,7 @@ struct pvt_ctx {
     std::vector<void*> stage;  // [max_streams * kStageDepth], lazily allocated
     size_t stage_bytes = 0;
     cudaEvent_t ev_done[kStageDepth]{}, ev_copied[kStageDepth]{};
+    cudaEvent_t rb_ready[2]{}, rb_done[2]{};   // pipelined result read-back (pvt_submit_sequence)
     bool ev_done_used[kStageDepth]{};
     unsigned long long submitted = 0;  // time steps enqueued
     int hold_pending = 0;              // batch mode: frames since the last searched one
@@ -815,6 +816,21 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
     return PVT_OK;
 }
 
+// a batch of result rows on its way to the host (pvt_submit_sequence, resident rings)
+struct Readback {
+    unsigned long long first;   // first time step of the batch
+    int n, out_row, ev;         // steps, first row in results_out, event pair
+};
+int finish_readback(pvt_ctx* c, Readback& rb, pvt_result* results_out, int mt)
+{
+    CK(cudaEventSynchronize(c->rb_done[rb.ev]));
+    if (results_out)
+        for (int k = 0; k < rb.n; ++k)
+            std::memcpy(results_out + (size_t)(rb.out_row + k) * mt, c->h_results + (size_t)((rb.first + k) % kRing) * mt, sizeof(pvt_result) * mt);
+    rb.n = 0;
+    return PVT_OK;
+}
+
 int resolve_profile(pvt_ctx* c)
 {
     CK(cudaStreamSynchronize(c->compute));
@@ -925,6 +941,7 @@ int pvt_destroy(pvt_ctx* c)
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     }
     for (auto& p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (int k = 0; k < 2; ++k) { if (c->rb_ready[k]) cudaEventDestroy(c->rb_ready[k]); if (c->rb_done[k]) cudaEventDestroy(c->rb_done[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
@@ -1041,6 +1058,10 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CKD(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     }
     for (int k = 0; k < 5; ++k) { CKD(cudaEventCreate(&c->pev[k][0])); CKD(cudaEventCreate(&c->pev[k][1])); }
+    for (int k = 0; k < 2; ++k) {
+        CKD(cudaEventCreateWithFlags(&c->rb_ready[k], cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->rb_done[k], cudaEventDisableTiming));
+    }
     CKD(cudaEventCreate(&c->timer_a));
     CKD(cudaEventCreate(&c->timer_b));
     c->stage.assign((size_t)d.max_streams * kStageDepth, nullptr);
@@ -1248,6 +1269,8 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
                 row[f->stream] = FrameDesc{dptr[(size_t)k * n_frames + i], (unsigned long long)f->step, f->format, 1};
             }
         }
+        Readback pend[2] = {};
+        bool had_prev = false;
         CK(cudaMemcpyAsync(c->d.table, c->h_table, sizeof(FrameDesc) * (size_t)ring_len * ms, cudaMemcpyHostToDevice, c->compute));
         CK(cudaEventRecord(c->table_ev[0], c->compute));
         c->table_ev_used[0] = true;
@@ -1273,19 +1296,32 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             c->submitted += 1;
             }
             if (collect_every > 0 && (s + 1) % collect_every == 0) {
+                // Device -> host read of these steps' results WITHOUT draining the pipeline: the copy runs on the copy stream
+                // behind an event, the host goes on enqueuing the next batch and picks the rows up one batch later.
+                // (Batches of at most half the 64-step results ring; larger ones are read back synchronously.)
                 const unsigned long long first = c->submitted - collect_every;
+                const bool lag = 2 * collect_every <= kRing;
+                const int b = (int)(((s + 1) / collect_every - 1) & 1);
+                if (lag && pend[b ^ 1].n) { int r2 = finish_readback(c, pend[b ^ 1], results_out, mt); if (r2) return r2; }
+                CK(cudaEventRecord(c->rb_ready[b], c->compute));
+                CK(cudaStreamWaitEvent(c->copy, c->rb_ready[b], 0));
                 for (int k = 0; k < collect_every; ++k) {
                     const int slot = (int)((first + k) % kRing);
                     CK(cudaMemcpyAsync(c->h_results + (size_t)slot * mt, c->d.results + (size_t)slot * mt, sizeof(pvt_result) * mt,
-                                       cudaMemcpyDeviceToHost, c->compute));
+                                       cudaMemcpyDeviceToHost, c->copy));
                 }
-                CK(cudaStreamSynchronize(c->compute));
-                if (results_out)
-                    for (int k = 0; k < collect_every; ++k)
-                        std::memcpy(results_out + (size_t)(s + 1 - collect_every + k) * mt, c->h_results + (size_t)((first + k) % kRing) * mt,
-                                    sizeof(pvt_result) * mt);
+                CK(cudaEventRecord(c->rb_done[b], c->copy));
+                // the steps that overwrite result slots (64 steps after the ones that filled them) must not start before the
+                // slots have been copied: the NEXT batch waits for the PREVIOUS batch's copy (this batch's own when not lagging)
+                if (!lag) CK(cudaStreamWaitEvent(c->compute, c->rb_done[b], 0));
+                else if (had_prev) CK(cudaStreamWaitEvent(c->compute, c->rb_done[b ^ 1], 0));
+                had_prev = true;
+                pend[b] = Readback{first, collect_every, s + 1 - collect_every, b};
+                if (!lag) { int r2 = finish_readback(c, pend[b], results_out, mt); if (r2) return r2; }
             }
         }
+        for (int b = 0; b < 2; ++b)
+            if (pend[b].n) { int r2 = finish_readback(c, pend[b], results_out, mt); if (r2) return r2; }
         return PVT_OK;
     }
     for (int s = 0; s < n_steps; ++s) {

@@ -8,7 +8,8 @@ wname = sys.argv[1] if len(sys.argv) > 1 else "C2"
 wl = dict(bench.WORKLOADS[wname])
 W, H, tw, th, R, L, S = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], wl["ring"], wl["streams"]
 scenes, host, dev = bench.build_rings(wl, 0, torch)
-ring = bench.ring_descs(pvt, wl, dev, True)
+on_host = len(sys.argv) > 2 and sys.argv[2] == "host"   # pinned host ring: the ROI ingest reads the tiles zero-copy over PCIe
+ring = bench.ring_descs(pvt, wl, host if on_host else dev, not on_host)
 tr = pvt.Tracker(W, H, tw, th, max_streams=S, max_tracks=S * wl["rois"], search_radius_x=R, search_radius_y=R)
 t = 0
 for s in range(S):
