@@ -335,10 +335,15 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
     tre.close()
     roi = ingest_mode.startswith("roi")
     tile_bytes = n_tracks * (2 * R + 1 + tw + 3) * (2 * R + th) * 3
+    prefetch = roi and n_tracks <= 8      # pvt_create's condition for k_prefetch_roi (pinned host rings)
+    if prefetch:                          # the tile grown by R on every side crosses PCIe instead of the tile (clamped at the frame)
+        tile_bytes = n_tracks * min(W, 3 * R + 1 + tw + 3) * min(H, 3 * R + th) * 3
     out["e2e"] = {"value": world * S * Ke / e2e_s, "unit": "frames/s",
                   "h2d_bytes_per_step": int(tile_bytes if roi else S * W * H * 3), "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke,
-                  "how": ("pvt_submit_sequence over pinned host BGR frames; ROI ingest reads the search tiles zero-copy over PCIe "
-                          "(bytes = tiles actually read; whole frames are %d B); results read back every %d steps" % (S * W * H * 3, ce)) if roi else
+                  "how": ("pvt_submit_sequence over pinned host BGR frames; " +
+                          ("k_prefetch_roi reads the next step's likely search tile (the tile grown by R/2) zero-copy over PCIe beside the current step; "
+                           if prefetch else "ROI ingest reads the search tiles zero-copy over PCIe; ") +
+                          "bytes = pixels actually read (whole frames are %d B); results read back every %d steps, pipelined" % (S * W * H * 3, ce)) if roi else
                          "pvt_submit_sequence over pinned host BGR frames, staged H2D copy of whole frames; results read back every %d steps" % ce}
     out["_scene0"], out["_host0"] = scenes[0], host[0].numpy()
     return out

@@ -137,12 +137,101 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     const int x0 = win[0] & ~3, x1 = min(c.W, win[0] + win[2] + t.w - 1), rows = win[3] + t.h - 1;
     const int gpr = (x1 - x0 + 3) >> 2;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c.stage && gid < 4) c.stage_hdr[track].win[gid] = win[gid];   // for k_prefetch_roi, which runs behind this kernel
     if (gid >= gpr * rows) return;
     const int r = gid / gpr, x = x0 + ((gid - r * gpr) << 2), y = win[1] + r;
     float* out = c.gray + (size_t)t.stream * c.plane + (size_t)y * c.pitch + x;
+    // Did k_prefetch_roi stage this tile during the previous step (pinned host rings)?  Then it is a device-to-device copy
+    // of already converted pixels; the zero-copy read over PCIe happened off the critical path.
+    if (c.stage) {
+        const StageHdr h = c.stage_hdr[track];
+        if (h.step == step && h.data == d.data && x0 >= h.x0 && x1 <= h.x1 && win[1] >= h.y0 && win[1] + rows <= h.y1) {
+            const float* sp = c.stage + (size_t)track * c.stage_w * c.stage_h + (size_t)(y - h.y0) * c.stage_w + (x - h.x0);
+            *reinterpret_cast<float4*>(out) = *reinterpret_cast<const float4*>(sp);
+            trace_end(c, step, TR_INGEST);
+            return;
+        }
+    }
     const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
     *reinterpret_cast<float4*>(out) = ingest_group(d, row, x, min(4, c.W - x));
     trace_end(c, step, TR_INGEST);
+}
+
+// Pinned host rings (SeqDesc.prefetch): while time step k computes, convert the pixels step k+1 will most likely need into
+// a per-track staging buffer: the current search tile grown by HALF the search radius on every side (the next tile lies
+// inside it whenever the box moves by at most R/2 in this step; otherwise the next ingest simply reads zero-copy as
+// before -- the staging is an accelerator, never a correctness dependency).  ~1.9x the tile's bytes cross PCIe, but
+// beside the step instead of in front of its search.  Runs on a parallel graph branch that joins at the end of the step;
+// it works from the window k_ingest_roi recorded, not from the box, which the step's update moves.
+__global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c)
+{
+    const SeqDesc q = *c.seq;
+    if (!q.prefetch) return;
+    const int track = blockIdx.y;
+    const TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!t.active) return;
+    const size_t nrow = (size_t)(q.row0 + (int)((step + 1ull - q.step0) % (unsigned long long)q.ring_len)) * c.max_streams;
+    const FrameDesc d = c.table[nrow + t.stream];
+    StageHdr* hdr = c.stage_hdr + track;
+    if (!d.valid) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) hdr->step = ~0ull;
+        return;
+    }
+    const DevParams P = *c.params;
+    const int win[4] = {hdr->win[0], hdr->win[1], hdr->win[2], hdr->win[3]};
+    if (win[2] <= 0 || win[3] <= 0) return;
+    const int gx = P.rx / 2, gy = P.ry / 2;
+    const int x0 = max(0, win[0] - gx) & ~3, x1 = min(c.W, win[0] + win[2] + t.w - 1 + gx);
+    const int y0 = max(0, win[1] - gy), y1 = min(c.H, win[1] + win[3] + t.h - 1 + gy);
+    const int gpr = (x1 - x0 + 3) >> 2, rows = y1 - y0;
+    if (gpr * 4 > c.stage_w || rows > c.stage_h) {      // cannot happen with the sizes pvt_create derives; never overrun
+        if (blockIdx.x == 0 && threadIdx.x == 0) hdr->step = ~0ull;
+        return;
+    }
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (gid == 0) { hdr->x0 = x0; hdr->y0 = y0; hdr->x1 = x1; hdr->y1 = y1; hdr->step = step + 1ull; hdr->data = d.data; }
+    // A SMALL grid (it shares the GPU with the step's own kernels), every thread converts several 4-pixel groups and has all
+    // their loads in flight before the first conversion: the reads are PCIe round trips
+    float* stage = c.stage + (size_t)track * c.stage_w * c.stage_h;
+    const int total = gpr * rows;
+    const bool fast = d.format == PVT_FMT_BGR8 && ((((size_t)d.data) | d.step) & 3) == 0 && (c.W & 3) == 0;
+    for (int g0 = gid; g0 < total; g0 += 4 * nthr) {
+        if (fast) {
+            unsigned int a[4], b[4], e[4];
+            int off[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int g = g0 + k * nthr;
+                off[k] = -1;
+                if (g < total) {
+                    const int r = g / gpr, x = x0 + ((g - r * gpr) << 2);
+                    const unsigned int* p32 = (const unsigned int*)((const unsigned char*)d.data + (size_t)(y0 + r) * d.step + 3 * x);
+                    a[k] = __ldg(p32); b[k] = __ldg(p32 + 1); e[k] = __ldg(p32 + 2);
+                    off[k] = r * c.stage_w + (x - x0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (off[k] >= 0) {
+                    float4 o;  // bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                    o.x = gray_to_f32(bgr_to_gray(a[k] & 255u, (a[k] >> 8) & 255u, (a[k] >> 16) & 255u));
+                    o.y = gray_to_f32(bgr_to_gray(a[k] >> 24, b[k] & 255u, (b[k] >> 8) & 255u));
+                    o.z = gray_to_f32(bgr_to_gray((b[k] >> 16) & 255u, b[k] >> 24, e[k] & 255u));
+                    o.w = gray_to_f32(bgr_to_gray((e[k] >> 8) & 255u, (e[k] >> 16) & 255u, e[k] >> 24));
+                    *reinterpret_cast<float4*>(stage + off[k]) = o;
+                }
+            }
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                const int g = g0 + k * nthr;
+                if (g >= total) break;
+                const int r = g / gpr, x = x0 + ((g - r * gpr) << 2);
+                const unsigned char* row = (const unsigned char*)d.data + (size_t)(y0 + r) * d.step;
+                *reinterpret_cast<float4*>(stage + (size_t)r * c.stage_w + (x - x0)) = ingest_group(d, row, x, min(4, c.W - x));
+            }
+        }
+    }
 }
 
 // =============================================================================================

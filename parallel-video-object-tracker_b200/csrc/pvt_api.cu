@@ -63,6 +63,7 @@ struct Pass {
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
     bool pdl = true;           // k_ncc_fringe behind the search with a programmatic dependency (plain stream order otherwise)
+    bool prefetch = false;     // k_prefetch_roi beside the step (graphs for pinned host rings)
 };
 
 }  // namespace
@@ -85,10 +86,12 @@ struct pvt_ctx {
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
-    cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr;   // aux, aux2: further branches inside the captured graph
+    cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;   // aux*: further branches inside the captured graph
+    cudaEvent_t ev_join3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
     cudaGraphExec_t graph_multi = nullptr;   // kMultiStep consecutive time steps in one launch (resident frame rings)
+    cudaGraphExec_t graph_pf = nullptr, graph_multi_pf = nullptr;   // the same with k_prefetch_roi (pinned host rings)
     cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
     bool graph_valid = false;
     std::vector<void*> allocs;
@@ -403,11 +406,11 @@ int upload_params(pvt_ctx* c)
     return PVT_OK;
 }
 
-int upload_seq(pvt_ctx* c, unsigned long long step0, int ring_len, int row0)
+int upload_seq(pvt_ctx* c, unsigned long long step0, int ring_len, int row0, int prefetch = 0)
 {
-    SeqDesc q{step0, ring_len, row0};
+    SeqDesc q{step0, ring_len, row0, prefetch, 0};
     CK(cudaMemcpyAsync(c->d.seq, &q, sizeof(q), cudaMemcpyHostToDevice, c->compute));  // pageable source: staged before return
-    c->seq_default = (step0 == 0 && ring_len == kRing && row0 == 0);
+    c->seq_default = (step0 == 0 && ring_len == kRing && row0 == 0 && !prefetch);
     return PVT_OK;
 }
 
@@ -502,6 +505,21 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     if (profile) { int r = pnode(c, CLS_INGEST, 1, c->compute); if (r) return r; }
     { int r = dbg(c, "k_ingest"); if (r) return r; }
+    // pinned host rings: stage the next step's pixels beside this step (a branch that joins before the box moves)
+    bool join3 = false;
+    if (d.stage && p.roi_ingest && !d.global_pass && p.prefetch) {
+        const dim3 pgrid(24, (unsigned)d.max_tracks);   // small on purpose: see k_prefetch_roi
+        if (capturing) {
+            CK(cudaEventRecord(c->ev_fork, c->compute));
+            CK(cudaStreamWaitEvent(c->aux3, c->ev_fork, 0));
+            k_prefetch_roi<<<pgrid, 256, 0, c->aux3>>>(d);
+            CK(cudaEventRecord(c->ev_join3, c->aux3));
+            join3 = true;
+        } else {
+            k_prefetch_roi<<<pgrid, 256, 0, c->compute>>>(d);
+            { int r = dbg(c, "k_prefetch_roi"); if (r) return r; }
+        }
+    }
 
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
@@ -584,6 +602,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_update"); if (r) return r; }
     }
+    if (join3) CK(cudaStreamWaitEvent(c->compute, c->ev_join3, 0));   // the prefetch branch ends with the step
     CK(cudaGetLastError());
     return PVT_OK;
 }
@@ -668,6 +687,22 @@ int build_graphs(pvt_ctx* c)
         CK(e);
         CK(cudaGraphInstantiate(&c->graph_multi, g, 0));
         CK(cudaGraphDestroy(g));
+    }
+    if (c->graph_pf) { cudaGraphExecDestroy(c->graph_pf); c->graph_pf = nullptr; }
+    if (c->graph_multi_pf) { cudaGraphExecDestroy(c->graph_multi_pf); c->graph_multi_pf = nullptr; }
+    if (!c->lost_mode && c->d.stage) {
+        Pass pp = lp;
+        pp.prefetch = true;
+        for (int variant = 0; variant < 2; ++variant) {
+            CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+            r = PVT_OK;
+            for (int k = 0; k < (variant ? kMultiStep : 1) && !r; ++k) r = launch_step_kernels(c, pp, false, true);
+            e = cudaStreamEndCapture(c->compute, &g);
+            if (r) return r;
+            CK(e);
+            CK(cudaGraphInstantiate(variant ? &c->graph_multi_pf : &c->graph_pf, g, 0));
+            CK(cudaGraphDestroy(g));
+        }
     }
     if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
@@ -930,6 +965,8 @@ int pvt_destroy(pvt_ctx* c)
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
     if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
     if (c->graph_multi) cudaGraphExecDestroy(c->graph_multi);
+    if (c->graph_pf) cudaGraphExecDestroy(c->graph_pf);
+    if (c->graph_multi_pf) cudaGraphExecDestroy(c->graph_multi_pf);
     if (c->graph_global) cudaGraphExecDestroy(c->graph_global);
     for (int k = 0; k < 5; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
@@ -947,6 +984,8 @@ int pvt_destroy(pvt_ctx* c)
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->aux2) cudaStreamDestroy(c->aux2);
+    if (c->aux3) cudaStreamDestroy(c->aux3);
+    if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -1028,6 +1067,8 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     CKD(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CKD(cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, prio_hi));
     CKD(cudaStreamCreateWithPriority(&c->aux2, cudaStreamNonBlocking, prio_lo));
+    CKD(cudaStreamCreateWithPriority(&c->aux3, cudaStreamNonBlocking, prio_lo));
+    CKD(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
@@ -1077,6 +1118,13 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         c->roi_ingest = lp.roi_ingest;
     }
     c->kps = pass_kernels(c->tile, c->fringe);
+    if (c->roi_ingest && !c->lost_mode && d.max_tracks <= 8) {
+        // staging buffers of k_prefetch_roi: the search tile grown by the search radius on every side
+        d.stage_w = (d.Wmax + c->cfg.max_radius_x + d.mtw + 8 + 3) & ~3;
+        d.stage_h = d.Hmax + c->cfg.max_radius_y + d.mth;
+        CR(dev_alloc(c, &d.stage, (size_t)d.max_tracks * d.stage_w * d.stage_h));
+        CR(dev_alloc(c, &d.stage_hdr, (size_t)d.max_tracks));
+    }
     c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
     if (c->templ_smem > 48u * 1024u) {
         CR(raise_smem((const void*)k_update, c->templ_smem));
@@ -1246,8 +1294,10 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
     // the ring's rows and a SeqDesc ONCE; after that a time step is a bare graph launch (no host-side bookkeeping per frame).
     bool resident = ring_len <= kRing && !c->profiling && !debug_sync() && n_steps > 0;
     std::vector<const void*> dptr((size_t)std::max(ring_len * n_frames, 0), nullptr);
+    bool any_host = false;
     for (int i = 0; resident && i < ring_len * n_frames; ++i) {
         if (frames[i].memory == PVT_MEM_DEVICE) { dptr[i] = frames[i].data; continue; }
+        any_host = true;
         cudaPointerAttributes pa{};
         if (c->roi_ingest && frames[i].data && cudaPointerGetAttributes(&pa, frames[i].data) == cudaSuccess &&
             pa.type == cudaMemoryTypeHost && pa.devicePointer) dptr[i] = pa.devicePointer;
@@ -1274,25 +1324,27 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
         CK(cudaMemcpyAsync(c->d.table, c->h_table, sizeof(FrameDesc) * (size_t)ring_len * ms, cudaMemcpyHostToDevice, c->compute));
         CK(cudaEventRecord(c->table_ev[0], c->compute));
         c->table_ev_used[0] = true;
-        int r = upload_seq(c, c->submitted, ring_len, 0);
+        const bool pf = any_host && c->d.stage && !c->lost_mode;
+        int r = upload_seq(c, c->submitted, ring_len, 0, pf ? 1 : 0);
         if (r) return r;
         if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }
+        cudaGraphExec_t g_one = pf ? c->graph_pf : c->graph, g_multi = pf ? c->graph_multi_pf : c->graph_multi;
         const bool batch = c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1;
         for (int s = 0; s < n_steps; ++s) {
             // several steps per launch while no result read-back falls inside the group
-            const bool multi_ok = !batch && c->graph_multi && s + kMultiStep <= n_steps &&
+            const bool multi_ok = !batch && g_multi && s + kMultiStep <= n_steps &&
                                   (collect_every <= 0 || (s % collect_every) + kMultiStep <= collect_every);
             if (multi_ok) {
-                CK(cudaGraphLaunch(c->graph_multi, c->compute));
-                c->launches += (int64_t)kMultiStep * c->kps;
+                CK(cudaGraphLaunch(g_multi, c->compute));
+                c->launches += (int64_t)kMultiStep * (c->kps + (pf ? 1 : 0));
                 c->submitted += kMultiStep;
                 s += kMultiStep - 1;
                 if (collect_every <= 0 || (s + 1) % collect_every != 0) continue;
             } else {
             bool hold = false;
             if (batch) { if (++c->hold_pending < c->params.batch_size) hold = true; else c->hold_pending = 0; }
-            CK(cudaGraphLaunch(hold ? c->graph_hold : c->graph, c->compute));
-            c->launches += hold ? 1 : c->kps + (c->lost_mode ? c->kps_global : 0);
+            CK(cudaGraphLaunch(hold ? c->graph_hold : g_one, c->compute));
+            c->launches += hold ? 1 : c->kps + (pf ? 1 : 0) + (c->lost_mode ? c->kps_global : 0);
             c->submitted += 1;
             }
             if (collect_every > 0 && (s + 1) % collect_every == 0) {

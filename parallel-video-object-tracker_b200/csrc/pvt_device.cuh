@@ -36,6 +36,17 @@ struct FrameDesc {
 struct SeqDesc {
     unsigned long long step0;
     int ring_len, row0;
+    int prefetch;              // != 0: the ring's frames are pinned host memory -> k_prefetch_roi stages the next step's pixels
+    int pad;
+};
+
+// What k_prefetch_roi staged for a track: gray f32 pixels of region [x0, x1) x [y0, y1) of the frame `data`, valid for `step`
+struct StageHdr {
+    int x0, y0, x1, y1;
+    unsigned long long step;
+    const void* data;
+    int win[4];                // the track's search window at the START of the current step (stored by k_ingest_roi): what
+    int pad[2];                // k_prefetch_roi grows -- it must not read the box itself, which the step's update moves
 };
 
 struct TrackState {
@@ -79,6 +90,9 @@ struct Ctx {
     float* maps;
     float* partial;            // [parts][max_tracks][tiles][8*kCY] K-split partial cross terms, tile-major
     float* fringe_acc;         // [max_tracks][parts][Hmax + Wmax] partial cross terms of the fringe column (by y) and row (by x), K-split mode
+    float* stage;              // [max_tracks][stage_h][stage_w] next step's search-tile superset, staged by k_prefetch_roi (NULL: off)
+    StageHdr* stage_hdr;       // [max_tracks]
+    int stage_w, stage_h;
     TrackState* tracks;
     FrameDesc* table;
     SeqDesc* seq;

@@ -288,6 +288,32 @@ def test_submit_sequence_fast_paths_equal_step_by_step(memory, collect_every):
     assert list(got[:, 0]["step"]) == list(range(n - 1))
 
 
+@pytest.mark.parametrize("radius", [80, 24])
+def test_pinned_ring_prefetch_and_its_fallback(radius):
+    """Pinned host rings: k_prefetch_roi stages the next step's tile (current tile grown by R/2) while the step computes.
+    radius 80: the object moves 20 px per frame, the staged region always covers the next tile.  radius 24: it moves more
+    than R/2, the coverage check fails and the ingest falls back to the zero-copy read.  Same records either way."""
+    torch = pytest.importorskip("torch")
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi, search_radius_x=radius, search_radius_y=radius)[0]
+    assert want[:, 5].all()                      # the object stays inside the window in both cases
+    n, H, W, _ = frames.shape
+    buf = torch.from_numpy(frames).pin_memory()
+    ring = [[pvt.Frame(0, pvt.FMT_BGR8, pvt.MEM_HOST, 0, buf[k].data_ptr(), W * 3)] for k in range(1, n)]
+    with pvt.Tracker(W, H, 32, 32, ingest=pvt.INGEST_ROI, search_radius_x=radius, search_radius_y=radius) as tr:
+        tr.init_track(0, frames[0], roi)
+        tr.submit_sequence(n - 1, ring)
+        got = tr.collect(n - 1)
+        # a second pass over the same ring from a box that was moved by hand: the staged region of the last step does not
+        # cover it; nothing may be taken from the stale staging buffer
+        tr.set_state(0, (roi[0], roi[1], 32, 32), None)
+        tr.submit_sequence(3, ring)
+        again = tr.collect(3)
+    assert np.array_equal(records_of(got[:, 0]), want)
+    assert np.array_equal(records_of(again[:, 0])[:, :4], want[:3, :4])
+
+
 def test_state_roundtrip_and_errors():
     (c, _) = Hp.clip("small")
     frames, roi = c["frames"], c["roi"]
