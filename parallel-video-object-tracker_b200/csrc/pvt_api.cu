@@ -533,7 +533,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     if (profile) { int r = pnode(c, CLS_STATS, 0, sstats); if (r) return r; }
     const bool pdl = capturing && !profile && p.pdl;   // programmatic edges: ingest ~> search / colprefix, colprefix ~> rowsum, search ~> finalize
-    { int r = launch_pdl(k_colprefix, dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats, pdl && fork, d); if (r) return r; }
+    { int r = launch_pdl(k_colprefix, dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats, pdl, d); if (r) return r; }
     { int r = dbg(c, "k_colprefix"); if (r) return r; }
     { int r = launch_pdl(k_rowsum, dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), dim3(p.rowsum_warps * 32),
                          (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats, pdl, d, p.rowsum_pw); if (r) return r; }
