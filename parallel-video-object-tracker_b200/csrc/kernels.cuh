@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     float* out = c.gray + (size_t)t.stream * c.plane + (size_t)y * c.pitch + x;
     // Did k_prefetch_roi stage this tile during the previous step (pinned host rings)?  Then it is a device-to-device copy
     // of already converted pixels; the zero-copy read over PCIe happened off the critical path.
-    if (c.stage) {
+    // (Only inside a sequence over a pinned ring, whose frames the caller keeps unchanged: SeqDesc.prefetch.)
+    if (c.stage && c.seq->prefetch) {
         const StageHdr h = c.stage_hdr[track];
         if (h.step == step && h.data == d.data && x0 >= h.x0 && x1 <= h.x1 && win[1] >= h.y0 && win[1] + rows <= h.y1) {
             const float* sp = c.stage + (size_t)track * c.stage_w * c.stage_h + (size_t)(y - h.y0) * c.stage_w + (x - h.x0);

@@ -1325,6 +1325,8 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
         CK(cudaEventRecord(c->table_ev[0], c->compute));
         c->table_ev_used[0] = true;
         const bool pf = any_host && c->d.stage && !c->lost_mode;
+        // nothing staged by an earlier sequence may be taken for this one (the caller may have refilled the buffers)
+        if (pf) CK(cudaMemsetAsync(c->d.stage_hdr, 0xFF, sizeof(StageHdr) * (size_t)c->cfg.max_tracks, c->compute));
         int r = upload_seq(c, c->submitted, ring_len, 0, pf ? 1 : 0);
         if (r) return r;
         if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }

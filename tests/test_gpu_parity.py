@@ -314,6 +314,32 @@ def test_pinned_ring_prefetch_and_its_fallback(radius):
     assert np.array_equal(records_of(again[:, 0])[:, :4], want[:3, :4])
 
 
+def test_pinned_buffers_refilled_between_sequences_are_not_served_from_the_stage():
+    """The staging buffer is keyed by (step, frame pointer): a caller that refills its pinned buffers between two calls, or
+    goes on with per-frame submits, must get the NEW pixels."""
+    torch = pytest.importorskip("torch")
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi)[0]
+    n, H, W, _ = frames.shape
+    buf = torch.empty((4, H, W, 3), dtype=torch.uint8).pin_memory()      # a 4-frame pinned ring, refilled by the caller
+    ring = [[pvt.Frame(0, pvt.FMT_BGR8, pvt.MEM_HOST, 0, buf[k].data_ptr(), W * 3)] for k in range(4)]
+    got = []
+    with pvt.Tracker(W, H, 32, 32, ingest=pvt.INGEST_ROI) as tr:
+        tr.init_track(0, frames[0], roi)
+        k = 1
+        while k + 4 <= n:
+            buf.copy_(torch.from_numpy(frames[k:k + 4]))                   # same pointers, new content
+            tr.submit_sequence(4, ring)
+            got.append(tr.collect(4))
+            k += 4
+        for j in range(k, n):                                              # then frame by frame through the same buffer
+            buf[0].copy_(torch.from_numpy(frames[j]))
+            got.append(tr.step([ring[0][0]])[None])
+    got = np.concatenate(got)
+    assert np.array_equal(records_of(got[:, 0]), want)
+
+
 def test_state_roundtrip_and_errors():
     (c, _) = Hp.clip("small")
     frames, roi = c["frames"], c["roi"]
