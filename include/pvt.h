@@ -207,6 +207,12 @@ PVT_API int pvt_ncc_match(int device, int mode, const float* frame, int fw, int 
 PVT_API int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes,
                                   const float* templ, int tw, int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes);
 
+/* The search-kernel plan pvt_create would derive for this geometry on a device with `sm_count` SMs; pure host logic (no
+ * device needed).  out = {G, C, GB, bands, ctas_per_band, span, boxW, boxH, pj, pd, ctas_per_track, n_full, n_tail, tail_parts,
+ * shared bytes per CTA, fringe bits (1: remainder column, 2: remainder row computed by k_ncc_fringe)}. */
+PVT_API int pvt_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y,
+                           int32_t out[16]);
+
 /* measurement hooks */
 PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA events, plain stream launches */
 PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);

@@ -37,7 +37,7 @@ SYMBOLS = [
     "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
-    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state",
+    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query",
 ]
 
 
@@ -147,6 +147,17 @@ def default_params(ghc=False, **kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+PLAN_FIELDS = ("G", "C", "GB", "bands", "ctas_per_band", "span", "boxW", "boxH", "pj", "pd", "ctas_per_track", "n_full", "n_tail",
+               "tail_parts", "smem", "fringe")
+
+
+def plan_query(n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x=80, radius_y=80, sm_count=148) -> dict:
+    """The k_ncc_search plan pvt_create would derive (host logic only: works without a GPU)."""
+    out = (C.c_int32 * 16)()
+    _ck(lib().pvt_plan_query(sm_count, n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x, radius_y, out))
+    return dict(zip(PLAN_FIELDS, out))
 
 
 def device_count() -> int:

@@ -277,6 +277,23 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f)
     return 4 + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
 
+// item grid + tail splitting (see TileCfg)
+void plan_items(TileCfg& g, int max_tracks, int mtp, int sm_count)
+{
+    g.cpt = g.bands * g.ctas_band;
+    const long long items = (long long)max_tracks * g.cpt, slots = (long long)sm_count * 2;
+    g.n_full = (int)items; g.n_tail = 0; g.tail_ps = 0;
+    const char* no_tail = getenv("PVT_NO_TAIL_SPLIT");
+    if (g.pj * g.pd == 1 && items > slots && !(no_tail && *no_tail == '1')) {
+        const long long rem = items % slots;
+        const int nch = mtp / 8;
+        const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
+        if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) {
+            g.n_tail = (int)rem; g.n_full = (int)(items - rem); g.tail_ps = ps;
+        }
+    }
+}
+
 // Plan one pass: p.d holds the geometry (W, H, templates, Wmax, Hmax, VW) and the shared pointers on entry; on return the
 // plan (tile grid, K-split / tail split, fringe, shared-memory sizes, TMA descriptor) and the pass's own scratch.
 int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
@@ -302,21 +319,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
             }
         }
     }
-    {   // item grid + tail splitting (see TileCfg)
-        TileCfg& g = p.tile;
-        g.cpt = g.bands * g.ctas_band;
-        const long long items = (long long)d.max_tracks * g.cpt, slots = (long long)sm_count * 2;
-        g.n_full = (int)items; g.n_tail = 0; g.tail_ps = 0;
-        const char* no_tail = getenv("PVT_NO_TAIL_SPLIT");
-        if (g.pj * g.pd == 1 && items > slots && !(no_tail && *no_tail == '1')) {
-            const long long rem = items % slots;
-            const int nch = d.mtp / 8;
-            const int ps = rem > 0 ? (int)std::min<long long>(nch, slots / rem) : 0;
-            if (rem > 0 && rem * 5 <= slots * 4 && ps >= 2) {
-                g.n_tail = (int)rem; g.n_full = (int)(items - rem); g.tail_ps = ps;
-            }
-        }
-    }
+    plan_items(p.tile, d.max_tracks, d.mtp, sm_count);
     {
         const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
         p.roi_ingest = !d.global_pass && (ingest == PVT_INGEST_ROI || (ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px));
@@ -889,6 +892,23 @@ int resolve_profile(pvt_ctx* c)
 extern "C" {
 
 int pvt_version(void) { return PVT_VERSION; }
+
+// The k_ncc_search plan pvt_create would derive, without touching a device (host logic only; used by the CPU tests).
+int pvt_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y, int32_t out[16])
+{
+    if (!out || sm_count <= 0 || n_tracks <= 0 || templ_w <= 0 || templ_h <= 0 || templ_w > frame_w || templ_h > frame_h || radius_x < 0 || radius_y < 0)
+        return fail(PVT_ERR_INVALID, "bad plan query");
+    const int mtp = (templ_w + 7) & ~7;
+    const int Wmax = std::min(2 * radius_x + 1, frame_w), Hmax = std::min(2 * radius_y + 1, frame_h);
+    TileCfg g{};
+    size_t smem = 0;
+    if (!choose_plan(sm_count, n_tracks, templ_w, mtp, templ_h, Wmax, Hmax, &g, &smem)) return fail(PVT_ERR_UNSUPPORTED, "no k_ncc_search plan fits this template / window size");
+    plan_items(g, n_tracks, mtp, sm_count);
+    const int32_t v[16] = {g.G, g.C, g.GB, g.bands, g.ctas_band, g.span, g.boxW, g.boxH, g.pj, g.pd, g.cpt, g.n_full, g.n_tail, g.tail_ps,
+                           (int32_t)smem, (int32_t)((Wmax > 8 * g.C ? 1 : 0) | (Hmax > kCY * g.G ? 2 : 0))};
+    std::memcpy(out, v, sizeof(v));
+    return PVT_OK;
+}
 const char* pvt_last_error(void) { return g_err.c_str(); }
 
 int pvt_device_count(void)
