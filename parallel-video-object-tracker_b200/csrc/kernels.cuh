@@ -1059,7 +1059,9 @@ __global__ void __launch_bounds__(kTilesPerCta) k_ncc_tail_finalize(Ctx c, TileC
 // K-split second stage: add the parts' partial sums in part order, normalise, pick the peak.
 // NOTE the summation order differs from the unsplit kernel (parts regroup template rows), so scores may differ
 // from it in the last bits; within one configuration every candidate is summed identically (exact ties stay exact).
-__global__ void __launch_bounds__(256) k_ncc_finalize(Ctx c, TileCfg g)
+constexpr int kFinalizeThreads = 512;   // upper bound; also the width of the fused update: launched 512 wide for templates above
+                                        // 8192 pixels (a 128 x 128 template: two EMA batches instead of four, C3 -5 %), else 256
+__global__ void __launch_bounds__(kFinalizeThreads) k_ncc_finalize(Ctx c, TileCfg g)
 {
     extern __shared__ float sm_f[];
     __shared__ double red[64];

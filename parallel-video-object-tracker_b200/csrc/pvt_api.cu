@@ -592,8 +592,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
         if (parts > 1) {
+            const int fthr = d.mth * d.mtw > 8192 ? kFinalizeThreads : 256;
             if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
-            { int r = launch_pdl(k_ncc_finalize, dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), dim3(256), c->templ_smem, c->compute, pdl && fork, d, p.tile); if (r) return r; }
+            { int r = launch_pdl(k_ncc_finalize, dim3((d.Wmax * d.Hmax + fthr - 1) / fthr, d.max_tracks), dim3(fthr), c->templ_smem, c->compute, pdl && fork, d, p.tile); if (r) return r; }
             if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         }
     }
