@@ -41,7 +41,7 @@ extern "C" {
 #define PVT_API
 #endif
 
-#define PVT_VERSION 101
+#define PVT_VERSION 102
 
 /* return codes */
 #define PVT_OK               0
@@ -74,6 +74,16 @@ typedef enum pvt_kernel {
  * identical.  AUTO picks ROI when the tiles of a context cover less than half of its frames' area. */
 typedef enum pvt_ingest { PVT_INGEST_AUTO = 0, PVT_INGEST_FULL = 1, PVT_INGEST_ROI = 2 } pvt_ingest;
 
+/* Score formula.  CCOEFF_NORMED is what the reference's CPU path computes (cv::matchTemplate, ncc_cpu.cpp:12) and what
+ * the parity gates are stated against.  EPS is the formula of the reference's five CUDA kernels
+ * (baseline_kernel.cu:44-49,62 with the host-side template statistics of :329-332):
+ *     ncc = cov / ((sqrt(max(var_w, 1e-6)) + 1e-6) * (sigma_t + 1e-6 + 1e-6) * N)
+ * for callers that depend on the reference's GPU-mode numbers: no clamp rules, a flat template scores 0 (not 1), a flat
+ * window scores ~0 through the 1e-3 floor.  Window sums come from the same FP64 integrals and the cross term from the same
+ * FP32 kernel as the default formula, so the values agree with exact arithmetic to ~1e-6; the reference's own kernels
+ * accumulate everything sequentially in FP32 and sit ~4e-5 away on textured windows.  Must be chosen at pvt_create. */
+typedef enum pvt_formula { PVT_FORMULA_CCOEFF_NORMED = 0, PVT_FORMULA_EPS = 1 } pvt_formula;
+
 typedef enum pvt_format { PVT_FMT_BGR8 = 0, PVT_FMT_GRAY8 = 1, PVT_FMT_GRAYF32 = 2 } pvt_format;
 typedef enum pvt_memory { PVT_MEM_HOST = 0, PVT_MEM_DEVICE = 1 } pvt_memory;
 
@@ -95,7 +105,8 @@ typedef struct pvt_params {
      * at ncc_global_confidence; once found it returns to the local window.  Must be chosen at pvt_create (it sizes
      * the whole-frame scratch: ~53 MB per track at 1080p); the value may be changed later while it stays > 0. */
     int lost_frame_threshold;     /* LOST_FRAME_THRESHOLD = 50 in tracker_ghc */
-    int reserved[2];
+    int formula;                  /* pvt_formula */
+    int reserved;
     double ncc_global_confidence; /* NCC_GLOBAL_CONFIDENCE = 0.60 in tracker_ghc */
 } pvt_params;
 
@@ -116,7 +127,9 @@ typedef struct pvt_config {
 typedef struct pvt_frame {
     int stream;       /* 0 .. max_streams-1 */
     int format;       /* pvt_format; BGR8 is what cv::VideoCapture hands the reference (main.cpp:95) */
-    int memory;       /* pvt_memory; host buffers are copied with cudaMemcpyAsync (pin them for overlap) */
+    int memory;       /* pvt_memory.  Host buffers: pageable ones are staged with cudaMemcpyAsync; pinned ones (pvt_alloc_pinned,
+                       * cudaHostAlloc, cudaHostRegister) are read in place by the ROI ingest, tiles only.  Either way the
+                       * buffer must stay unchanged until the step has run (pvt_step returns / pvt_sync / pvt_collect). */
     int reserved;
     const void* data; /* first row */
     size_t step;      /* bytes per row (cv::Mat::step) */
@@ -199,13 +212,18 @@ PVT_API int pvt_to_gray_f32(pvt_ctx* ctx, const pvt_frame* frame, float* out, si
 
 /* baseline_kernel.hpp:8-17 map-level operators: full (fh-th+1) x (fw-tw+1) map, host buffers in, host
  * buffer out, synchronous -- the contract of ncc_match_naive_cuda / _shared_cuda / _const / _const_tiled
- * (mode picks nothing but is validated; PVT_MODE_CPU -> PVT_ERR_UNSUPPORTED).  Unlike the reference's
- * GPU modes there is no 4096-pixel template limit (baseline_kernel.cu:500) and no 48 KB limit. */
+ * (the low byte of mode picks nothing but is validated; PVT_MODE_CPU -> PVT_ERR_UNSUPPORTED).  Values are those of the
+ * reference's CPU operator ncc_match_cpu unless mode carries PVT_MODE_FLAG_EPS, which selects PVT_FORMULA_EPS, the
+ * formula of those four GPU operators.  Unlike them there is no 4096-pixel template limit (baseline_kernel.cu:500)
+ * and no 48 KB limit.  pvt_ncc_match_batched takes the same flag in `formula` through pvt_ncc_match_batched_f. */
+#define PVT_MODE_FLAG_EPS 0x100
 PVT_API int pvt_ncc_match(int device, int mode, const float* frame, int fw, int fh, size_t fstep_bytes,
                           const float* templ, int tw, int th, size_t tstep_bytes, float* out, size_t ostep_bytes);
 /* baseline_kernel.hpp:14 ncc_match_naive_cuda_batched: n frames of one geometry against one template */
 PVT_API int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes,
                                   const float* templ, int tw, int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes);
+PVT_API int pvt_ncc_match_batched_f(int device, int formula, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes,
+                                    const float* templ, int tw, int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes);
 
 /* The search-kernel plan pvt_create would derive for this geometry on a device with `sm_count` SMs; pure host logic (no
  * device needed).  out = {G, C, GB, bands, ctas_per_band, span, boxW, boxH, pj, pd, ctas_per_track, n_full, n_tail, tail_parts,

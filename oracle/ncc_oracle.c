@@ -11,6 +11,8 @@
  *     window clamp / peak / gate / EMA  /root/reference/tracker/src/main.cpp:135-161
  *     batch hold semantics              /root/reference/tracker/src/main.cpp:115-130
  *     lost-object re-acquisition        /root/reference/tracker_ghc/src/main.cpp:17-23,143-144,183-239 (orc_track_clip_ghc)
+ *     the CUDA kernels' eps formula     /root/reference/tracker/src/baseline_kernel.cu:21-64,329-332 (orc_ncc_window_eps;
+ *                                       PARITY UNPINNED: those kernels cannot be run in the build container, see there)
  * and every arithmetic call on it lands in a THIRD-PARTY dependency that is not vendored under
  * /root/reference: OpenCV (imgproc/core), pinned at 4.13.0 by tracker/Makefile:19-27
  * (opencv_core4130.lib ...).  The functions below restate OpenCV 4.13.0's published algorithms
@@ -260,6 +262,62 @@ ORC_API int orc_ncc_match_cpu(const float* frame, int fw, int fh, size_t fstep_b
                           0, 0, fw - tw + 1, fh - th + 1, out, ostep_bytes);
 }
 
+/* ---- baseline_kernel.cu:21-64 nccKernelNaive (+ host statistics :329-332): the formula all five CUDA kernels of the
+ * reference share, restricted to a candidate rectangle like orc_ncc_window.  FP32 throughout, two
+ * sequential passes per candidate in the kernel's loop order (dy outer, dx inner):
+ *     pass 1  sum += v; sumSq += v*v                       mean = sum/N; var = sumSq/N - mean*mean; std = sqrtf(fmaxf(var, 1e-6f))
+ *     pass 2  cov += (v - mean) * (t - templMean)          ncc = cov * (1/(std + 1e-6f)) * (1/(templStd + 1e-6f)) / N
+ * with templMean = (float)mean_t, templStd = (float)(sigma_t + 1e-6f) from cv::meanStdDev (double, population).
+ * nvcc contracts a*b+c into one FMA by default (-fmad=true), so the two accumulations are written with fmaf here.
+ * PARITY UNPINNED: the reference ships no vectors for its GPU modes and its kernels cannot run in the build container
+ * (no GPU), so this restatement is checked only against exact (float64) evaluation of the same formula
+ * (tests/test_oracle_golden.py), from which sequential FP32 summation drifts by ~4e-5 on textured 64x64 windows. */
+ORC_API int orc_ncc_window_eps(const float* frame, int fw, int fh, size_t fstep_bytes,
+                               const float* templ, int tw, int th, size_t tstep_bytes,
+                               int x0, int y0, int ww, int wh, float* out, size_t ostep_bytes)
+{
+    if (tw <= 0 || th <= 0 || fw < tw || fh < th) return -1;
+    int outW = fw - tw + 1, outH = fh - th + 1;
+    if (x0 < 0 || y0 < 0 || ww <= 0 || wh <= 0 || x0 + ww > outW || y0 + wh > outH) return -2;
+    double mean_t, sdv_t;
+    orc_mean_stddev(templ, tw, th, tstep_bytes, &mean_t, &sdv_t);
+    const float templMean = (float)mean_t;
+    const float templStd = (float)(sdv_t + 1e-6f);
+    const int N = tw * th;
+    for (int oy = 0; oy < wh; ++oy) {
+        float* o = (float*)((char*)out + (size_t)oy * ostep_bytes);
+        for (int ox = 0; ox < ww; ++ox) {
+            float sum = 0.0f, sumSq = 0.0f;
+            for (int dy = 0; dy < th; ++dy) {
+                const float* fr = (const float*)((const char*)frame + (size_t)(y0 + oy + dy) * fstep_bytes) + x0 + ox;
+                for (int dx = 0; dx < tw; ++dx) {
+                    const float v = fr[dx];
+                    sum += v;
+                    sumSq = fmaf(v, v, sumSq);
+                }
+            }
+            const float mean = sum / N;
+            const float var = fmaf(-mean, mean, sumSq / N);
+            const float sd = sqrtf(fmaxf(var, 1e-6f));
+            const float inv_std = 1.0f / (sd + 1e-6f);
+            const float inv_t_std = 1.0f / (templStd + 1e-6f);
+            float cov = 0.0f;
+            for (int dy = 0; dy < th; ++dy) {
+                const float* fr = (const float*)((const char*)frame + (size_t)(y0 + oy + dy) * fstep_bytes) + x0 + ox;
+                const float* tr = (const float*)((const char*)templ + (size_t)dy * tstep_bytes);
+                for (int dx = 0; dx < tw; ++dx) cov = fmaf(fr[dx] - mean, tr[dx] - templMean, cov);
+            }
+            o[ox] = cov * inv_std * inv_t_std / (float)N;
+        }
+    }
+    return 0;
+}
+
+/* which map the tracker loops below search: 0 = orc_ncc_window (the --cpu path, the parity target), 1 = orc_ncc_window_eps
+ * (what main.cpp:103-133 gets from any of the GPU modes).  Test-only global, not thread-safe. */
+static int g_formula = 0;
+ORC_API void orc_set_formula(int f) { g_formula = f; }
+
 /* ---- main.cpp:135-146 search window (C int arithmetic) ------------------------------------ */
 ORC_API void orc_search_window(int x, int y, int w, int h, int outW, int outH, int rx, int ry, int* win /*x0,y0,ww,wh*/)
 {
@@ -314,7 +372,7 @@ ORC_API int orc_track_step(const float* gray, int fw, int fh, float* templ, int 
     orc_search_window(*bx, *by, tw, th, outW, outH, rx, ry, win);
     if (win[2] <= 0 || win[3] <= 0) return -2;
     float* map = map_out ? map_out : (float*)malloc(sizeof(float) * (size_t)win[2] * win[3]);
-    int rc = orc_ncc_window(gray, fw, fh, sizeof(float) * (size_t)fw, templ, tw, th, sizeof(float) * (size_t)tw,
+    int rc = (g_formula ? orc_ncc_window_eps : orc_ncc_window)(gray, fw, fh, sizeof(float) * (size_t)fw, templ, tw, th, sizeof(float) * (size_t)tw,
                             win[0], win[1], win[2], win[3], map, sizeof(float) * (size_t)win[2]);
     if (rc) { if (!map_out) free(map); return rc; }
     double best; int lx, ly;

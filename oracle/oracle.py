@@ -92,6 +92,48 @@ def ncc_window(frame: np.ndarray, templ: np.ndarray, x0, y0, ww, wh) -> np.ndarr
     return out
 
 
+def ncc_window_eps(frame: np.ndarray, templ: np.ndarray, x0, y0, ww, wh) -> np.ndarray:
+    """The formula of the reference's CUDA kernels (baseline_kernel.cu:21-64), FP32 sequential like the kernel."""
+    frame = np.ascontiguousarray(frame, np.float32)
+    templ = np.ascontiguousarray(templ, np.float32)
+    out = np.empty((wh, ww), np.float32)
+    rc = lib().orc_ncc_window_eps(_p(frame), C.c_int(frame.shape[1]), C.c_int(frame.shape[0]), C.c_size_t(frame.shape[1] * 4),
+                                  _p(templ), C.c_int(templ.shape[1]), C.c_int(templ.shape[0]), C.c_size_t(templ.shape[1] * 4),
+                                  C.c_int(x0), C.c_int(y0), C.c_int(ww), C.c_int(wh), _p(out), C.c_size_t(ww * 4))
+    if rc:
+        raise ValueError(f"orc_ncc_window_eps rc={rc}")
+    return out
+
+
+def ncc_eps_exact(frame: np.ndarray, templ: np.ndarray, x0, y0, ww, wh) -> np.ndarray:
+    """The same formula evaluated in float64 (numpy): what the FP32 kernel approximates."""
+    f = np.asarray(frame, np.float64)
+    t = np.asarray(templ, np.float64)
+    th, tw = t.shape
+    n = tw * th
+    tm = float(np.float32(t.mean()))
+    ts = float(np.float32(np.float32(t.std() + float(np.float32(1e-6))) + np.float32(1e-6)))
+    win = np.lib.stride_tricks.sliding_window_view(f[y0:y0 + wh + th - 1, x0:x0 + ww + tw - 1], (th, tw))
+    mean = win.mean(axis=(2, 3))
+    var = (win * win).mean(axis=(2, 3)) - mean * mean
+    sd = np.sqrt(np.maximum(var, float(np.float32(1e-6))))
+    cov = np.einsum("yxij,ij->yx", win, t - tm) - mean * (t - tm).sum()
+    return cov / ((sd + float(np.float32(1e-6))) * ts * n)
+
+
+class formula:
+    """with oracle.formula(1): ...  -- the tracker loops search the eps map (what the reference's GPU modes hand main.cpp)."""
+
+    def __init__(self, f):
+        self.f = int(f)
+
+    def __enter__(self):
+        lib().orc_set_formula(C.c_int(self.f))
+
+    def __exit__(self, *a):
+        lib().orc_set_formula(C.c_int(0))
+
+
 def ncc_match_cpu(frame: np.ndarray, templ: np.ndarray) -> np.ndarray:
     fh, fw = frame.shape
     th, tw = templ.shape

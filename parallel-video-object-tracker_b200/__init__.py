@@ -29,6 +29,8 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TILED = range(3)
 FMT_BGR8, FMT_GRAY8, FMT_GRAYF32 = range(3)
 MEM_HOST, MEM_DEVICE = range(2)
 INGEST_AUTO, INGEST_FULL, INGEST_ROI = range(3)
+FORMULA_CCOEFF_NORMED, FORMULA_EPS = range(2)   # pvt_formula: the reference's CPU operator / its CUDA kernels' eps formula
+MODE_FLAG_EPS = 0x100
 
 # every symbol include/pvt.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
@@ -37,7 +39,7 @@ SYMBOLS = [
     "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
-    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query",
+    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query", "pvt_ncc_match_batched_f",
 ]
 
 
@@ -46,7 +48,7 @@ class Params(C.Structure):
                 ("ncc_min_confidence", C.c_double), ("ncc_strong_confidence", C.c_double),
                 ("template_update_lr", C.c_double), ("batch_size", C.c_int), ("mode", C.c_int),
                 ("kernel", C.c_int), ("keep_maps", C.c_int), ("ingest", C.c_int), ("lost_frame_threshold", C.c_int),
-                ("reserved", C.c_int * 2), ("ncc_global_confidence", C.c_double)]
+                ("formula", C.c_int), ("reserved", C.c_int), ("ncc_global_confidence", C.c_double)]
 
 
 class Config(C.Structure):
@@ -122,6 +124,8 @@ def lib():
                                 C.c_size_t, C.c_void_p, C.c_size_t]
     L.pvt_ncc_match_batched.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t, C.c_void_p,
                                         C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t]
+    L.pvt_ncc_match_batched_f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t]
     L.pvt_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.pvt_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_int]
     L.pvt_trace_enable.argtypes = [C.c_void_p, C.c_int]
@@ -372,7 +376,8 @@ class Tracker:
 
 
 # ---- map-level operators, reference names (tracker/include/baseline_kernel.hpp:8-17) ----------------
-def _ncc_match(mode, frame_gray_f32, templ_gray_f32, device=0):
+def _ncc_match(mode, frame_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
+    mode |= MODE_FLAG_EPS if formula == FORMULA_EPS else 0
     f = np.asarray(frame_gray_f32)
     t = np.asarray(templ_gray_f32)
     if f.dtype != np.float32 or t.dtype != np.float32 or f.ndim != 2 or t.ndim != 2:
@@ -389,20 +394,20 @@ def _ncc_match(mode, frame_gray_f32, templ_gray_f32, device=0):
     return out
 
 
-def ncc_match_naive_cuda(frame_gray_f32, templ_gray_f32, device=0):
-    return _ncc_match(MODE_NAIVE, frame_gray_f32, templ_gray_f32, device)
+def ncc_match_naive_cuda(frame_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
+    return _ncc_match(MODE_NAIVE, frame_gray_f32, templ_gray_f32, device, formula)
 
 
-def ncc_match_shared_cuda(frame_gray_f32, templ_gray_f32, device=0):
-    return _ncc_match(MODE_SHARED, frame_gray_f32, templ_gray_f32, device)
+def ncc_match_shared_cuda(frame_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
+    return _ncc_match(MODE_SHARED, frame_gray_f32, templ_gray_f32, device, formula)
 
 
-def ncc_match_const(frame_gray_f32, templ_gray_f32, device=0):
-    return _ncc_match(MODE_CONST, frame_gray_f32, templ_gray_f32, device)
+def ncc_match_const(frame_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
+    return _ncc_match(MODE_CONST, frame_gray_f32, templ_gray_f32, device, formula)
 
 
-def ncc_match_const_tiled(frame_gray_f32, templ_gray_f32, device=0):
-    return _ncc_match(MODE_CONST_TILED, frame_gray_f32, templ_gray_f32, device)
+def ncc_match_const_tiled(frame_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
+    return _ncc_match(MODE_CONST_TILED, frame_gray_f32, templ_gray_f32, device, formula)
 
 
 def ncc_match_cpu(frame_gray_f32, templ_gray_f32, device=0):
@@ -410,7 +415,7 @@ def ncc_match_cpu(frame_gray_f32, templ_gray_f32, device=0):
     return _ncc_match(MODE_CPU, frame_gray_f32, templ_gray_f32, device)
 
 
-def ncc_match_naive_cuda_batched(frames_gray_f32, templ_gray_f32, device=0):
+def ncc_match_naive_cuda_batched(frames_gray_f32, templ_gray_f32, device=0, formula=FORMULA_CCOEFF_NORMED):
     frames = [np.ascontiguousarray(f, np.float32) for f in frames_gray_f32]
     if not frames:
         raise ValueError("empty batch (baseline_kernel.cu:412)")
@@ -421,8 +426,8 @@ def ncc_match_naive_cuda_batched(frames_gray_f32, templ_gray_f32, device=0):
     outs = [np.empty((fh - t.shape[0] + 1, fw - t.shape[1] + 1), np.float32) for _ in frames]
     fp = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
     op = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
-    _ck(lib().pvt_ncc_match_batched(device, len(frames), fp, fw, fh, fw * 4, t.ctypes.data, t.shape[1], t.shape[0], t.strides[0],
-                                    op, outs[0].strides[0]))
+    _ck(lib().pvt_ncc_match_batched_f(device, formula, len(frames), fp, fw, fh, fw * 4, t.ctypes.data, t.shape[1], t.shape[0], t.strides[0],
+                                      op, outs[0].strides[0]))
     return outs
 
 

@@ -411,7 +411,13 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
         if (diff2 < 0.0) diff2 = 0.0;
         double lim = __dmul_rn(10.0 * (double)FLT_EPSILON, wsq);
         if (lim > 0.5) lim = 0.5;
-        dn[x] = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
+        double dnv = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
+        if (c.formula) {
+            // baseline_kernel.cu:44-48: std = sqrtf(fmaxf(var, 1e-6f)); the score divides by (std + 1e-6f) * (templStd + 1e-6f) * N
+            const float sd = sqrtf(fmaxf((float)(diff2 * invArea), 1e-6f));
+            dnv = (double)(sd + 1e-6f) * tn;
+        }
+        dn[x] = dnv;
     }
     if (lane == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
 // OpenCV's final rule for TM_CCOEFF_NORMED (common_matchTemplate): never NaN, always in [-1, 1]
 __device__ __forceinline__ float ncc_finalize(float num_f32, double t, int flat_templ)
 {
-    if (flat_templ) return 1.0f;
+    if (flat_templ) return flat_templ == 1 ? 1.0f : (float)((double)num_f32 / t);   // 2: PVT_FORMULA_EPS, t > 0 always
     double num = (double)num_f32;
     double r;
     if (fabs(num) < t) r = num / t;
@@ -1221,6 +1227,11 @@ __device__ void finish_template(const Ctx& c, int track, TrackState& t, const fl
         t.mean = mean;
         t.flat = norm2 < DBL_EPSILON;
         t.templ_norm = sqrt(norm2) / sqrt(scale);
+        if (c.formula) {
+            // baseline_kernel.cu:331-332 templStd = (float)(stddev + 1e-6f); :49 1 / (templStd + 1e-6f); :62 ... / N
+            t.flat = 2;
+            t.templ_norm = (double)((float)(sdv + (double)1e-6f) + 1e-6f) * (double)n;
+        }
         t.tp = tpad;
     }
     // centred template, CHUNK-MAJOR: tc[(x / 8) * th * 8 + y * 8 + (x % 8)], columns >= tw are zero.

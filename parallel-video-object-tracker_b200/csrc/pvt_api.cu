@@ -429,6 +429,7 @@ int validate_params(const pvt_params* p)
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
     if (!(p->template_update_lr >= 0.0 && p->template_update_lr <= 1.0)) return fail(PVT_ERR_INVALID, "template_update_lr outside [0,1]");
     if (p->lost_frame_threshold < 0) return fail(PVT_ERR_INVALID, "negative lost_frame_threshold");
+    if (p->formula != PVT_FORMULA_CCOEFF_NORMED && p->formula != PVT_FORMULA_EPS) return fail(PVT_ERR_INVALID, "unknown formula");
     return PVT_OK;
 }
 
@@ -1048,6 +1049,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     c->lost_mode = params->lost_frame_threshold > 0;
     Ctx& d = c->d;
     d.lost_mode = c->lost_mode ? 1 : 0;
+    d.formula = params->formula;
     d.global_pass = 0;
     d.W = cfg->frame_w;
     d.H = cfg->frame_h;
@@ -1172,6 +1174,7 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
         return fail(PVT_ERR_INVALID, "search radius exceeds the maxima the context was created with");
     if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
     if ((p->lost_frame_threshold > 0) != c->lost_mode) return fail(PVT_ERR_INVALID, "lost-object mode (lost_frame_threshold > 0) must be chosen at pvt_create");
+    if (p->formula != c->params.formula) return fail(PVT_ERR_INVALID, "the score formula must be chosen at pvt_create (templates carry its statistics)");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->compute));
     const bool regraph = p->kernel != c->params.kernel || p->ingest != c->params.ingest;
@@ -1555,11 +1558,11 @@ int pvt_to_gray_f32(pvt_ctx* c, const pvt_frame* frame, float* out, size_t out_s
 // ---- map-level operators (baseline_kernel.hpp:8-17) ---------------------------------------------
 namespace {
 std::mutex g_map_mu;
-std::map<std::tuple<int, int, int, int, int>, pvt_ctx*> g_map_ctx;
+std::map<std::tuple<int, int, int, int, int, int>, pvt_ctx*> g_map_ctx;
 
-int map_ctx(int device, int fw, int fh, int tw, int th, pvt_ctx** out)
+int map_ctx(int device, int formula, int fw, int fh, int tw, int th, pvt_ctx** out)
 {
-    auto key = std::make_tuple(device, fw, fh, tw, th);
+    auto key = std::make_tuple(device, formula, fw, fh, tw, th);
     auto it = g_map_ctx.find(key);
     if (it != g_map_ctx.end()) { *out = it->second; return PVT_OK; }
     pvt_params p;
@@ -1567,6 +1570,7 @@ int map_ctx(int device, int fw, int fh, int tw, int th, pvt_ctx** out)
     p.search_radius_x = fw;  // window == the whole map
     p.search_radius_y = fh;
     p.keep_maps = 1;
+    p.formula = formula;
     pvt_config cfg{};
     cfg.device = device; cfg.frame_w = fw; cfg.frame_h = fh; cfg.max_streams = 1; cfg.max_tracks = 1;
     cfg.max_templ_w = tw; cfg.max_templ_h = th;
@@ -1581,16 +1585,17 @@ int map_ctx(int device, int fw, int fh, int tw, int th, pvt_ctx** out)
 }
 }  // namespace
 
-int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes, const float* templ, int tw,
-                          int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes)
+int pvt_ncc_match_batched_f(int device, int formula, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes, const float* templ,
+                            int tw, int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes)
 {
+    if (formula != PVT_FORMULA_CCOEFF_NORMED && formula != PVT_FORMULA_EPS) return fail(PVT_ERR_INVALID, "unknown formula");
     if (n <= 0 || !frames || !templ || !outs) return fail(PVT_ERR_INVALID, "empty batch / NULL argument (baseline_kernel.cu:412)");
     if (tw <= 0 || th <= 0 || fw < tw || fh < th) return fail(PVT_ERR_INVALID, "frame smaller than template (ncc_cpu.cpp:9-10)");
     const int outW = fw - tw + 1, outH = fh - th + 1;
     if (fstep_bytes < (size_t)fw * 4 || tstep_bytes < (size_t)tw * 4 || ostep_bytes < (size_t)outW * 4) return fail(PVT_ERR_INVALID, "step too small");
     std::lock_guard<std::mutex> lk(g_map_mu);
     pvt_ctx* c = nullptr;
-    int r = map_ctx(device, fw, fh, tw, th, &c);
+    int r = map_ctx(device, formula, fw, fh, tw, th, &c);
     if (r) return r;
     for (int i = 0; i < n; ++i) {
         if (!frames[i] || !outs[i]) return fail(PVT_ERR_INVALID, "NULL frame / output in batch");
@@ -1610,12 +1615,20 @@ int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw,
     return PVT_OK;
 }
 
+int pvt_ncc_match_batched(int device, int n, const float* const* frames, int fw, int fh, size_t fstep_bytes, const float* templ, int tw,
+                          int th, size_t tstep_bytes, float* const* outs, size_t ostep_bytes)
+{
+    return pvt_ncc_match_batched_f(device, PVT_FORMULA_CCOEFF_NORMED, n, frames, fw, fh, fstep_bytes, templ, tw, th, tstep_bytes, outs, ostep_bytes);
+}
+
 int pvt_ncc_match(int device, int mode, const float* frame, int fw, int fh, size_t fstep_bytes, const float* templ, int tw, int th,
                   size_t tstep_bytes, float* out, size_t ostep_bytes)
 {
+    const int formula = (mode & PVT_MODE_FLAG_EPS) ? PVT_FORMULA_EPS : PVT_FORMULA_CCOEFF_NORMED;
+    mode &= ~PVT_MODE_FLAG_EPS;
     if (mode == PVT_MODE_CPU) return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path");
     if (mode < PVT_MODE_NAIVE || mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
-    return pvt_ncc_match_batched(device, 1, &frame, fw, fh, fstep_bytes, templ, tw, th, tstep_bytes, &out, ostep_bytes);
+    return pvt_ncc_match_batched_f(device, formula, 1, &frame, fw, fh, fstep_bytes, templ, tw, th, tstep_bytes, &out, ostep_bytes);
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------------

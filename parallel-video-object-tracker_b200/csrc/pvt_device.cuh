@@ -53,8 +53,8 @@ struct TrackState {
     int active, stream;
     int x, y, w, h;            // bbox; (w, h) is also the template size (main.cpp never changes it)
     int tp;                    // centred-template row pitch in floats (w rounded up to 8)
-    int flat;                  // sigma_t^2 < DBL_EPSILON -> whole map is 1 (OpenCV common_matchTemplate)
-    double mean, templ_norm;   // mean_t, sigma_t * sqrt(N)
+    int flat;                  // 1: sigma_t^2 < DBL_EPSILON -> whole map is 1 (OpenCV common_matchTemplate); 2: Ctx.formula == EPS (plain quotient)
+    double mean, templ_norm;   // mean_t, sigma_t * sqrt(N)   (EPS formula: (fl32(sigma_t + 1e-6) + 1e-6) * N)
     unsigned long long peak;   // packed (ordered score << 32 | ~index); 0 = empty
     int win[4];                // minTx, minTy, width, height of the current search window
     unsigned int ticket;       // CTAs of k_ncc_finalize that are done with this track (last one runs the update)
@@ -74,6 +74,7 @@ struct DevParams {
 // geometry + pointers every kernel needs; passed by value (fits in the parameter bank)
 struct Ctx {
     int lost_mode;             // != 0: tracker_ghc semantics; a time step = local pass (global_pass 0) + global pass (1)
+    int formula;               // pvt_formula, fixed at creation
     int global_pass;           // which pass this launch belongs to: a track is handled by exactly one pass per step
     int* stream_need;          // global pass: streams with at least one whole-frame track this step (whole-frame ingest)
     int W, H, pitch;           // frame geometry, gray-plane pitch in floats

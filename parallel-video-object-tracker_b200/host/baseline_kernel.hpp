@@ -13,6 +13,10 @@
 // without OpenCV (this image has no OpenCV C++ headers) they take pvt::Mat, a minimal row-major matrix view with
 // cv::Mat's fields (rows, cols, step, data).  ncc_match_cpu is declared for source compatibility and throws: the
 // library has no CPU path (the CPU implementation lives in oracle/, test-only).
+//
+// Values: by default every operator returns the map of the reference's CPU operator (cv::matchTemplate TM_CCOEFF_NORMED,
+// the parity target).  With -DPVT_BASELINE_GPU_FORMULA the GPU-named operators return the eps formula of the reference's own
+// CUDA kernels instead (baseline_kernel.cu:44-49,62; pvt_formula in pvt.h) for callers that depend on those numbers.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -94,8 +98,15 @@ inline int& default_device()
     return d;
 }
 
+#ifdef PVT_BASELINE_GPU_FORMULA
+constexpr int kFormula = PVT_FORMULA_EPS;
+#else
+constexpr int kFormula = PVT_FORMULA_CCOEFF_NORMED;
+#endif
+
 inline void ncc_match_mode(int mode, const MatArg& frame, const MatArg& templ, MatArg& ncc_map)
 {
+    if (kFormula == PVT_FORMULA_EPS) mode |= PVT_MODE_FLAG_EPS;
     if (!is_f32c1(frame) || !is_f32c1(templ)) throw Error(PVT_ERR_INVALID, "CV_32FC1 inputs required (ncc_cpu.cpp:7-8)");
     if (frame.cols < templ.cols || frame.rows < templ.rows) throw Error(PVT_ERR_INVALID, "frame smaller than template (ncc_cpu.cpp:9-10)");
     create_f32(ncc_map, frame.rows - templ.rows + 1, frame.cols - templ.cols + 1);
@@ -139,7 +150,7 @@ inline void ncc_match_naive_cuda_batched(const std::vector<Mat>& frames_gray_f32
         in.push_back(pvt::fptr(f));
         out.push_back(pvt::fptr(ncc_maps[i]));
     }
-    pvt::check(pvt_ncc_match_batched(pvt::default_device(), (int)in.size(), in.data(), fw, fh, fstep, pvt::fptr(templ_gray_f32), templ_gray_f32.cols,
+    pvt::check(pvt_ncc_match_batched_f(pvt::default_device(), pvt::kFormula, (int)in.size(), in.data(), fw, fh, fstep, pvt::fptr(templ_gray_f32), templ_gray_f32.cols,
                                      templ_gray_f32.rows, pvt::step_of(templ_gray_f32), out.data(), pvt::step_of(ncc_maps[0])));
 }
 

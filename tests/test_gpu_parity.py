@@ -477,3 +477,55 @@ def test_window_origin_clamp_and_fringe_sweep(R, tw, th):
         seen_fringe += win[2] == 2 * R + 1 and win[3] == 2 * R + 1
         seen_clamped += win[2] < 2 * R + 1 or win[3] < 2 * R + 1
     assert seen_fringe >= 4 and seen_clamped >= 20
+
+
+# ---- §8(f) n4: the eps formula of the reference's CUDA kernels (pvt_formula) ----------------------------------------
+def _textured(rng, H, W):
+    from scipy.ndimage import gaussian_filter
+    f = gaussian_filter(rng.random((H, W)), 2.0)
+    return ((f - f.min()) / (f.max() - f.min())).astype(np.float32)
+
+
+@pytest.mark.parametrize("fn", ["ncc_match_naive_cuda", "ncc_match_shared_cuda", "ncc_match_const", "ncc_match_const_tiled"])
+def test_eps_formula_map_operators(fn):
+    rng = np.random.default_rng(11)
+    f = _textured(rng, 150, 210)
+    t = f[40:72, 90:130].copy() + rng.normal(0, 0.01, (32, 40)).astype(np.float32)
+    m = getattr(pvt, fn)(f, t, formula=pvt.FORMULA_EPS)
+    exact = O.ncc_eps_exact(f, t, 0, 0, m.shape[1], m.shape[0])
+    seq = O.ncc_window_eps(f, t, 0, 0, m.shape[1], m.shape[0])           # FP32 sequential, like baseline_kernel.cu:21-64
+    assert np.abs(m - exact).max() <= 2e-5                                # FP64 window sums + blocked FP32 cross term
+    assert np.abs(m - seq).max() <= Hp.TOL_SCORE
+    assert np.argmax(m) == np.argmax(seq) == np.argmax(exact)
+    # and the default formula is untouched by a context of the other kind living next to it
+    assert np.abs(getattr(pvt, fn)(f, t) - O.ncc_match_cpu(f, t)).max() <= 2e-5
+
+
+def test_eps_formula_degenerate_cells_follow_the_kernel_not_opencv():
+    rng = np.random.default_rng(12)
+    f = _textured(rng, 90, 120)
+    flat_t = pvt.ncc_match_naive_cuda(f, np.full((16, 24), 0.25, np.float32), formula=pvt.FORMULA_EPS)
+    assert np.abs(flat_t).max() <= 1e-3 and np.all(np.isfinite(flat_t))    # cov == 0 (OpenCV's rule says 1 everywhere)
+    t = f[10:26, 30:54].copy()
+    flat_w = pvt.ncc_match_naive_cuda(np.full_like(f, 0.5), t, formula=pvt.FORMULA_EPS)
+    want = O.ncc_eps_exact(np.full_like(f, 0.5), t, 0, 0, flat_w.shape[1], flat_w.shape[0])
+    assert np.abs(flat_w - want).max() <= 1e-4 and np.abs(flat_w).max() <= 1e-2   # the 1e-3 floor on sigma_w, not a 0/0
+    outs = pvt.ncc_match_naive_cuda_batched([f, f[::-1].copy()], t, formula=pvt.FORMULA_EPS)
+    assert np.abs(outs[0] - O.ncc_eps_exact(f, t, 0, 0, outs[0].shape[1], outs[0].shape[0])).max() <= 2e-5
+    assert np.abs(outs[1] - O.ncc_eps_exact(f[::-1], t, 0, 0, outs[1].shape[1], outs[1].shape[0])).max() <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["small", "oddsize", "c1_standin"])
+def test_eps_formula_tracker_follows_the_gpu_mode_loop(name):
+    """main.cpp:103-161 fed by a GPU-mode map: same peaks, gates and EMA as the oracle loop run on the eps map."""
+    (c, tk) = Hp.clip(name)
+    kw = dict(search_radius_x=tk.get("rx", 80), search_radius_y=tk.get("ry", 80))
+    with O.formula(1):
+        want, wt = O.track_clip(c["frames"], c["roi"], rx=kw["search_radius_x"], ry=kw["search_radius_y"])
+    rec, templ = run_clip(c["frames"], c["roi"], formula=pvt.FORMULA_EPS, **kw)
+    Hp.check_records(rec, want[:, :7], name + " (eps)")
+    assert np.array_equal(templ, wt)
+    # the formula is a creation-time choice
+    with pvt.Tracker(64, 64, 8, 8) as tr:
+        with pytest.raises(pvt.PvtError):
+            tr.set_params(formula=pvt.FORMULA_EPS)

@@ -107,3 +107,32 @@ def test_window_map(name, k):
     deg = (off == 0) | (np.abs(off) == 1)
     assert np.array_equal(m[deg], off[deg])                          # G4 degenerate cells identical
     assert np.argmax(m) == np.argmax(on)                             # G1
+
+
+# ---- the eps formula of the reference's CUDA kernels (parity unpinned, see oracle/ncc_oracle.c) -----
+def test_eps_formula_restatement_vs_exact_arithmetic():
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(5)
+    f = gaussian_filter(rng.random((100, 140)), 2.0)
+    f = ((f - f.min()) / (f.max() - f.min())).astype(np.float32)
+    t = f[20:52, 60:92].copy() + rng.normal(0, 0.01, (32, 32)).astype(np.float32)
+    seq = O.ncc_window_eps(f, t, 3, 2, 90, 60)
+    exact = O.ncc_eps_exact(f, t, 3, 2, 90, 60)
+    assert np.abs(seq - exact).max() <= 5e-5            # sequential FP32 sums vs float64
+    assert np.unravel_index(np.argmax(seq), seq.shape) == (18, 57)
+    # close to, but not the same as, the CPU operator ("NOT the oracle formula")
+    cv = O.ncc_window(f, t, 3, 2, 90, 60)
+    assert 0 < np.abs(seq - cv).max() <= 1e-3
+    # flat template: cov == 0 -> 0 (OpenCV: 1); flat windows: the 1e-3 floor on sigma_w keeps the quotient finite
+    assert np.abs(O.ncc_window_eps(f, np.full((8, 8), 0.5, np.float32), 0, 0, 20, 20)).max() <= 1e-3
+    assert np.all(np.isfinite(O.ncc_window_eps(np.full_like(f, 0.5), t, 0, 0, 20, 20)))
+
+
+def test_eps_formula_switch_drives_the_tracker_loop_and_resets():
+    (c, tk) = Hp.clip("small")
+    base, _ = O.track_clip(c["frames"], c["roi"])
+    with O.formula(1):
+        eps, _ = O.track_clip(c["frames"], c["roi"])
+    again, _ = O.track_clip(c["frames"], c["roi"])
+    assert np.array_equal(base, again)
+    assert np.array_equal(base[:, :4], eps[:, :4]) and not np.array_equal(base[:, 4], eps[:, 4])
