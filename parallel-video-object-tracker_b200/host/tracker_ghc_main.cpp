@@ -44,6 +44,7 @@ int main(int argc, char** argv)
         else if (arg == "--radius" && i + 1 < argc) p.search_radius_x = p.search_radius_y = std::atoi(argv[++i]);
         else if (arg == "--lost" && i + 1 < argc) p.lost_frame_threshold = std::atoi(argv[++i]);
         else if (arg == "--global" && i + 1 < argc) p.ncc_global_confidence = std::atof(argv[++i]);
+        else if (arg == "--gpu-formula") p.formula = PVT_FORMULA_EPS;   // score like the reference's CUDA kernels, not like --cpu
     }
     if (mode == "cpu") { std::cerr << "--cpu is not available: libpvt has no CPU path (see oracle/ for the CPU restatement)\n"; return -1; }
     std::ifstream f(video_path, std::ios::binary);

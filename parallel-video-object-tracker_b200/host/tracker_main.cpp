@@ -7,6 +7,7 @@
 //   * input is a raw BGR clip instead of ../data/car.mp4:   magic "PVTBGR1\n", int32 W, H, N, then N*H*W*3 bytes
 //   * the ROI comes from --roi x,y,w,h instead of cv::selectROI (main.cpp:63; the reference has no default ROI)
 //   * instead of an annotated .mp4 the per-frame bbox/confidence goes to --out FILE as CSV (main.cpp:166 only draws it)
+//   * --gpu-formula (new) scores with the eps formula of the reference's CUDA kernels (pvt_formula) instead of the --cpu path's
 //   * --cpu is rejected: the library has no CPU path (the reference's CPU mode is restated in oracle/, test-only)
 #include <chrono>
 #include <cstdio>
@@ -32,7 +33,7 @@ int main(int argc, char** argv)
     std::string mode = NCC_MODE, input, out_csv;
     int batch = BATCH_SIZE;
     pvt::Rect bbox;
-    bool have_roi = false;
+    bool have_roi = false, gpu_formula = false;
     for (int i = 1; i < argc; ++i) {
         std::string arg = argv[i];
         if (arg == "--cpu") mode = "cpu";
@@ -42,6 +43,7 @@ int main(int argc, char** argv)
         else if (arg.rfind("--batch=", 0) == 0) { mode = "batch"; batch = std::max(1, std::atoi(arg.substr(8).c_str())); }
         else if (arg == "--roi" && i + 1 < argc) { have_roi = std::sscanf(argv[++i], "%d,%d,%d,%d", &bbox.x, &bbox.y, &bbox.width, &bbox.height) == 4; }
         else if (arg == "--out" && i + 1 < argc) out_csv = argv[++i];
+        else if (arg == "--gpu-formula") gpu_formula = true;
         else if (arg[0] != '-') input = arg;
     }
     std::cout << "--------\nNCC Tracker Starting\nInput video : " << input << "\nMode        : " << mode << "\n";
@@ -65,6 +67,7 @@ int main(int argc, char** argv)
     p.search_radius_x = SEARCH_RADIUS_X; p.search_radius_y = SEARCH_RADIUS_Y;
     p.ncc_min_confidence = NCC_MIN_CONFIDENCE; p.ncc_strong_confidence = NCC_STRONG_CONFIDENCE; p.template_update_lr = TEMPLATE_UPDATE_LR;
     p.batch_size = batch;
+    p.formula = gpu_formula ? PVT_FORMULA_EPS : PVT_FORMULA_CCOEFF_NORMED;
     p.mode = mode == "shared" ? PVT_MODE_SHARED : mode == "const" ? PVT_MODE_CONST : mode == "const_tiled" ? PVT_MODE_CONST_TILED
              : mode == "batch" ? PVT_MODE_BATCH : PVT_MODE_NAIVE;
     pvt_config cfg{};

@@ -56,6 +56,24 @@ def test_cli_trajectory_matches_golden(built, tmp_path, name, flags):
     Hp.check_records(got, g, f"cli {name} {flags}")
 
 
+@pytest.mark.gpu
+def test_cli_gpu_formula_flag_follows_the_eps_oracle(built, tmp_path):
+    from oracle import oracle as O
+    (c, tk) = Hp.clip("small")
+    with O.formula(1):
+        want, _ = O.track_clip(c["frames"], c["roi"])
+    write_clip(tmp_path / "c.bgr", c["frames"])
+    roi = ",".join(str(v) for v in c["roi"])
+    r = subprocess.run([os.path.join(built, "tracker"), "--gpu-formula", str(tmp_path / "c.bgr"), "--roi", roi, "--out", str(tmp_path / "o.csv")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = np.genfromtxt(tmp_path / "o.csv", delimiter=",", skip_header=1)
+    got = np.column_stack([rows[:, 1:5], rows[:, 5], rows[:, 6:8]])
+    Hp.check_records(got, want[:, :7], "cli --gpu-formula")
+    base = Hp.golden("clip_small.npz")["records"]
+    assert not np.array_equal(got[:, 4].astype(np.float32), base[:, 4].astype(np.float32))   # it is a different score
+
+
 def test_ghc_cli_builds_and_rejects(built, tmp_path):
     exe = os.path.join(built, "tracker_ghc")
     r = subprocess.run([exe, "nothing.bgr", "--cpu"], capture_output=True, text=True)
