@@ -529,3 +529,41 @@ def test_eps_formula_tracker_follows_the_gpu_mode_loop(name):
     with pvt.Tracker(64, 64, 8, 8) as tr:
         with pytest.raises(pvt.PvtError):
             tr.set_params(formula=pvt.FORMULA_EPS)
+
+
+# ---- random geometries under the planner's own choices (no PVT_PLAN): unequal radii, odd templates, boxes anywhere -----
+@pytest.mark.parametrize("seed", range(24))
+def test_random_geometries_vs_oracle(seed):
+    rng = np.random.default_rng(4242 + seed)
+    W, H = int(rng.integers(90, 420)), int(rng.integers(70, 300))
+    tw, th = int(rng.integers(3, min(72, W // 2))), int(rng.integers(3, min(72, H // 2)))
+    rx, ry = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+    n_tracks = int(rng.choice([1, 1, 3, 7]))
+    from scipy.ndimage import gaussian_filter
+    base = gaussian_filter(rng.random((H, W, 3)), (1.2, 1.2, 0))
+    f0 = np.clip((base - base.min()) / (base.max() - base.min()) * 255, 0, 255).astype(np.uint8)
+    f1 = np.clip(np.roll(f0, (int(rng.integers(-2, 3)), int(rng.integers(-2, 3))), (0, 1)).astype(np.int16)
+                 + rng.integers(-3, 4, f0.shape), 0, 255).astype(np.uint8)
+    outW, outH = W - tw + 1, H - th + 1
+    boxes = [(int(rng.integers(0, outW)), int(rng.integers(0, outH))) for _ in range(n_tracks)]
+    boxes[0] = [(0, 0), (outW - 1, outH - 1), (outW // 2, outH // 2)][seed % 3]        # corners and the middle
+    g0, g1 = O.to_gray_f32(f0), O.to_gray_f32(f1)
+    with pvt.Tracker(W, H, tw, th, max_streams=1, max_tracks=n_tracks, keep_maps=1, search_radius_x=rx, search_radius_y=ry) as tr:
+        for t, (x, y) in enumerate(boxes):
+            tr.init_track(t, f0 if t == 0 else None, (x, y, tw, th))
+        res = tr.step([f1])
+        for t, (x, y) in enumerate(boxes):
+            templ = g0[y:y + th, x:x + tw].copy()
+            rec, win, want = O.track_step(g1, templ, x, y, rx=rx, ry=ry, want_map=True)
+            m, w = tr.window_map(t)
+            assert w == win, (seed, t)
+            sig = Hp.window_sigma(g1, tw, th, win)
+            d = np.abs(m - want)
+            assert d[sig >= 0.002].max(initial=0) <= Hp.TOL_SCORE and d.max() <= Hp.TOL_LOWVAR, (seed, t, float(d.max()))
+            gap = np.sort(want.ravel())[-2:]
+            if want.size == 1 or gap[1] - gap[0] >= Hp.AMBIGUOUS_GAP:                          # G1, unless the oracle itself is ambiguous
+                assert (res[t]["x"], res[t]["y"]) == (rec.x, rec.y), (seed, t)
+                assert (res[t]["moved"], res[t]["updated"]) == (rec.moved, rec.updated)
+                assert abs(float(res[t]["conf"]) - rec.conf) <= Hp.TOL_SCORE
+                _, got_t = tr.get_state(t)
+                assert np.array_equal(got_t, templ), (seed, t)                                  # EMA bit-exact given the same peak
