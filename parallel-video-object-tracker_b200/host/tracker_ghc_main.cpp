@@ -54,7 +54,15 @@ int main(int argc, char** argv)
         std::cerr << "Cannot open video: " << video_path << std::endl;   // :84
         return -1;
     }
-    std::vector<uint8_t> frame((size_t)W * H * 3);
+    // page-locked frame buffer: the ROI ingest then reads just the search tile from it over PCIe (zero-copy) instead of
+    // staging the whole frame through a pageable copy; falls back to a plain buffer if pinning fails
+    struct FrameBuf {
+        uint8_t* p = nullptr; bool pinned = false; size_t n = 0;
+        explicit FrameBuf(size_t bytes) : n(bytes) { void* q = nullptr; if (pvt_alloc_pinned(&q, bytes) == PVT_OK) { p = (uint8_t*)q; pinned = true; } else p = new uint8_t[bytes]; }
+        ~FrameBuf() { if (pinned) pvt_free_pinned(p); else delete[] p; }
+        uint8_t* data() { return p; }
+        size_t size() const { return n; }
+    } frame((size_t)W * H * 3);
     if (N < 1 || !f.read((char*)frame.data(), frame.size())) { std::cerr << "Cannot read first frame from video." << std::endl; return -1; }   // :91
     std::cout << "Select template from the first frame.\n";   // :94
     if (!have_roi || roi.width == 0 || roi.height == 0) { std::cerr << "No template selected" << std::endl; return -1; }   // :117-120
