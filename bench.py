@@ -63,14 +63,14 @@ def peaks():
 
 def ncu_traffic(wname):
     """dram__bytes_read.sum + dram__bytes_write.sum of k_ncc_search per launch, from the committed `ncu --set full` capture of
-    this workload (profiles/traffic_r1.json names the summary file each number comes from); None when there is no capture."""
+    this workload and the summary file it comes from (profiles/traffic_r1.json); (None, None) when there is no capture."""
     p = os.path.join(ROOT, "profiles", "traffic_r1.json")
     try:
         with open(p) as fh:
             e = json.load(fh).get(wname)
-        return {"dram_bytes_per_launch": e["dram_bytes"], "source": e["source"]} if e else None
+        return (float(e["dram_bytes"]), e["source"]) if e else (None, None)
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -265,7 +265,8 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
         "value": value, "ms_per_step": ms / K, "launches": int(launches), "clocks": clocks, "conf_min": conf_min,
         "macs_per_step": macs_per_launch, "n_tracks": n_tracks, "wl": wl, "ingest_mode": ingest_mode,
         "roofline": {"kernel": "k_ncc_search", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": ncc_tf / fp32_peak, "traffic": ncu_traffic(wname),
+                     "frac": ncc_tf / fp32_peak, "traffic": ncu_traffic(wname)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
+                     "traffic_source": ncu_traffic(wname)[1],
                      "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
                      "us_per_launch": ncc_s * 1e6, "macs_per_launch": kmacs_per_launch,
                      "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps; "
