@@ -37,6 +37,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 constexpr int kMultiStep = 4;   // steps per launch of graph_multi: a graph-to-graph boundary costs ~4 us on the device, an edge inside a graph ~1.5 us
+constexpr int kLongStep = 16;   // ... and of graph_long (latency shape only: there 4 us per four 27 us steps is still 4 %)
 constexpr int kStageDepth = 3;  // host frames in flight per stream (H2D overlaps the previous step's kernels)
 constexpr size_t kSmemBudget = 227u * 1024u;
 
@@ -92,6 +93,7 @@ struct pvt_ctx {
     cudaGraphExec_t graph = nullptr, graph_hold = nullptr, graph_prof = nullptr;
     cudaGraphExec_t graph_multi = nullptr;   // kMultiStep consecutive time steps in one launch (resident frame rings)
     cudaGraphExec_t graph_pf = nullptr, graph_multi_pf = nullptr;   // the same with k_prefetch_roi (pinned host rings)
+    cudaGraphExec_t graph_long = nullptr, graph_long_pf = nullptr;  // kLongStep steps per launch (K-split shape)
     cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
     bool graph_valid = false;
     std::vector<void*> allocs;
@@ -681,33 +683,32 @@ int build_graphs(pvt_ctx* c)
     }
     CK(cudaGraphInstantiate(&c->graph, g, 0));
     CK(cudaGraphDestroy(g));
-    if (c->graph_multi) { cudaGraphExecDestroy(c->graph_multi); c->graph_multi = nullptr; }
-    if (!c->lost_mode) {
-        // every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
+    for (cudaGraphExec_t* ge : {&c->graph_multi, &c->graph_long, &c->graph_pf, &c->graph_multi_pf, &c->graph_long_pf})
+        if (*ge) { cudaGraphExecDestroy(*ge); *ge = nullptr; }
+    // every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
+    auto capture_steps = [&](const Pass& p, int n, cudaGraphExec_t* out) -> int {
+        cudaGraph_t gs = nullptr;
         CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-        r = PVT_OK;
-        for (int k = 0; k < kMultiStep && !r; ++k) r = launch_step_kernels(c, lp, false, true);
-        e = cudaStreamEndCapture(c->compute, &g);
-        if (r) return r;
-        CK(e);
-        CK(cudaGraphInstantiate(&c->graph_multi, g, 0));
-        CK(cudaGraphDestroy(g));
+        int rr = PVT_OK;
+        for (int k = 0; k < n && !rr; ++k) rr = launch_step_kernels(c, p, false, true);
+        cudaError_t ee = cudaStreamEndCapture(c->compute, &gs);
+        if (rr) return rr;
+        CK(ee);
+        CK(cudaGraphInstantiate(out, gs, 0));
+        CK(cudaGraphDestroy(gs));
+        return PVT_OK;
+    };
+    const bool latency_shape = c->params.kernel != PVT_KERNEL_DIRECT && lp.tile.pj * lp.tile.pd > 1;
+    if (!c->lost_mode) {
+        if ((r = capture_steps(lp, kMultiStep, &c->graph_multi))) return r;
+        if (latency_shape && (r = capture_steps(lp, kLongStep, &c->graph_long))) return r;
     }
-    if (c->graph_pf) { cudaGraphExecDestroy(c->graph_pf); c->graph_pf = nullptr; }
-    if (c->graph_multi_pf) { cudaGraphExecDestroy(c->graph_multi_pf); c->graph_multi_pf = nullptr; }
     if (!c->lost_mode && c->d.stage) {
         Pass pp = lp;
         pp.prefetch = true;
-        for (int variant = 0; variant < 2; ++variant) {
-            CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-            r = PVT_OK;
-            for (int k = 0; k < (variant ? kMultiStep : 1) && !r; ++k) r = launch_step_kernels(c, pp, false, true);
-            e = cudaStreamEndCapture(c->compute, &g);
-            if (r) return r;
-            CK(e);
-            CK(cudaGraphInstantiate(variant ? &c->graph_multi_pf : &c->graph_pf, g, 0));
-            CK(cudaGraphDestroy(g));
-        }
+        if ((r = capture_steps(pp, 1, &c->graph_pf))) return r;
+        if ((r = capture_steps(pp, kMultiStep, &c->graph_multi_pf))) return r;
+        if (latency_shape && (r = capture_steps(pp, kLongStep, &c->graph_long_pf))) return r;
     }
     if (c->graph_prof) { cudaGraphExecDestroy(c->graph_prof); c->graph_prof = nullptr; }
     CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
@@ -987,6 +988,8 @@ int pvt_destroy(pvt_ctx* c)
     if (c->graph_hold) cudaGraphExecDestroy(c->graph_hold);
     if (c->graph_prof) cudaGraphExecDestroy(c->graph_prof);
     if (c->graph_multi) cudaGraphExecDestroy(c->graph_multi);
+    if (c->graph_long) cudaGraphExecDestroy(c->graph_long);
+    if (c->graph_long_pf) cudaGraphExecDestroy(c->graph_long_pf);
     if (c->graph_pf) cudaGraphExecDestroy(c->graph_pf);
     if (c->graph_multi_pf) cudaGraphExecDestroy(c->graph_multi_pf);
     if (c->graph_global) cudaGraphExecDestroy(c->graph_global);
@@ -1355,16 +1358,19 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
         if (r) return r;
         if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }
         cudaGraphExec_t g_one = pf ? c->graph_pf : c->graph, g_multi = pf ? c->graph_multi_pf : c->graph_multi;
+        cudaGraphExec_t g_long = pf ? c->graph_long_pf : c->graph_long;
         const bool batch = c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1;
         for (int s = 0; s < n_steps; ++s) {
             // several steps per launch while no result read-back falls inside the group
-            const bool multi_ok = !batch && g_multi && s + kMultiStep <= n_steps &&
-                                  (collect_every <= 0 || (s % collect_every) + kMultiStep <= collect_every);
-            if (multi_ok) {
-                CK(cudaGraphLaunch(g_multi, c->compute));
-                c->launches += (int64_t)kMultiStep * (c->kps + (pf ? 1 : 0));
-                c->submitted += kMultiStep;
-                s += kMultiStep - 1;
+            auto fits = [&](cudaGraphExec_t ge, int n) {
+                return !batch && ge && s + n <= n_steps && (collect_every <= 0 || (s % collect_every) + n <= collect_every);
+            };
+            const int group = fits(g_long, kLongStep) ? kLongStep : fits(g_multi, kMultiStep) ? kMultiStep : 1;
+            if (group > 1) {
+                CK(cudaGraphLaunch(group == kLongStep ? g_long : g_multi, c->compute));
+                c->launches += (int64_t)group * (c->kps + (pf ? 1 : 0));
+                c->submitted += group;
+                s += group - 1;
                 if (collect_every <= 0 || (s + 1) % collect_every != 0) continue;
             } else {
             bool hold = false;
