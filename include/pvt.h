@@ -17,6 +17,8 @@
  *   tracker/src/main.cpp:115-130               --batch=N hold semantics                 -> pvt_params.mode == PVT_MODE_BATCH
  *   tracker/src/baseline_kernel.cu:12-18       checkCuda -> exit(1)                     -> negative return code + pvt_last_error()
  *   tracker_ghc/src/main.cpp:17-23,183-239     lost-object logic: whole-frame re-acquisition -> pvt_params.lost_frame_threshold / ncc_global_confidence
+ *   tracker/src/baseline_kernel.cu:44-49,62,329-332  score formula of the five CUDA kernels (differs from --cpu) -> pvt_params.formula = PVT_FORMULA_EPS,
+ *                                                    PVT_MODE_FLAG_EPS, pvt_ncc_match_batched_f (opt-in; the default is the --cpu path's)
  *
  * Results follow the reference's `--cpu` path (cv::matchTemplate TM_CCOEFF_NORMED, OpenCV 4.13.0):
  * identical peak per frame (ties -> lowest row-major index), scores within 1e-4, identical bbox
