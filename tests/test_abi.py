@@ -42,7 +42,7 @@ def test_default_params_are_the_reference_constants():
 def test_struct_layouts():
     assert C.sizeof(pvt.Result) == 32 and pvt.RESULT_DTYPE.itemsize == 32
     assert C.sizeof(pvt.Frame) == 32
-    assert C.sizeof(pvt.Params) == 8 + 24 + 5 * 4 + 4 + 8 + 8   # + lost_frame_threshold, reserved[2], ncc_global_confidence
+    assert C.sizeof(pvt.Params) == 8 + 24 + 5 * 4 + 4 + 8 + 8   # + lost_frame_threshold, formula, reserved, ncc_global_confidence
     assert C.sizeof(pvt.Config) == 16 * 4
 
 
@@ -80,6 +80,16 @@ def test_invalid_arguments_return_codes():
     with pytest.raises(pvt.PvtError) as e:
         pvt.Tracker(64, 64, 8, 8, search_radius_x=-1)
     assert e.value.code == pvt.ERR_INVALID
+    with pytest.raises(pvt.PvtError) as e:
+        pvt.Tracker(64, 64, 8, 8, formula=7)                      # pvt_formula is validated before any device is touched
+    assert e.value.code == pvt.ERR_INVALID and "formula" in str(e.value)
+    f = np.zeros((16, 16), np.float32)
+    with pytest.raises(pvt.PvtError) as e:
+        pvt.ncc_match_naive_cuda_batched([f], f[:4, :4], formula=7)
+    assert e.value.code == pvt.ERR_INVALID
+    with pytest.raises(pvt.PvtError) as e:                        # the eps flag does not unlock the CPU mode either
+        pvt._ncc_match(pvt.MODE_CPU, f, f[:4, :4], formula=pvt.FORMULA_EPS)
+    assert e.value.code == pvt.ERR_UNSUPPORTED
 
 
 def test_product_never_touches_the_oracle():
