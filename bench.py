@@ -13,8 +13,9 @@ headline; the batch=4 figure is reported beside it under "batch4".)
 With N>1 every rank runs its own seeded stream of the same shape (tracks shard by stream, no collective on the
 data path; scaling "weak").  Other workloads: --workload C3 | C4 | C5.
 
-Prints ONE JSON line (rank 0).  `value` = frames/s with the frame ring resident in HBM, timed with CUDA events on
-the library's stream (max over ranks).  `e2e` = the same loop through the C ABI with PINNED HOST frames: the H2D
+Prints ONE JSON line (rank 0).  `value` = frames/s with the frame ring resident in HBM: the K-step region, bracketed by
+barrier + synchronize and timed with CUDA events on the library's stream (max over ranks), is repeated REGIONS times and
+the MEDIAN region is reported (`regions_ms` holds all of them).  `e2e` = the same loop through the C ABI with PINNED HOST frames: the H2D
 copy of every frame and the D2H read of every result are inside the timed region.  `roofline` = the NCC search
 kernel (FP32-FMA bound: 2*MACs / t / (SMs*128*2*f_max)), durations from CUDA events around each launch in an
 identical second pass; `ingest` HBM fraction is reported beside it against MEASURED_PEAKS.json.
@@ -118,22 +119,50 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_rings(wl, rank, torch):
-    """Per stream: a periodic clip of `ring` frames (frame `ring` == frame 0), resident in HBM and in pinned host memory."""
-    W, H, tw, th, R = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"]
+_SCENES = {}
+
+
+def scene_for(wl, seed):
+    """Scenes are expensive to build (seconds at 1080p): cache by (seed, geometry)."""
     L = wl["ring"]
-    n_distinct = min(wl["streams"], 8)  # distinct contents; further streams reuse them in their OWN buffers
-    scenes = [synth.Scene(synth.ClipSpec(seed=100 + 17 * rank + i, W=W, H=H, tw=tw, th=th, n_frames=L, R=R, period=L)) for i in range(n_distinct)]
-    host = torch.empty((wl["streams"], L, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    key = (seed, wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], L)
+    if key not in _SCENES:
+        _SCENES[key] = synth.Scene(synth.ClipSpec(seed=seed, W=wl["W"], H=wl["H"], tw=wl["tw"], th=wl["th"], n_frames=L, R=wl["R"], period=L))
+    return _SCENES[key]
+
+
+def build_rings(wl, rank, torch, stream_ids=None, want_host=True):
+    """Per stream: a periodic clip of `ring` frames (frame `ring` == frame 0), resident in HBM and in pinned host memory.
+    stream_ids: GLOBAL stream ids of this rank's shard (sharded workloads: content depends on the global id only, so the
+    gathered records can be checked against the ground truth on rank 0); default: `streams` rank-seeded streams."""
+    W, H = wl["W"], wl["H"]
+    L, S = wl["ring"], wl["streams"]
+    if stream_ids is None:
+        seeds = [100 + 17 * rank + (i % 8) for i in range(S)]  # 8 distinct contents; further streams reuse them in their OWN buffers
+    else:
+        seeds = [100 + (g % 8) for g in stream_ids]
+    scenes = [scene_for(wl, sd) for sd in seeds]
+    first = {}
+    nbytes = S * L * H * W * 3
+    pin = want_host
+    if pin:
+        try:
+            import psutil
+            pin = psutil.virtual_memory().available > 3 * nbytes + (8 << 30)
+        except Exception:
+            pin = nbytes < (4 << 30)
+    host = torch.empty((S, L, H, W, 3), dtype=torch.uint8, pin_memory=bool(pin))
     hn = host.numpy()
-    for i, sc in enumerate(scenes):
-        for k in range(L):
-            hn[i, k] = sc.frame(k)
-    for s in range(n_distinct, wl["streams"]):
-        hn[s] = hn[s % n_distinct]
+    for i, sd in enumerate(seeds):
+        if sd in first:
+            hn[i] = hn[first[sd]]
+        else:
+            first[sd] = i
+            for k in range(L):
+                hn[i, k] = scenes[i].frame(k)
     dev = host.cuda(non_blocking=False)
     torch.cuda.synchronize()
-    return scenes, host, dev
+    return scenes, (host if pin else None), dev
 
 
 def rois_for(wl, scene):
@@ -160,18 +189,30 @@ def ring_descs(pvt, wl, buf, device_mem):
         fr = []
         for s in range(S):
             ptr = buf[s, k].data_ptr()
-            fr.append(pvt.Frame(s, pvt.FMT_BGR8, pvt.MEM_DEVICE if device_mem else pvt.MEM_HOST, 0, ptr, W * 3))
+            fr.append(pvt.Frame(s, pvt.FMT_BGR8, pvt.MEM_DEVICE if device_mem else pvt.MEM_HOST_PINNED, 0, ptr, W * 3))
         ring.append(fr)
     return ring
 
 
-def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
-    """All legs of one workload on this rank.  full=False: only the resident leg + the roofline pass (used for `extra`)."""
-    wl = dict(WORKLOADS[wname])
+REGIONS = 5   # the K-step timed region is repeated this many times; the median is reported
+
+
+def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=None, stream_ids=None, total_streams=None,
+            gather=None, e2e_leg=None):
+    """All legs of one workload on this rank.  full=False: only the resident leg + the roofline pass (used for `extra`).
+    wl / stream_ids / total_streams: a sharded workload (this rank's share of `total_streams` global streams);
+    gather(records) -> all ranks' last-step records in global order (off the timed path); e2e_leg: force the pinned-host leg."""
+    wl = dict(wl or WORKLOADS[wname])
     W, H, tw, th, R, L, S = wl["W"], wl["H"], wl["tw"], wl["th"], wl["R"], wl["ring"], wl["streams"]
     n_tracks = S * wl["rois"]
+    total = total_streams if total_streams is not None else world * S      # streams the whole job advances per step
     dev_index = torch.cuda.current_device()
-    scenes, host, dev = build_rings(wl, rank, torch)
+    want_e2e = full if e2e_leg is None else e2e_leg
+    # clocks / throttle reasons: the sampler runs from before the warm-up to after the last timed region (starting an
+    # nvidia-smi process per rank BETWEEN the barrier and the timer, as round 1 did, perturbs the measurement)
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    scenes, host, dev = build_rings(wl, rank, torch, stream_ids=stream_ids, want_host=want_e2e)
     info = pvt.device_info(dev_index)
 
     def make_tracker(**kw):
@@ -179,7 +220,7 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
                          search_radius_x=R, search_radius_y=R, **kw)
         t = 0
         for s in range(S):
-            for j, roi in enumerate(rois_for(wl, scenes[s % len(scenes)])):
+            for j, roi in enumerate(rois_for(wl, scenes[s])):
                 tr.init_track(t, pvt.device_frame(dev[s, 0].data_ptr(), W * 3, stream=s) if j == 0 else None, roi, stream=s)
                 t += 1
         return tr
@@ -190,58 +231,78 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
     # ---- leg 1: frames resident in HBM (value) -----------------------------------------------------
     ring_dev = ring_descs(pvt, wl, dev, True)
     tr = make_tracker()
-    # pre-warm: the same load for >= 50 ms (whole ring revolutions, so the W warm-up steps below start where they always did):
-    # a few-ms timed region right after an idle GPU otherwise measures the clock ramp, +-4 % from run to run
-    prewarm, t_pre = 0, time.perf_counter()
-    while full and time.perf_counter() - t_pre < 0.05:
-        tr.submit_sequence(4 * L, shifted(ring_dev, 1))
+    pos = 0                      # steps submitted so far == ring phase
+    # pre-warm: the same load for >= 50 ms and until nvidia-smi has delivered its first sample: a few-ms timed region right
+    # after an idle GPU otherwise measures the clock ramp
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.05 or (full and len(sampler.rows) < 1 and time.perf_counter() - t_pre < 1.0):
+        tr.submit_sequence(K, shifted(ring_dev, 1 + pos))
         tr.sync()
-        prewarm += 4 * L
-    tr.submit_sequence(Wm, shifted(ring_dev, 1))
+        pos += K
+    prewarm = pos
+    tr.submit_sequence(Wm, shifted(ring_dev, 1 + pos))   # the W untimed warm-up steps
     tr.sync()
-    sampler = ClockSampler(dev_index)
-    barrier()
-    sampler.start()
-    l0 = tr.launch_count()
-    tr.timer_start()
-    tr.submit_sequence(K, shifted(ring_dev, 1 + Wm))
-    ms = tr.timer_stop()
-    barrier()
-    launches = tr.launch_count() - l0
-    # nvidia-smi samples every 100 ms; a timed region of a few tens of ms may see none, so the IDENTICAL load keeps
+    pos += Wm
+    regions, launches = [], 0
+    for _ in range(REGIONS):
+        barrier()
+        l0 = tr.launch_count()
+        tr.timer_start()
+        tr.submit_sequence(K, shifted(ring_dev, 1 + pos))
+        ms = tr.timer_stop()
+        barrier()
+        launches = tr.launch_count() - l0
+        pos += K
+        regions.append(maxr(ms))
+    # nvidia-smi samples every 100 ms; the timed regions may be shorter than that, so the IDENTICAL load keeps
     # running (untimed) until three samples under load exist
     extra_steps, t_wait = 0, time.perf_counter()
-    while len(sampler.rows) < 3 and time.perf_counter() - t_wait < 3.0:
-        tr.submit_sequence(K, shifted(ring_dev, 1 + Wm + K + extra_steps))
+    while full and len(sampler.rows) < 3 and time.perf_counter() - t_wait < 3.0:
+        tr.submit_sequence(K, shifted(ring_dev, 1 + pos))
         tr.sync()
+        pos += K
         extra_steps += K
     clocks = sampler.stop()
-    clocks["sampled_over"] = "timed region + %d further identical untimed steps" % extra_steps
-    ms = maxr(ms)
+    clocks["sampled_over"] = "pre-warm + warm-up + %d timed regions + %d further identical untimed steps" % (REGIONS, extra_steps)
+    ms = float(np.median(regions))
     # correctness guard: the last steps must sit exactly on the synthetic ground truth
     last = tr.collect(min(64, K))
     ok = True
     for i in range(len(last)):
-        stp = Wm + K + extra_steps - len(last) + i + 1
+        stp = pos - len(last) + i + 1
         for s in range(S):
-            tx, ty = scenes[s % len(scenes)].obj_pos(stp % L)
+            tx, ty = scenes[s].obj_pos(stp % L)
             r = last[i][s * wl["rois"]]
             ok &= bool(r["x"] == tx and r["y"] == ty and r["searched"] == 1)
     if not ok:
         raise SystemExit("bench: tracked boxes left the synthetic ground truth -- refusing to report a number")
+    gathered = None
+    if gather is not None:
+        # sharded workload: every rank's last-step records, all-gathered in GLOBAL stream order (NCCL, off the timed path)
+        # and checked against the ground truth of every stream of the job, not just this rank's
+        allr = gather(np.ascontiguousarray(last[-1][::wl["rois"]]))
+        good = 0
+        for g in range(total):
+            tx, ty = scene_for(wl, 100 + (g % 8)).obj_pos(pos % L)
+            good += int(allr[g]["x"] == tx and allr[g]["y"] == ty and allr[g]["searched"] == 1 and allr[g]["valid"] == 1)
+        if good != total:
+            raise SystemExit("bench: gathered records of the sharded job left the ground truth (%d of %d ok)" % (good, total))
+        gathered = {"tracks_checked": int(total), "how": "shard.gather_records (all_gather of the last step's pvt_result rows), every "
+                    "global stream compared with the synthetic ground truth on each rank"}
     conf_min = float(last["conf"][:, ::wl["rois"]].min())
-    value = world * S * K / (ms * 1e-3)
+    value = total * K / (ms * 1e-3)
 
     # ---- leg 2: identical pass with CUDA event-record nodes around every kernel class inside the graph ------
     Kp = min(K, 100)
     tr.profile_enable(True)
     tr.profile_get(reset=True)
-    tr.submit_sequence(Kp, shifted(ring_dev, 1 + Wm + K + extra_steps))
+    tr.submit_sequence(Kp, shifted(ring_dev, 1 + pos))
+    pos += Kp
     prof = tr.profile_get(reset=True)
     tr.profile_enable(False)
     # warm device-side timeline of the same graph (globaltimer stamps; first CTA start .. last CTA end per kernel)
     tr.trace_enable(True)
-    tr.submit_sequence(24, shifted(ring_dev, 1 + Wm + K + extra_steps + Kp))
+    tr.submit_sequence(24, shifted(ring_dev, 1 + pos))
     T = tr.trace_get(16).astype(np.int64)
     tr.trace_enable(False)
     names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe", "ncc_tail_finalize"]
@@ -270,11 +331,15 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
     steps_p = max(prof["steps"], 1)
     out = {
         "value": value, "ms_per_step": ms / K, "launches": int(launches), "clocks": clocks, "conf_min": conf_min, "prewarm_steps": prewarm,
+        "regions_ms": [round(r, 5) for r in regions], "regions_spread": (max(regions) - min(regions)) / ms, "gathered": gathered,
         "macs_per_step": macs_per_launch, "n_tracks": n_tracks, "wl": wl, "ingest_mode": ingest_mode,
         "roofline": {"kernel": "k_ncc_search", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": ncc_tf / fp32_peak, "traffic": ncu_traffic(wname)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
                      "traffic_source": ncu_traffic(wname)[1],
                      "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
+                     "peak_measured": 0.985 * fp32_peak, "frac_of_measured": ncc_tf / (0.985 * fp32_peak),
+                     "peak_measured_source": "tools/microbench.cu on B200: dependent-free FFMA stream sustains 98.5 % of nominal "
+                                             "(profiles/microbench_r1.log); MEASURED_PEAKS.json has no FP32 entry",
                      "us_per_launch": ncc_s * 1e6, "macs_per_launch": kmacs_per_launch,
                      "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps; "
                             "MACs = candidates of the kernel's thread-tile grid x tw x th" % Kp,
@@ -286,7 +351,53 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
                                "finalize_update": prof["update_ms"] / steps_p},
         "device_timeline_us": timeline,
     }
+
+    # ---- end to end through the C ABI with pinned HOST frames (leg 5 of a full run; also the sharded extra) ---------
+    def run_e2e():
+        if host is None:
+            return {"value": None, "unit": "frames/s", "skipped": "not enough free host memory to pin %.1f GB of frames" % (S * L * H * W * 3 / 1e9)}
+        ring_host = ring_descs(pvt, wl, host, False)
+        tre = make_tracker()
+        ce = 32 if K >= 32 else K
+        Ke = (K // ce) * ce
+        pe = 0
+        for _ in range(2):   # untimed: the same call shape as the timed one (graphs uploaded, staging and read-back paths warm)
+            tre.submit_sequence(Ke, shifted(ring_host, 1 + pe), collect_every=ce, want_results=True)
+            tre.sync()
+            pe += Ke
+        times = []
+        for _ in range(REGIONS):
+            barrier()
+            t0 = time.perf_counter()
+            res = tre.submit_sequence(Ke, shifted(ring_host, 1 + pe), collect_every=ce, want_results=True)
+            tre.sync()
+            times.append(maxr(time.perf_counter() - t0))
+            pe += Ke
+            for i in range(max(0, Ke - 8), Ke):
+                stp = pe - Ke + i + 1
+                for s2 in range(S):
+                    tx, ty = scenes[s2].obj_pos(stp % L)
+                    if not (res[i][s2 * wl["rois"]]["x"] == tx and res[i][s2 * wl["rois"]]["y"] == ty):
+                        raise SystemExit("bench: e2e leg lost the object")
+        tre.close()
+        e2e_s = float(np.median(times))
+        roi = ingest_mode.startswith("roi")
+        tile_bytes = n_tracks * (2 * R + 1 + tw + 3) * (2 * R + th) * 3
+        prefetch = roi and n_tracks <= 8      # pvt_create's condition for k_prefetch_roi (pinned host rings)
+        if prefetch:                          # the tile grown by R on every side crosses PCIe instead of the tile (clamped at the frame)
+            tile_bytes = n_tracks * min(W, 3 * R + 1 + tw + 3) * min(H, 3 * R + th) * 3
+        return {"value": total * Ke / e2e_s, "unit": "frames/s",
+                "h2d_bytes_per_step": int(tile_bytes if roi else S * W * H * 3), "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke,
+                "regions_s": [round(t, 6) for t in times],
+                "how": ("pvt_submit_sequence over pinned host BGR frames (PVT_MEM_HOST_PINNED), wall clock around the call + sync, median of %d regions; " % REGIONS +
+                        ("k_prefetch_roi reads the next step's likely search tile (the tile grown by R/2) zero-copy over PCIe beside the current step; "
+                         if prefetch else "ROI ingest reads the search tiles zero-copy over PCIe; ") +
+                        "bytes = pixels actually read (whole frames are %d B); results read back every %d steps, pipelined" % (S * W * H * 3, ce)) if roi else
+                       "pvt_submit_sequence over pinned host BGR frames, staged H2D copy of whole frames; results read back every %d steps" % ce}
+
     if not full:
+        if want_e2e:
+            out["e2e"] = run_e2e()
         return out
 
     # ---- leg 3: full-frame ingest (the reference's toGrayF32 on whole frames) against the HBM roofline -------
@@ -323,37 +434,8 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True):
         trb.close()
         out["batch4"] = {"frames_per_s": world * K / (msb * 1e-3), "searched_frames_per_s": world * (K // 4) / (msb * 1e-3), "ms_per_frame": msb / K}
 
-    # ---- leg 5: end to end through the C ABI with pinned HOST frames ------------------------------------
-    ring_host = ring_descs(pvt, wl, host, False)
-    tre = make_tracker()
-    ce = 32 if K >= 32 else K
-    Ke = (K // ce) * ce
-    tre.submit_sequence(min(Wm, 8), shifted(ring_host, 1), collect_every=0)
-    tre.sync()
-    barrier()
-    t0 = time.perf_counter()
-    res = tre.submit_sequence(Ke, shifted(ring_host, 1 + min(Wm, 8)), collect_every=ce, want_results=True)
-    tre.sync()
-    e2e_s = maxr(time.perf_counter() - t0)
-    for i in range(max(0, Ke - 8), Ke):
-        stp = min(Wm, 8) + i + 1
-        tx, ty = scenes[0].obj_pos(stp % L)
-        if not (res[i][0]["x"] == tx and res[i][0]["y"] == ty):
-            raise SystemExit("bench: e2e leg lost the object")
-    tre.close()
-    roi = ingest_mode.startswith("roi")
-    tile_bytes = n_tracks * (2 * R + 1 + tw + 3) * (2 * R + th) * 3
-    prefetch = roi and n_tracks <= 8      # pvt_create's condition for k_prefetch_roi (pinned host rings)
-    if prefetch:                          # the tile grown by R on every side crosses PCIe instead of the tile (clamped at the frame)
-        tile_bytes = n_tracks * min(W, 3 * R + 1 + tw + 3) * min(H, 3 * R + th) * 3
-    out["e2e"] = {"value": world * S * Ke / e2e_s, "unit": "frames/s",
-                  "h2d_bytes_per_step": int(tile_bytes if roi else S * W * H * 3), "d2h_bytes_per_step": int(32 * n_tracks), "steps": Ke,
-                  "how": ("pvt_submit_sequence over pinned host BGR frames; " +
-                          ("k_prefetch_roi reads the next step's likely search tile (the tile grown by R/2) zero-copy over PCIe beside the current step; "
-                           if prefetch else "ROI ingest reads the search tiles zero-copy over PCIe; ") +
-                          "bytes = pixels actually read (whole frames are %d B); results read back every %d steps, pipelined" % (S * W * H * 3, ce)) if roi else
-                         "pvt_submit_sequence over pinned host BGR frames, staged H2D copy of whole frames; results read back every %d steps" % ce}
-    out["_scene0"], out["_host0"] = scenes[0], host[0].numpy()
+    out["e2e"] = run_e2e()
+    out["_scene0"], out["_host0"] = scenes[0], dev[0].cpu().numpy()
     return out
 
 
@@ -391,30 +473,50 @@ def run_ours(args):
     out = {
         "metric": "tracked_frames_per_s", "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [wl["W"], wl["H"]], "template": [wl["tw"], wl["th"]], "radius": wl["R"],
-                   "streams_per_gpu": wl["streams"], "tracks_per_gpu": m["n_tracks"], "ring_frames_per_stream": wl["ring"], "ingest": m["ingest_mode"],
-                   "l2_policy": "frame ring %.0f MB per GPU > 126 MB L2; no explicit flush" % (wl["streams"] * wl["ring"] * wl["W"] * wl["H"] * 3 / 1e6),
-                   "parallelism": "1 process per GPU, tracks sharded by stream, no data-path collective"},
-        "ncc_gmacs_per_s": world * m["macs_per_step"] * K / (m["ms_per_step"] * K * 1e-3) / 1e9,
+        "config": config_of(args.workload, wl),
+        "run": {"ingest": m["ingest_mode"], "timed_regions": REGIONS, "regions_ms": m["regions_ms"], "regions_spread": m["regions_spread"],
+                "value_is": "median over the timed regions of (streams x K steps) / (max over ranks of the region's CUDA-event time)"},
+        "ncc_gmacs_per_s": world * m["macs_per_step"] / (m["ms_per_step"] * 1e-3) / 1e9,
         "roofline": m["roofline"], "ingest": m["ingest"], "kernel_ms_per_step": m["kernel_ms_per_step"],
         "device_timeline_us": m["device_timeline_us"], "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": m["clocks"],
         "conf_min": m["conf_min"], "batch4": m["batch4"], "prewarm_steps": m["prewarm_steps"],
     }
-    if rank == 0 and world == 1 and args.extra:
-        # the search kernel with the GPU filled: SURVEY.md 8(d) configs C4 (256 ROIs) and C5's per-GPU share (64 streams)
+    if args.extra:
         out["extra"] = {}
-        for w2 in ("C4", "C5"):
+        # BASELINE.json configs[4]: 512 independent 1080p tracks sharded by stream over the N GPUs of the job (track i ->
+        # rank i mod N, shard.shard_tracks); every rank takes part; resident and pinned-host legs; records all-gathered
+        # over NCCL off the timed path and checked against the ground truth of all 512 streams
+        shard = importlib.import_module("parallel-video-object-tracker_b200.shard")
+        TOTAL = 512
+        ids = shard.shard_tracks(TOTAL, world, rank)
+        wl5 = dict(WORKLOADS["C5"], streams=len(ids))
+
+        def gather(local):
+            return shard.gather_records(local, TOTAL, world, rank, dist if world > 1 else None)
+
+        e = measure(pvt, torch, "C5_sharded", rank, world, 20, 4, barrier, maxr, full=False, wl=wl5, stream_ids=ids, total_streams=TOTAL,
+                    gather=gather, e2e_leg=True)
+        out["extra"]["C5_sharded"] = {
+            "workload": "512 independent 1920x1080 streams sharded by stream over %d GPU(s): %d streams on rank 0, 64x64 template, radius 80" % (world, len(ids)),
+            "tracks_total": TOTAL, "tracks_rank0": len(ids), "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
+            "regions_ms": e["regions_ms"], "e2e": e.get("e2e"), "ncc_gmacs_per_s": world * e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9,
+            "roofline": e["roofline"], "kernel_ms_per_step": e["kernel_ms_per_step"], "ingest": e["ingest_mode"], "gathered": e["gathered"]}
+    if rank == 0 and world == 1 and args.extra:
+        # the search kernel with the GPU filled: SURVEY.md 8(d) configs C3 (one 4K stream), C4 (256 ROIs) and C5's per-GPU share (64 streams)
+        for w2 in ("C3", "C4", "C5"):
             if w2 == args.workload:
                 continue
-            e = measure(pvt, torch, w2, 0, 1, 40, 6, barrier, maxr, full=False)
+            e = measure(pvt, torch, w2, 0, 1, 40 if w2 != "C3" else 60, 6, barrier, maxr, full=False)
             out["extra"][w2] = {"workload": WORKLOADS[w2]["desc"], "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
+                                "regions_ms": e["regions_ms"],
                                 "ncc_gmacs_per_s": e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9, "roofline": e["roofline"],
-                                "kernel_ms_per_step": e["kernel_ms_per_step"], "ingest": e["ingest_mode"]}
+                                "kernel_ms_per_step": e["kernel_ms_per_step"], "device_timeline_us": e["device_timeline_us"], "ingest": e["ingest_mode"]}
         out["extra"]["whole_frame_search"] = whole_frame_leg(pvt, torch, m)
+        out["extra"]["map_operator"] = map_operator_leg(pvt, m)
         # the search kernel's roofline fraction where the GPU is full (the headline workload is a single latency-bound stream)
         out["roofline"]["filled_gpu"] = {w2: {"frac": e2["roofline"]["frac"], "achieved": e2["roofline"]["achieved"],
                                               "search_phase_frac": e2["roofline"]["search_phase"]["frac"], "traffic": e2["roofline"]["traffic"]}
-                                         for w2, e2 in out["extra"].items() if w2 in WORKLOADS}
+                                         for w2, e2 in out["extra"].items() if "roofline" in e2}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, m["_scene0"], m["_host0"], budget_s=args.cpu_seconds)
     if rank == 0:
@@ -424,6 +526,45 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def config_of(wname, wl):
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    return {"workload": f"{wname}: {wl['desc']}", "frame": [wl["W"], wl["H"]], "template": [wl["tw"], wl["th"]], "radius": wl["R"],
+            "streams_per_gpu": wl["streams"], "tracks_per_gpu": wl["streams"] * wl["rois"], "ring_frames_per_stream": wl["ring"],
+            "l2_policy": "every step reads a different frame of a %d-frame ring (%.0f MB per GPU > 126 MB L2); no explicit flush" %
+                         (wl["ring"], wl["streams"] * wl["ring"] * wl["W"] * wl["H"] * 3 / 1e6),
+            "parallelism": "1 process per GPU, tracks sharded by stream, no data-path collective"}
+
+
+def map_operator_leg(pvt, m, n=6):
+    """The operator-level drop-in (baseline_kernel.hpp:8-17): pvt_ncc_match on HOST buffers, full 1857x1017 map out, synchronous --
+    the contract of the reference's ncc_match_* calls, whose own cost is cudaMalloc/Free + H2D + kernel + D2H per call."""
+    from tools import synth as _s  # noqa: F401
+    frames = m["_host0"]
+    sc = m["_scene0"]
+    x, y = sc.obj_pos(0)
+    lut = (np.arange(256, dtype=np.float32) * (np.float32(1.0) / np.float32(255.0))).astype(np.float32)
+
+    def gray(f):   # any f32 image serves the timing; (B+G+R)/3 through the ingest LUT keeps realistic texture without the oracle
+        return lut[(f.astype(np.uint16).sum(2) // 3).astype(np.uint8)]
+
+    g0 = gray(frames[0])
+    t = np.ascontiguousarray(g0[y:y + 64, x:x + 64])
+    pvt.ncc_match_naive_cuda(g0, t)
+    ts = []
+    for k in range(n):
+        g = gray(frames[(k + 1) % len(frames)])
+        t0 = time.perf_counter()
+        mp = pvt.ncc_match_naive_cuda(g, t)
+        ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    pvt.ncc_match_naive_cuda_batched([g0] * 4, t)
+    tb = (time.perf_counter() - t0) / 4
+    return {"what": "pvt_ncc_match(naive): 1920x1080 f32 frame + 64x64 template in pageable host memory -> 1857x1017 map in host memory, synchronous",
+            "ms_per_call": 1e3 * float(np.median(ts)), "maps_per_s": 1.0 / float(np.median(ts)), "batched_ms_per_frame": 1e3 * tb,
+            "bytes_h2d": int(g0.nbytes), "bytes_d2h": int(mp.nbytes), "macs": float(mp.size * 4096),
+            "reference_cpu_ms": None}
+
+
 def whole_frame_leg(pvt, torch, m, steps=40):
     """the lost-object mode's whole-frame search (tracker_ghc/src/main.cpp:186-193), one 1080p stream,
     64x64 template, the track held in the lost state (acceptance threshold 2.0 is never met), so every step computes the
@@ -431,7 +572,7 @@ def whole_frame_leg(pvt, torch, m, steps=40):
     bound for the search kernel: ingest, statistics and update are inside)."""
     wl = dict(WORKLOADS["C2"])
     W, H, tw, th, L = wl["W"], wl["H"], wl["tw"], wl["th"], wl["ring"]
-    scenes, host, dev = build_rings(wl, 0, torch)
+    scenes, host, dev = build_rings(wl, 0, torch, want_host=False)
     info = pvt.device_info(torch.cuda.current_device())
     ring = ring_descs(pvt, wl, dev, True)
     res = {}
@@ -512,8 +653,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "tracked_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
            "warmup": Wm, "ms_per_step": 1e3 * wl["streams"] / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {wl['desc']}", "frame": [wl["W"], wl["H"]], "template": [wl["tw"], wl["th"]],
-                      "radius": wl["R"], "searches_per_step": scale, "world_size_ignored": world},
+           "config": config_of(args.workload, wl),
+           "run": {"searches_per_step": scale, "world_size_ignored": world},
            "cpu_baseline": dict(cb, value=fps),
            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

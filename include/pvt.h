@@ -43,7 +43,7 @@ extern "C" {
 #define PVT_API
 #endif
 
-#define PVT_VERSION 102
+#define PVT_VERSION 200
 
 /* return codes */
 #define PVT_OK               0
@@ -66,8 +66,7 @@ typedef enum pvt_mode {
 
 typedef enum pvt_kernel {
     PVT_KERNEL_AUTO = 0,   /* production kernel (TMA-staged tile, register-blocked FP32) */
-    PVT_KERNEL_DIRECT = 1, /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
-    PVT_KERNEL_TILED = 2
+    PVT_KERNEL_DIRECT = 1  /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
 } pvt_kernel;
 
 /* frame ingest (utils.hpp:5-14 toGrayF32).  FULL converts whole frames, as the reference does.  ROI converts only each
@@ -87,7 +86,10 @@ typedef enum pvt_ingest { PVT_INGEST_AUTO = 0, PVT_INGEST_FULL = 1, PVT_INGEST_R
 typedef enum pvt_formula { PVT_FORMULA_CCOEFF_NORMED = 0, PVT_FORMULA_EPS = 1 } pvt_formula;
 
 typedef enum pvt_format { PVT_FMT_BGR8 = 0, PVT_FMT_GRAY8 = 1, PVT_FMT_GRAYF32 = 2 } pvt_format;
-typedef enum pvt_memory { PVT_MEM_HOST = 0, PVT_MEM_DEVICE = 1 } pvt_memory;
+/* HOST: any host pointer; the library probes whether it is page-locked (one driver query per frame descriptor) and stages
+ * pageable buffers.  HOST_PINNED: the caller states the buffer is page-locked (pvt_alloc_pinned, cudaHostAlloc,
+ * cudaHostRegister) -- no query on the submission path; a buffer that is not ends in PVT_ERR_INVALID or a CUDA fault. */
+typedef enum pvt_memory { PVT_MEM_HOST = 0, PVT_MEM_DEVICE = 1, PVT_MEM_HOST_PINNED = 2 } pvt_memory;
 
 /* tracker/src/main.cpp:6-20 */
 typedef struct pvt_params {
@@ -179,7 +181,10 @@ PVT_API int pvt_alloc_pinned(void** out, size_t bytes);
 PVT_API int pvt_free_pinned(void* p);
 
 /* main.cpp:70-71: ingest `frame0` into its stream (NULL: keep the stream's current image) and cut the
- * template of `track` from it at (x, y, w, h).  Synchronous. */
+ * template of `track` from it at (x, y, w, h).  Synchronous.  frame0 == NULL needs the stream's plane to hold one complete
+ * frame: that is the case after a pvt_track_init with a frame and after steps of a context that ingests whole frames
+ * (PVT_INGEST_FULL, or AUTO with many tracks); a context on the ROI ingest only refreshes the search tiles of its
+ * tracks, so there a later pvt_track_init(frame0 = NULL) fails with PVT_ERR_STATE instead of cutting stale pixels. */
 PVT_API int pvt_track_init(pvt_ctx* ctx, int track, int stream, const pvt_frame* frame0, int x, int y, int w, int h);
 PVT_API int pvt_track_remove(pvt_ctx* ctx, int track);
 

@@ -132,13 +132,17 @@ def _bbox_outside(x, y, w, h, fw, fh):
 
 def track_clip_ghc(frames, roi, rx=GHC_SEARCH_RADIUS, ry=GHC_SEARCH_RADIUS, min_conf=NCC_MIN_CONFIDENCE,
                    global_conf=NCC_GLOBAL_CONFIDENCE, strong_conf=NCC_STRONG_CONFIDENCE, lr=TEMPLATE_UPDATE_LR,
-                   lost_threshold=LOST_FRAME_THRESHOLD):
+                   lost_threshold=LOST_FRAME_THRESHOLD, start_box=None, lost0=0, use_global0=False):
     """tracker_ghc/src/main.cpp:145-239 (mode "cpu") with cv2: full-frame matchTemplate, then either the local window
-    or the whole map.  records = [n-1, 10]: x y w h conf moved updated searched(1 local, 2 whole map) lost_count use_global."""
+    or the whole map.  records = [n-1, 10]: x y w h conf moved updated searched(1 local, 2 whole map) lost_count use_global.
+    start_box / lost0 / use_global0: resume from a checkpointed state (the loop's variables :143-144 and bbox after the
+    template has been cut from frames[0] at roi); the defaults are the reference's initial state."""
     x, y, w, h = roi
     g = to_gray_f32(frames[0])
     templ = g[y:y + h, x:x + w].copy()
-    lost, use_global, recs = 0, False, []
+    lost, use_global, recs = int(lost0), bool(use_global0), []
+    if start_box is not None:
+        x, y = int(start_box[0]), int(start_box[1])
     for k in range(1, len(frames)):
         g = to_gray_f32(frames[k])
         fh, fw = g.shape

@@ -11,7 +11,7 @@
 namespace pvt {
 
 // defined in section (5), used earlier
-__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red);
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th);
 __device__ void track_update(const Ctx& c, int track, unsigned long long step, bool stepped, float* s_t, double* red);
 
 // =============================================================================================
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     const int gpr = (x1 - x0 + 3) >> 2;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (c.stage && gid < 4) c.stage_hdr[track].win[gid] = win[gid];   // for k_prefetch_roi, which runs behind this kernel
+    if (c.stage && gid == 0) c.stage_hdr[track].cur_step = step;
     if (gid >= gpr * rows) return;
     const int r = gid / gpr, x = x0 + ((gid - r * gpr) << 2), y = win[1] + r;
     float* out = c.gray + (size_t)t.stream * c.plane + (size_t)y * c.pitch + x;
@@ -164,17 +165,25 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
 // before -- the staging is an accelerator, never a correctness dependency).  ~1.9x the tile's bytes cross PCIe, but
 // beside the step instead of in front of its search.  Runs on a parallel graph branch that joins at the end of the step;
 // it works from the window k_ingest_roi recorded, not from the box, which the step's update moves.
-__global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c)
+__global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c, int debug_delay_ns)
 {
     const SeqDesc q = *c.seq;
     if (!q.prefetch) return;
+    if (debug_delay_ns > 0) {   // test hook (PVT_DEBUG_PREFETCH_DELAY_US): start late, as if the SMs had been busy
+        const unsigned long long t0 = gtime();
+        while (gtime() - t0 < (unsigned long long)debug_delay_ns) { }
+    }
     const int track = blockIdx.y;
     const TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
     if (!t.active) return;
-    const size_t nrow = (size_t)(q.row0 + (int)((step + 1ull - q.step0) % (unsigned long long)q.ring_len)) * c.max_streams;
-    const FrameDesc d = c.table[nrow + t.stream];
     StageHdr* hdr = c.stage_hdr + track;
+    // The step this branch belongs to comes from the header k_ingest_roi filled, NOT from *c.step: the branch only joins
+    // at the end of the step, after the update has advanced the counter, and a CTA that starts late would otherwise stage
+    // frame step+2 under the tag of step+1.
+    const unsigned long long step = hdr->cur_step;
+    if (step == ~0ull) return;                           // no ingest has run for this track in this sequence yet
+    const size_t nrow = (size_t)(q.row0 + (int)((step + 1ull - q.step0 + (unsigned long long)q.phase) % (unsigned long long)q.ring_len)) * c.max_streams;
+    const FrameDesc d = c.table[nrow + t.stream];
     if (!d.valid) {
         if (blockIdx.x == 0 && threadIdx.x == 0) hdr->step = ~0ull;
         return;
@@ -581,7 +590,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
     }
     const int ww = win[2], wh = win[3];
-    const int th = t.h, nchunk = t.tp >> 3;
+    const int th = t.h, nchunk = t.tp >> 3, tstream = t.stream;   // read BEFORE griddepcontrol.wait (a memory clobber)
     // A TMA tile must start on a 16-byte boundary in x (an unaligned innermost start coordinate raises "illegal
     // instruction" on sm_100a: tools/tma_align_probe.cu), but the window origin is arbitrary.  The tile is therefore
     // fetched from the origin rounded DOWN to 4 pixels and, when xs = origin & 3 is not 0, every row is shifted left by
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         // the tile is fetched.  (Unsplit shape: launched behind k_rowsum, whose output only the epilogue needs: see below.)
         if (split) pdl_wait();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
-        tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, t.stream);
+        tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, tstream);
         for (int s = 0; s < 2 && s < nj; ++s) {
             mbar_arrive_expect_tx(&full[s], slice_bytes);
             bulk_load(s_templ + (size_t)s * sstride, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
@@ -1164,7 +1173,7 @@ __global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream
         t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
     }
     __syncthreads();
-    finish_template(c, track, t, sm_f, red);
+    finish_template(c, track, t, sm_f, red, w, h);
 }
 
 // re-derive statistics after pvt_set_state wrote bbox/template from the host
@@ -1174,9 +1183,10 @@ __global__ void __launch_bounds__(256) k_track_refresh(Ctx c, int track)
     __shared__ double red[64];
     TrackState& t = c.tracks[track];
     const float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
-    for (int i = threadIdx.x; i < t.w * t.h; i += blockDim.x) sm_f[i] = tp_[i];
+    const int w = t.w, h = t.h;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) sm_f[i] = tp_[i];
     __syncthreads();
-    finish_template(c, track, t, sm_f, red);
+    finish_template(c, track, t, sm_f, red, w, h);
 }
 
 // =============================================================================================
@@ -1206,9 +1216,10 @@ __device__ void block_sum2(double& s, double& q, double* red /* 2 * 32 doubles *
 }
 
 // statistics + centred chunk-major template from the template held in shared memory (s_t, th*tw floats)
-__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red)
+// (tw, th) = (t.w, t.h), passed in registers: callers sit behind a barrier, where re-reading them costs an L2 round trip
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th)
 {
-    const int tw = t.w, th = t.h, n = tw * th, tid = threadIdx.x;
+    const int n = tw * th, tid = threadIdx.x;
     double s = 0.0, q = 0.0;
     for (int i = tid; i < n; i += blockDim.x) {
         const double v = (double)s_t[i];
@@ -1261,18 +1272,20 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         const unsigned long long key = *((volatile unsigned long long*)&t.peak);
         const float val = unord_f32((unsigned int)(key >> 32));
         const unsigned int idx = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
-        const int ww = t.win[2];
+        // every field of the track this function needs, read in ONE batch with the peak (nothing below re-reads t.* behind a
+        // barrier: each such read is a dependent L2 round trip on the step's critical path)
+        const int ww = t.win[2], wh = t.win[3], tw = t.w, th = t.h, tstream = t.stream, ox = t.x, oy = t.y;
         const int bx = t.win[0] + (int)(idx % (unsigned int)ww), by = t.win[1] + (int)(idx / (unsigned int)ww);
         const double best = (double)val;
         const bool moved = best >= P.min_conf;
         const bool updated = moved && best >= P.strong_conf;
-        const int nx = moved ? bx : t.x, ny = moved ? by : t.y;
+        const int nx = moved ? bx : ox, ny = moved ? by : oy;
         __syncthreads();  // everyone has read t.peak / t.x / t.y
         if (updated) {
-            const int tw = t.w, n = tw * t.h;
+            const int n = tw * th;
             const double alpha = 1.0 - P.lr, beta = P.lr;
             float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
-            const float* g = c.gray + (size_t)t.stream * c.plane + (size_t)ny * c.pitch + nx;
+            const float* g = c.gray + (size_t)tstream * c.plane + (size_t)ny * c.pitch + nx;
             // one batch of 32 loads per thread covers a 64 x 64 template with 256 threads: one L2 round trip, then the EMA.
             // (row, column) of pixel i advance incrementally: no division per element
             const int stride = blockDim.x, dq = stride / tw, dr = stride - dq * tw;
@@ -1299,7 +1312,7 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
                 }
             }
             __syncthreads();
-            finish_template(c, track, t, s_t, red);
+            finish_template(c, track, t, s_t, red, tw, th);
         }
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
@@ -1312,9 +1325,9 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
                 else t.lost_count += 1;
                 if (!t.use_global && t.lost_count >= P.lost_threshold) { t.use_global = 1; t.global_since = step + 1ull; }
             }
-            atomicAdd(c.macs, (unsigned long long)t.win[2] * t.win[3] * t.w * t.h);
-            atomicAdd(c.macs_grid, (unsigned long long)min(t.win[2], c.gridW) * min(t.win[3], c.gridH) * t.w * t.h);
-            res->x = nx; res->y = ny; res->w = t.w; res->h = t.h;
+            atomicAdd(c.macs, (unsigned long long)ww * wh * tw * th);
+            atomicAdd(c.macs_grid, (unsigned long long)min(ww, c.gridW) * min(wh, c.gridH) * tw * th);
+            res->x = nx; res->y = ny; res->w = tw; res->h = th;
             res->conf = val; res->moved = moved; res->updated = updated; res->searched = c.global_pass ? 2 : 1; res->valid = 1;
             res->track = track; res->step = (int32_t)step;
         }
@@ -1375,6 +1388,15 @@ __global__ void k_global_mark(Ctx c, cudaGraphConditionalHandle cond, int use_co
 __global__ void k_step_advance(Ctx c)
 {
     if (threadIdx.x == 0) { *c.ticket = 0u; *c.step = *c.step + 1ull; }
+}
+
+// Start of a frame sequence (pvt_submit_sequence) or return to per-step submission: set the sequence descriptor, passed
+// by value, and (invalidate) forget what k_prefetch_roi staged before -- the caller may have refilled its buffers.
+__global__ void k_seq_begin(Ctx c, SeqDesc q, int invalidate)
+{
+    if (threadIdx.x == 0) *c.seq = q;
+    if (invalidate && c.stage_hdr)
+        for (int t = threadIdx.x; t < c.max_tracks; t += blockDim.x) { c.stage_hdr[t].step = ~0ull; c.stage_hdr[t].cur_step = ~0ull; }
 }
 
 // hold step (batch mode, main.cpp:118-123): no NCC, no update; emit the stale box and advance

@@ -118,6 +118,14 @@ struct pvt_ctx {
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     pvt_result* h_results = nullptr;  // pinned, [kRing][max_tracks]
     std::vector<int> track_stream;    // host mirror: -1 = inactive
+    std::vector<char> plane_full;     // per stream: the gray plane holds ONE complete frame (false once a ROI-ingest step refreshed only tiles)
+    int prefetch_delay_ns = 0;        // test hook PVT_DEBUG_PREFETCH_DELAY_US: k_prefetch_roi starts late
+    // pvt_submit_sequence: what the device-side frame table / SeqDesc currently hold, so that an unchanged ring costs no upload
+    std::vector<FrameDesc> seq_rows;  // the rows uploaded by the last resident sequence ([ring_len][max_streams])
+    int seq_ring_len = 0;
+    bool seq_rows_valid = false;      // d.table rows [0, seq_ring_len) == seq_rows (any per-step submit invalidates it)
+    std::vector<FrameDesc> seq_scratch;
+    bool host_ptr_is_dev = false;     // cudaDevAttrCanUseHostPointerForRegisteredMem: a pinned host pointer is its own device alias
 };
 
 namespace {
@@ -279,6 +287,12 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f)
     return 4 + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
 
+// ... of the local pass under the context's kernel choice (k_ncc_direct: ingest, 2 statistics, search, update)
+int kernels_per_step(const pvt_ctx* c)
+{
+    return c->params.kernel == PVT_KERNEL_DIRECT ? 5 : pass_kernels(c->tile, c->fringe);
+}
+
 // item grid + tail splitting (see TileCfg)
 void plan_items(TileCfg& g, int max_tracks, int mtp, int sm_count)
 {
@@ -413,8 +427,8 @@ int upload_params(pvt_ctx* c)
 
 int upload_seq(pvt_ctx* c, unsigned long long step0, int ring_len, int row0, int prefetch = 0)
 {
-    SeqDesc q{step0, ring_len, row0, prefetch, 0};
-    CK(cudaMemcpyAsync(c->d.seq, &q, sizeof(q), cudaMemcpyHostToDevice, c->compute));  // pageable source: staged before return
+    k_seq_begin<<<1, 64, 0, c->compute>>>(c->d, SeqDesc{step0, ring_len, row0, prefetch, 0}, 0);
+    CK(cudaGetLastError());
     c->seq_default = (step0 == 0 && ring_len == kRing && row0 == 0 && !prefetch);
     return PVT_OK;
 }
@@ -425,7 +439,7 @@ int validate_params(const pvt_params* p)
     if (p->mode == PVT_MODE_CPU)
         return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path (the CPU oracle lives in oracle/, test-only)");
     if (p->mode < PVT_MODE_NAIVE || p->mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
-    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TILED) return fail(PVT_ERR_INVALID, "unknown kernel variant");
+    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_DIRECT) return fail(PVT_ERR_INVALID, "unknown kernel variant");
     if (p->ingest < PVT_INGEST_AUTO || p->ingest > PVT_INGEST_ROI) return fail(PVT_ERR_INVALID, "unknown ingest mode");
     if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
@@ -518,11 +532,11 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         if (capturing) {
             CK(cudaEventRecord(c->ev_fork, c->compute));
             CK(cudaStreamWaitEvent(c->aux3, c->ev_fork, 0));
-            k_prefetch_roi<<<pgrid, 256, 0, c->aux3>>>(d);
+            k_prefetch_roi<<<pgrid, 256, 0, c->aux3>>>(d, c->prefetch_delay_ns);
             CK(cudaEventRecord(c->ev_join3, c->aux3));
             join3 = true;
         } else {
-            k_prefetch_roi<<<pgrid, 256, 0, c->compute>>>(d);
+            k_prefetch_roi<<<pgrid, 256, 0, c->compute>>>(d, 0);
             { int r = dbg(c, "k_prefetch_roi"); if (r) return r; }
         }
     }
@@ -683,6 +697,7 @@ int build_graphs(pvt_ctx* c)
     }
     CK(cudaGraphInstantiate(&c->graph, g, 0));
     CK(cudaGraphDestroy(g));
+    CK(cudaGraphUpload(c->graph, c->compute));
     for (cudaGraphExec_t* ge : {&c->graph_multi, &c->graph_long, &c->graph_pf, &c->graph_multi_pf, &c->graph_long_pf})
         if (*ge) { cudaGraphExecDestroy(*ge); *ge = nullptr; }
     // every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
@@ -696,6 +711,7 @@ int build_graphs(pvt_ctx* c)
         CK(ee);
         CK(cudaGraphInstantiate(out, gs, 0));
         CK(cudaGraphDestroy(gs));
+        CK(cudaGraphUpload(*out, c->compute));   // the first launch must not pay the upload inside a caller's timed loop
         return PVT_OK;
     };
     const bool latency_shape = c->params.kernel != PVT_KERNEL_DIRECT && lp.tile.pj * lp.tile.pd > 1;
@@ -746,7 +762,7 @@ int check_frame(const pvt_ctx* c, const pvt_frame* f)
     if (!f->data) return fail(PVT_ERR_INVALID, "frame.data is NULL");
     if (f->stream < 0 || f->stream >= c->cfg.max_streams) return fail(PVT_ERR_INVALID, "frame.stream out of range");
     if (f->format < PVT_FMT_BGR8 || f->format > PVT_FMT_GRAYF32) return fail(PVT_ERR_INVALID, "unknown frame format");
-    if (f->memory != PVT_MEM_HOST && f->memory != PVT_MEM_DEVICE) return fail(PVT_ERR_INVALID, "unknown frame memory kind");
+    if (f->memory != PVT_MEM_HOST && f->memory != PVT_MEM_DEVICE && f->memory != PVT_MEM_HOST_PINNED) return fail(PVT_ERR_INVALID, "unknown frame memory kind");
     if (f->step < frame_row_bytes(c, f->format)) return fail(PVT_ERR_INVALID, "frame.step smaller than one row");
     if (f->format == PVT_FMT_GRAYF32 && (f->step % 4 || ((size_t)f->data) % 4)) return fail(PVT_ERR_INVALID, "f32 frame not 4-byte aligned");
     return PVT_OK;
@@ -759,6 +775,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
     const int ms = c->cfg.max_streams;
     if (!c->seq_default) { int r = upload_seq(c, 0, kRing, 0); if (r) return r; }
     FrameDesc* row = c->h_table + (size_t)slot * ms;
+    c->seq_rows_valid = false;   // this step's row overwrites part of what a resident sequence uploaded
     if (c->table_ev_used[slot]) CK(cudaEventSynchronize(c->table_ev[slot]));  // previous upload of this pinned row is done
     for (int s = 0; s < ms; ++s) row[s] = FrameDesc{nullptr, 0, 0, 0};
     const int sd = (int)(c->submitted % kStageDepth);
@@ -771,7 +788,8 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
             FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
             bool zero_copy = false;
-            if (f->memory == PVT_MEM_HOST && c->roi_ingest) {
+            const bool host = f->memory != PVT_MEM_DEVICE;
+            if (host && c->roi_ingest) {
                 // pinned (cudaHostAlloc / cudaHostRegister) memory is readable from the device under UVA: let k_ingest_roi
                 // pull just the search tiles over PCIe; pageable memory falls back to the staged full-frame copy
                 cudaPointerAttributes pa{};
@@ -782,7 +800,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
                     cudaGetLastError();
                 }
             }
-            if (f->memory == PVT_MEM_HOST && !zero_copy) {
+            if (host && !zero_copy) {
                 void*& st = c->stage[(size_t)f->stream * kStageDepth + sd];
                 if (!st) {
                     CK(cudaMalloc(&st, c->stage_bytes));
@@ -796,6 +814,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
                 fd.step = rb;
             }
             row[f->stream] = fd;
+            c->plane_full[f->stream] = !c->roi_ingest;   // the ROI ingest refreshes the tracks' search tiles only
             c->prof.ingest_bytes += (c->profiling && !c->roi_ingest) ? (double)c->cfg.frame_w * c->cfg.frame_h * ((f->format == PVT_FMT_BGR8 ? 3 : f->format == PVT_FMT_GRAY8 ? 1 : 4) + 4) : 0.0;
         }
     }
@@ -1134,6 +1153,13 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     c->stage.assign((size_t)d.max_streams * kStageDepth, nullptr);
     c->stage_bytes = (size_t)d.W * d.H * 4;
     c->track_stream.assign(d.max_tracks, -1);
+    c->plane_full.assign(d.max_streams, 0);
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrCanUseHostPointerForRegisteredMem, cfg->device) == cudaSuccess) c->host_ptr_is_dev = v != 0;
+        else cudaGetLastError();
+        if (const char* e = getenv("PVT_DEBUG_PREFETCH_DELAY_US")) c->prefetch_delay_ns = std::max(0, atoi(e)) * 1000;
+    }
 
     {
         Pass lp;
@@ -1143,7 +1169,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
         c->roi_ingest = lp.roi_ingest;
     }
-    c->kps = pass_kernels(c->tile, c->fringe);
+    c->kps = kernels_per_step(c);
     if (c->roi_ingest && !c->lost_mode && d.max_tracks <= 8) {
         // staging buffers of k_prefetch_roi: the search tile grown by the search radius on every side
         d.stage_w = (d.Wmax + c->cfg.max_radius_x + d.mtw + 8 + 3) & ~3;
@@ -1186,7 +1212,9 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
         const double tiles = (double)d.max_tracks * (d.Wmax + d.mtw) * (d.Hmax + d.mth), frames_px = (double)d.max_streams * d.W * d.H;
         c->roi_ingest = p->ingest == PVT_INGEST_ROI || (p->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
     }
+    if (p->mode != c->params.mode || p->batch_size != c->params.batch_size) c->hold_pending = 0;   // a new cadence starts from a full batch
     c->params = *p;
+    c->kps = kernels_per_step(c);
     if (regraph) c->graph_valid = false;
     return upload_params(c);
 }
@@ -1213,15 +1241,20 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
     const int slot = (int)(c->submitted % kRing);
     std::vector<FrameDesc> row(d.max_streams, FrameDesc{nullptr, 0, 0, 0});
     FrameDesc fd{f->data, (unsigned long long)f->step, f->format, 1};
-    void* tmp = nullptr;
-    if (f->memory == PVT_MEM_HOST) {
+    c->seq_rows_valid = false;
+    if (f->memory != PVT_MEM_DEVICE) {
         const size_t rb = frame_row_bytes(c, f->format);
-        CK(cudaMalloc(&tmp, rb * d.H));
+        // the context's own staging slot of this stream (allocated once; nothing is in flight after the pvt_sync above) --
+        // the reference mallocs and frees per call (baseline_kernel.cu:340-358), this path does not
+        void*& st = c->stage[(size_t)f->stream * kStageDepth];
+        if (!st) {
+            CK(cudaMalloc(&st, c->stage_bytes));
+            c->allocs.push_back(st);
+        }
         // stream-ordered on the compute stream: a synchronous cudaMemcpy from pageable memory may return
         // while its DMA is still in flight, and the non-blocking compute stream would not wait for it
-        cudaError_t e = cudaMemcpy2DAsync(tmp, rb, f->data, f->step, rb, d.H, cudaMemcpyHostToDevice, c->compute);
-        if (e != cudaSuccess) { cudaFree(tmp); return fail(PVT_ERR_CUDA, std::string("cudaMemcpy2D: ") + cudaGetErrorString(e)); }
-        fd.data = tmp;
+        CK(cudaMemcpy2DAsync(st, rb, f->data, f->step, rb, d.H, cudaMemcpyHostToDevice, c->compute));
+        fd.data = st;
         fd.step = rb;
     }
     row[f->stream] = fd;
@@ -1235,8 +1268,8 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
     }
-    if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) return fail(PVT_ERR_CUDA, std::string("ingest: ") + cudaGetErrorString(e));
+    c->plane_full[f->stream] = 1;
     return PVT_OK;
 }
 
@@ -1254,6 +1287,11 @@ int pvt_track_init(pvt_ctx* c, int track, int stream, const pvt_frame* frame0, i
         int r = ingest_now(c, frame0);
         if (r) return r;
     } else {
+        // utils.hpp:5-14 / main.cpp:70-71 cut the template from a COMPLETELY converted frame.  A context on the ROI ingest
+        // only refreshes its tracks' search tiles, so after its first step the plane is a patchwork of frames.
+        if (!c->plane_full[stream])
+            return fail(PVT_ERR_STATE, "pvt_track_init(frame0 = NULL): this stream's plane holds no complete frame (the context uses the "
+                                       "ROI ingest, which refreshes search tiles only); pass the frame, or create the context with PVT_INGEST_FULL");
         int r = pvt_sync(c);
         if (r) return r;
     }
@@ -1284,12 +1322,15 @@ int pvt_submit(pvt_ctx* c, int n_frames, const pvt_frame* frames)
     if (n_frames < 0 || (n_frames > 0 && !frames)) return fail(PVT_ERR_INVALID, "frames is NULL");
     CK(cudaSetDevice(c->cfg.device));
     bool hold = false;
+    const int hold_before = c->hold_pending;
     if (c->params.mode == PVT_MODE_BATCH && c->params.batch_size > 1) {
         // main.cpp:115-130: frames are collected until the batch is full; only then is one searched
         if (++c->hold_pending < c->params.batch_size) hold = true;
         else c->hold_pending = 0;
     }
-    return enqueue_step(c, n_frames, frames, hold);
+    const int r = enqueue_step(c, n_frames, frames, hold);
+    if (r) c->hold_pending = hold_before;   // a rejected call (bad frame, ...) does not shift the --batch=N cadence
+    return r;
 }
 
 int pvt_collect(pvt_ctx* c, pvt_result* results, int max_steps)
@@ -1320,42 +1361,75 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
     // over PCIe (zero-copy: each step's tiles cross the bus inside k_ingest_roi) -- and the ring fits the table -> upload
     // the ring's rows and a SeqDesc ONCE; after that a time step is a bare graph launch (no host-side bookkeeping per frame).
     bool resident = ring_len <= kRing && !c->profiling && !debug_sync() && n_steps > 0;
-    std::vector<const void*> dptr((size_t)std::max(ring_len * n_frames, 0), nullptr);
+    const int ms = c->cfg.max_streams;
+    // The ring's rows as the device will see them, built in a scratch vector the context keeps (no allocation per call).
+    // Pointer kinds: DEVICE as is; HOST_PINNED is the caller's promise that the buffer is page-locked -- under unified
+    // addressing its device alias is the pointer itself, no driver query; plain HOST is probed (cudaPointerGetAttributes).
+    std::vector<FrameDesc>& rows = c->seq_scratch;
     bool any_host = false;
-    for (int i = 0; resident && i < ring_len * n_frames; ++i) {
-        if (frames[i].memory == PVT_MEM_DEVICE) { dptr[i] = frames[i].data; continue; }
-        any_host = true;
-        cudaPointerAttributes pa{};
-        if (c->roi_ingest && frames[i].data && cudaPointerGetAttributes(&pa, frames[i].data) == cudaSuccess &&
-            pa.type == cudaMemoryTypeHost && pa.devicePointer) dptr[i] = pa.devicePointer;
-        else { cudaGetLastError(); resident = false; }
-    }
     if (resident) {
-        CK(cudaSetDevice(c->cfg.device));
-        const int ms = c->cfg.max_streams;
-        for (int k = 0; k < kRing; ++k)
-            if (c->table_ev_used[k]) { CK(cudaEventSynchronize(c->table_ev[k])); c->table_ev_used[k] = false; }
-        for (int k = 0; k < ring_len; ++k) {
-            FrameDesc* row = c->h_table + (size_t)k * ms;
-            for (int s = 0; s < ms; ++s) row[s] = FrameDesc{nullptr, 0, 0, 0};
+        rows.assign((size_t)ring_len * ms, FrameDesc{nullptr, 0, 0, 0});
+        for (int k = 0; resident && k < ring_len; ++k)
             for (int i = 0; i < n_frames; ++i) {
                 const pvt_frame* f = frames + (size_t)k * n_frames + i;
                 int r = check_frame(c, f);
                 if (r) return r;
-                if (row[f->stream].valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
-                row[f->stream] = FrameDesc{dptr[(size_t)k * n_frames + i], (unsigned long long)f->step, f->format, 1};
+                FrameDesc& slot = rows[(size_t)k * ms + f->stream];
+                if (slot.valid) return fail(PVT_ERR_INVALID, "two frames for one stream in one step");
+                const void* dp = f->data;
+                if (f->memory != PVT_MEM_DEVICE) {
+                    any_host = true;
+                    if (!c->roi_ingest) { resident = false; break; }
+                    if (!(f->memory == PVT_MEM_HOST_PINNED && c->host_ptr_is_dev)) {
+                        cudaPointerAttributes pa{};
+                        if (cudaPointerGetAttributes(&pa, f->data) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) dp = pa.devicePointer;
+                        else {
+                            cudaGetLastError();
+                            if (f->memory == PVT_MEM_HOST_PINNED) return fail(PVT_ERR_INVALID, "frame declared PVT_MEM_HOST_PINNED is not page-locked memory");
+                            resident = false;
+                            break;
+                        }
+                    }
+                }
+                slot = FrameDesc{dp, (unsigned long long)f->step, f->format, 1};
+                c->plane_full[f->stream] = !c->roi_ingest;
+            }
+    }
+    if (resident) {
+        CK(cudaSetDevice(c->cfg.device));
+        // Is this the ring the device table already holds, possibly rotated (callers walk a ring and pass it from its
+        // current position)?  Then nothing is uploaded: the rotation goes into SeqDesc.phase.
+        int phase = -1;
+        const size_t row_bytes = sizeof(FrameDesc) * (size_t)ms;
+        if (c->seq_rows_valid && c->seq_ring_len == ring_len) {
+            for (int r0 = 0; r0 < ring_len && phase < 0; ++r0) {
+                if (std::memcmp(rows.data(), c->seq_rows.data() + (size_t)r0 * ms, row_bytes) != 0) continue;
+                bool same = true;
+                for (int k = 1; k < ring_len && same; ++k)
+                    same = std::memcmp(rows.data() + (size_t)k * ms, c->seq_rows.data() + (size_t)((k + r0) % ring_len) * ms, row_bytes) == 0;
+                if (same) phase = r0;
             }
         }
         Readback pend[2] = {};
         bool had_prev = false;
-        CK(cudaMemcpyAsync(c->d.table, c->h_table, sizeof(FrameDesc) * (size_t)ring_len * ms, cudaMemcpyHostToDevice, c->compute));
-        CK(cudaEventRecord(c->table_ev[0], c->compute));
-        c->table_ev_used[0] = true;
+        if (phase < 0) {
+            for (int k = 0; k < kRing; ++k)   // earlier uploads from the pinned table must have left it
+                if (c->table_ev_used[k]) { CK(cudaEventSynchronize(c->table_ev[k])); c->table_ev_used[k] = false; }
+            std::memcpy(c->h_table, rows.data(), row_bytes * ring_len);
+            CK(cudaMemcpyAsync(c->d.table, c->h_table, row_bytes * ring_len, cudaMemcpyHostToDevice, c->compute));
+            CK(cudaEventRecord(c->table_ev[0], c->compute));
+            c->table_ev_used[0] = true;
+            c->seq_rows.swap(rows);
+            c->seq_ring_len = ring_len;
+            c->seq_rows_valid = true;
+            phase = 0;
+        }
         const bool pf = any_host && c->d.stage && !c->lost_mode;
-        // nothing staged by an earlier sequence may be taken for this one (the caller may have refilled the buffers)
-        if (pf) CK(cudaMemsetAsync(c->d.stage_hdr, 0xFF, sizeof(StageHdr) * (size_t)c->cfg.max_tracks, c->compute));
-        int r = upload_seq(c, c->submitted, ring_len, 0, pf ? 1 : 0);
-        if (r) return r;
+        // one tiny kernel sets the sequence descriptor (passed by value: no staging copy, no pinned buffer to guard) and, for
+        // pinned rings, drops whatever an earlier sequence staged (the caller may have refilled the buffers since)
+        k_seq_begin<<<1, 64, 0, c->compute>>>(c->d, SeqDesc{c->submitted, ring_len, 0, pf ? 1 : 0, phase}, pf ? 1 : 0);
+        c->seq_default = false;
+        int r = PVT_OK;
         if (!c->graph_valid) { r = build_graphs(c); if (r) return r; }
         cudaGraphExec_t g_one = pf ? c->graph_pf : c->graph, g_multi = pf ? c->graph_multi_pf : c->graph_multi;
         cudaGraphExec_t g_long = pf ? c->graph_long_pf : c->graph_long;
@@ -1389,10 +1463,12 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
                 if (lag && pend[b ^ 1].n) { int r2 = finish_readback(c, pend[b ^ 1], results_out, mt); if (r2) return r2; }
                 CK(cudaEventRecord(c->rb_ready[b], c->compute));
                 CK(cudaStreamWaitEvent(c->copy, c->rb_ready[b], 0));
-                for (int k = 0; k < collect_every; ++k) {
-                    const int slot = (int)((first + k) % kRing);
-                    CK(cudaMemcpyAsync(c->h_results + (size_t)slot * mt, c->d.results + (size_t)slot * mt, sizeof(pvt_result) * mt,
+                {   // the batch's slots are contiguous in the results ring up to one wrap-around: at most two copies
+                    const int s0 = (int)(first % kRing), n0 = std::min(collect_every, kRing - s0);
+                    CK(cudaMemcpyAsync(c->h_results + (size_t)s0 * mt, c->d.results + (size_t)s0 * mt, sizeof(pvt_result) * mt * n0,
                                        cudaMemcpyDeviceToHost, c->copy));
+                    if (n0 < collect_every)
+                        CK(cudaMemcpyAsync(c->h_results, c->d.results, sizeof(pvt_result) * mt * (collect_every - n0), cudaMemcpyDeviceToHost, c->copy));
                 }
                 CK(cudaEventRecord(c->rb_done[b], c->copy));
                 // the steps that overwrite result slots (64 steps after the ones that filled them) must not start before the
@@ -1577,6 +1653,8 @@ int map_ctx(int device, int formula, int fw, int fh, int tw, int th, pvt_ctx** o
     p.search_radius_y = fh;
     p.keep_maps = 1;
     p.formula = formula;
+    p.ncc_min_confidence = 2.0;      // a map operator has no tracker state: no score reaches 2, so the box never moves and the
+    p.ncc_strong_confidence = 2.0;   // template is never blended -- one state upload serves every frame of a batch
     pvt_config cfg{};
     cfg.device = device; cfg.frame_w = fw; cfg.frame_h = fh; cfg.max_streams = 1; cfg.max_tracks = 1;
     cfg.max_templ_w = tw; cfg.max_templ_h = th;
@@ -1603,20 +1681,21 @@ int pvt_ncc_match_batched_f(int device, int formula, int n, const float* const* 
     pvt_ctx* c = nullptr;
     int r = map_ctx(device, formula, fw, fh, tw, th, &c);
     if (r) return r;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i)
         if (!frames[i] || !outs[i]) return fail(PVT_ERR_INVALID, "NULL frame / output in batch");
+    // every map is taken against the SAME template (baseline_kernel.cu:462-466), and the map context never moves its box
+    // or blends its template (map_ctx), so the state goes up once; per frame: staged H2D, one graph launch, one D2H of the map
+    const int32_t bbox[4] = {0, 0, tw, th};
+    c->track_stream[0] = 0;
+    r = pvt_set_state(c, 0, bbox, templ, tstep_bytes);
+    if (r) return r;
+    for (int i = 0; i < n; ++i) {
         pvt_frame f{0, PVT_FMT_GRAYF32, PVT_MEM_HOST, 0, frames[i], fstep_bytes};
-        const int32_t bbox[4] = {0, 0, tw, th};
-        // every map is taken against the SAME template (baseline_kernel.cu:462-466): reset state per frame
-        if (i == 0) c->track_stream[0] = 0;
-        r = pvt_set_state(c, 0, bbox, templ, tstep_bytes);
+        r = pvt_submit(c, 1, &f);
         if (r) return r;
-        r = pvt_step(c, 1, &f, nullptr);
-        if (r) return r;
-        int32_t win[4];
-        r = pvt_get_window_map(c, 0, outs[i], ostep_bytes, win);
-        if (r) return r;
-        if (win[2] != outW || win[3] != outH) return fail(PVT_ERR_STATE, "internal: window is not the full map");
+        // stream-ordered behind the step on the compute stream; the map of a 1-track context starts at c->d.maps
+        CK(cudaMemcpy2DAsync(outs[i], ostep_bytes, c->d.maps, (size_t)outW * 4, (size_t)outW * 4, outH, cudaMemcpyDeviceToHost, c->compute));
+        CK(cudaStreamSynchronize(c->compute));   // pageable destination: the copy has landed when this returns
     }
     return PVT_OK;
 }

@@ -31,14 +31,14 @@ struct FrameDesc {
     int valid;
 };
 
-// which frame-table row a time step reads: row0 + (step - step0) % ring_len.  Default {0, kRing, 0} = step % kRing
+// which frame-table row a time step reads: row0 + (phase + step - step0) % ring_len.  Default {0, kRing, 0, 0, 0} = step % kRing
 // (one row uploaded per step); a resident frame ring uploads its rows once and every later step needs no H2D at all.
 struct SeqDesc {
     unsigned long long step0;
     int ring_len, row0;
     int prefetch;              // != 0: the ring's frames are pinned host memory -> k_prefetch_roi stages the next step's pixels
-    int pad;
-};
+    int phase;                 // ring position of step0: row = row0 + (phase + step - step0) % ring_len (a caller that passes the
+};                             // same ring from a later position re-uses the uploaded rows)
 
 // What k_prefetch_roi staged for a track: gray f32 pixels of region [x0, x1) x [y0, y1) of the frame `data`, valid for `step`
 struct StageHdr {
@@ -46,8 +46,9 @@ struct StageHdr {
     unsigned long long step;
     const void* data;
     int win[4];                // the track's search window at the START of the current step (stored by k_ingest_roi): what
-    int pad[2];                // k_prefetch_roi grows -- it must not read the box itself, which the step's update moves
-};
+                               // k_prefetch_roi grows -- it must not read the box itself, which the step's update moves
+    unsigned long long cur_step;   // ... and the step it belongs to: k_prefetch_roi must not read *Ctx.step either (the update
+};                                 // advances it while the low-priority prefetch branch may still be waiting for an SM)
 
 struct TrackState {
     int active, stream;
@@ -121,7 +122,7 @@ __host__ __device__ inline void search_window(int x, int y, int w, int h, int ou
 __device__ __forceinline__ size_t table_row(const Ctx& c, unsigned long long step)
 {
     const SeqDesc q = *c.seq;
-    return (size_t)(q.row0 + (int)((step - q.step0) % (unsigned long long)q.ring_len)) * c.max_streams;
+    return (size_t)(q.row0 + (int)((step - q.step0 + (unsigned long long)q.phase) % (unsigned long long)q.ring_len)) * c.max_streams;
 }
 // whole-frame (global) search applies to this track at this step (decided by the previous step's update)
 __device__ __forceinline__ bool track_global(const TrackState& t, unsigned long long step)

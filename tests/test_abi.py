@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = pvt.lib()
     for s in _declared_symbols():
         assert hasattr(L, s), f"libpvt.so does not export {s}"
-    assert L.pvt_version() == 102
+    assert L.pvt_version() == 200
 
 
 def test_default_params_are_the_reference_constants():

@@ -567,3 +567,70 @@ def test_random_geometries_vs_oracle(seed):
                 assert abs(float(res[t]["conf"]) - rec.conf) <= Hp.TOL_SCORE
                 _, got_t = tr.get_state(t)
                 assert np.array_equal(got_t, templ), (seed, t)                                  # EMA bit-exact given the same peak
+
+
+# ---- round-2 regressions ------------------------------------------------------------------------------------
+def test_prefetch_branch_that_starts_late_still_stages_the_right_frame(monkeypatch):
+    """k_prefetch_roi runs on a low-priority branch that joins at the END of the step, i.e. after the update has advanced the
+    device step counter.  It must take its step from what k_ingest_roi recorded, not from the counter: a CTA that starts late
+    (here: forced by a 60 us spin, longer than a whole step) would otherwise stage frame k+2 under the tag of frame k+1."""
+    torch = pytest.importorskip("torch")
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    want = run_clip(frames, roi)[0]
+    n, H, W, _ = frames.shape
+    buf = torch.from_numpy(frames).pin_memory()
+    ring = [[pvt.Frame(0, pvt.FMT_BGR8, pvt.MEM_HOST_PINNED, 0, buf[k].data_ptr(), W * 3)] for k in range(1, n)]
+    monkeypatch.setenv("PVT_DEBUG_PREFETCH_DELAY_US", "60")
+    with pvt.Tracker(W, H, 32, 32, ingest=pvt.INGEST_ROI) as tr:
+        tr.init_track(0, frames[0], roi)
+        tr.submit_sequence(n - 1, ring)
+        got = tr.collect(n - 1)
+    assert np.array_equal(records_of(got[:, 0]), want)
+
+
+def test_track_init_from_current_image_needs_a_complete_plane():
+    """main.cpp:70-71 cuts the template from a fully converted frame.  On the ROI ingest only the search tiles are refreshed,
+    so pvt_track_init(frame0 = NULL) after a step must fail (PVT_ERR_STATE) instead of cutting stale pixels; on the full ingest
+    it keeps working and cuts from the CURRENT frame."""
+    (c, _) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    with pvt.Tracker(W, H, 32, 32, max_tracks=2, ingest=pvt.INGEST_ROI) as tr:
+        tr.init_track(0, frames[0], roi)
+        tr.init_track(1, None, (5, 5, 32, 32))            # right after a full ingest: fine
+        tr.step([frames[1]])
+        with pytest.raises(pvt.PvtError) as e:
+            tr.init_track(1, None, (200, 150, 32, 32))
+        assert e.value.code == pvt.ERR_STATE
+        tr.init_track(1, frames[1], (200, 150, 32, 32))   # with the frame: fine
+        _, t = tr.get_state(1)
+        assert np.array_equal(t, O.to_gray_f32(frames[1])[150:182, 200:232])
+    with pvt.Tracker(W, H, 32, 32, max_tracks=2, ingest=pvt.INGEST_FULL) as tr:
+        tr.init_track(0, frames[0], roi)
+        tr.step([frames[1]])
+        tr.init_track(1, None, (200, 150, 32, 32))
+        _, t = tr.get_state(1)
+        assert np.array_equal(t, O.to_gray_f32(frames[1])[150:182, 200:232])
+
+
+def test_rejected_submit_does_not_shift_the_batch_cadence():
+    (c, tk) = Hp.clip("batch4")
+    g = Hp.golden("clip_batch4.npz")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    with pvt.Tracker(W, H, 32, 32, mode=pvt.MODE_BATCH, batch_size=4) as tr:
+        tr.init_track(0, frames[0], roi)
+        out = []
+        for k in range(1, len(frames)):
+            if k in (2, 4, 7):                             # a bad call in every phase of the cadence
+                with pytest.raises(pvt.PvtError):
+                    tr.step([frames[k][:, : W - 1]])
+            out.append(tr.step([frames[k]])[0])
+        rec = records_of(np.array(out))
+        Hp.check_records(rec, g["records"], "batch4 with rejected submits")
+        # a new cadence (set_params) starts from an empty batch: the next three frames are held, the fourth searched
+        tr.set_params(batch_size=3)
+        tr.set_params(batch_size=4)
+        kinds = [int(tr.step([frames[1]])[0]["searched"]) for _ in range(4)]
+        assert kinds == [0, 0, 0, 1]
