@@ -60,58 +60,70 @@ __device__ __forceinline__ float4 ingest_group(const FrameDesc& d, const unsigne
     return o;
 }
 
-// Full-frame ingest.  HBM-bound: 3 B read + 4 B written per pixel.  A thread converts FOUR 4-pixel groups that are 256
-// groups apart (so every load / store instruction of a warp still touches one contiguous 384 B / 512 B span) and issues
-// all twelve 32-bit loads before converting: 48 B of loads in flight per thread, enough to cover HBM latency
-// (one group per thread sustained only 58 % of the measured copy bandwidth).
-constexpr int kIngestGroups = 4;
-__global__ void __launch_bounds__(256) k_ingest(Ctx c)
+// Full-frame ingest.  HBM-bound: 3 B read + 4 B written per pixel = 14.5 MB per 1080p frame.
+// Grid = (column blocks, rows, streams): no index division anywhere (round 1 spent more instructions on a 64-bit
+// gid / groups-per-row than on the conversion: ncu had the kernel issue-bound at 80 % of the slots, 78 % of the copy rate).
+// Fast path (BGR8, W % 16 == 0, 16-byte aligned rows -- every common video geometry): a thread converts 16 consecutive
+// pixels: three 16-byte loads (48 contiguous bytes), per pixel one PRMT (gather B, G, R into a word) + two DP2A
+// (3735 B + 19235 G + 16384, then + 9798 R: the 15-bit fixed point of cv::cvtColor, weights fit 16 bits) + shift + I2F +
+// FMUL, and two 32-byte stores (st.global.v8.f32: one full sector each).  Anything else takes the 4-pixel generic path.
+constexpr int kIngestThreads = 128;
+__device__ __forceinline__ float gray_px(unsigned int w /* bytes: B G R x */)
+{
+    unsigned int acc = __dp2a_lo((19235u << 16) | 3735u, w, 16384u);   // 3735 * B + 19235 * G + 16384
+    acc = __dp2a_hi(9798u, w, acc);                                     // + 9798 * R + 0 * x
+    return gray_to_f32(acc >> 15);
+}
+__device__ __forceinline__ void st_v8(float* p, const float (&v)[8])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__global__ void __launch_bounds__(kIngestThreads) k_ingest(Ctx c)
 {
     pdl_trigger();
     const unsigned long long step = *c.step;
-    const int stream = blockIdx.y;
+    const int stream = blockIdx.z, y = blockIdx.y;
     if (c.global_pass && !c.stream_need[stream]) return;   // whole-frame pass: only streams with a lost track
     const FrameDesc d = c.table[table_row(c, step) + stream];
     if (!d.valid) return;
     trace_begin(c, step, TR_INGEST);
-    const int gpr = (c.W + 3) >> 2;  // 4-pixel groups per row
-    const long long total = (long long)gpr * c.H;
-    const long long g0 = (long long)blockIdx.x * (256 * kIngestGroups) + threadIdx.x;
-    float* plane = c.gray + (size_t)stream * c.plane;
-    const bool fast = d.format == PVT_FMT_BGR8 && (c.W & 3) == 0 && ((((size_t)d.data) | d.step) & 3) == 0;
+    float* orow = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch;
+    const unsigned char* irow = (const unsigned char*)d.data + (size_t)y * d.step;
+    const bool fast = d.format == PVT_FMT_BGR8 && (c.W & 15) == 0 && ((((size_t)d.data) | d.step) & 15) == 0;
     if (fast) {
-        unsigned int a[kIngestGroups], b[kIngestGroups], e[kIngestGroups];
-        int xs[kIngestGroups], ys[kIngestGroups];
+        const int x = (blockIdx.x * kIngestThreads + threadIdx.x) * 16;
+        if (x < c.W) {
+            const uint4* p = reinterpret_cast<const uint4*>(irow + 3 * x);
+            const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+            const unsigned int w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            float o[16];
 #pragma unroll
-        for (int k = 0; k < kIngestGroups; ++k) {
-            const long long gid = g0 + k * 256;
-            const bool ok = gid < total;
-            ys[k] = ok ? (int)(gid / gpr) : -1;
-            xs[k] = ok ? ((int)(gid - (long long)ys[k] * gpr)) << 2 : 0;
-            if (ok) {
-                const unsigned int* p32 = (const unsigned int*)((const unsigned char*)d.data + (size_t)ys[k] * d.step + 3 * xs[k]);
-                a[k] = __ldg(p32); b[k] = __ldg(p32 + 1); e[k] = __ldg(p32 + 2);
+            for (int g = 0; g < 4; ++g) {   // 4 pixels = 3 words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                const unsigned int a = w[3 * g], b = w[3 * g + 1], e = w[3 * g + 2];
+                o[4 * g] = gray_px(a);                                   // bytes 0 1 2 of a
+                o[4 * g + 1] = gray_px(__byte_perm(a, b, 0x0543));       // a3 b0 b1
+                o[4 * g + 2] = gray_px(__byte_perm(b, e, 0x0432));       // b2 b3 e0
+                o[4 * g + 3] = gray_px(e >> 8);                          // e1 e2 e3
             }
-        }
+            if ((c.pitch & 7) == 0) {
+                st_v8(orow + x, *reinterpret_cast<const float(*)[8]>(o));
+                st_v8(orow + x + 8, *reinterpret_cast<const float(*)[8]>(o + 8));
+            } else {
 #pragma unroll
-        for (int k = 0; k < kIngestGroups; ++k) {
-            if (ys[k] >= 0) {
-                float4 o;  // bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
-                o.x = gray_to_f32(bgr_to_gray(a[k] & 255u, (a[k] >> 8) & 255u, (a[k] >> 16) & 255u));
-                o.y = gray_to_f32(bgr_to_gray(a[k] >> 24, b[k] & 255u, (b[k] >> 8) & 255u));
-                o.z = gray_to_f32(bgr_to_gray((b[k] >> 16) & 255u, b[k] >> 24, e[k] & 255u));
-                o.w = gray_to_f32(bgr_to_gray((e[k] >> 8) & 255u, (e[k] >> 16) & 255u, e[k] >> 24));
-                *reinterpret_cast<float4*>(plane + (size_t)ys[k] * c.pitch + xs[k]) = o;
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(orow + x + 4 * g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
             }
         }
     } else {
+        // generic: 4-pixel groups, 4 per thread (strided by the block so that a warp's accesses stay contiguous)
+        const int gpr = (c.W + 3) >> 2;
 #pragma unroll 1
-        for (int k = 0; k < kIngestGroups; ++k) {
-            const long long gid = g0 + k * 256;
-            if (gid >= total) break;
-            const int y = (int)(gid / gpr), x = ((int)(gid - (long long)y * gpr)) << 2;
-            const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
-            *reinterpret_cast<float4*>(plane + (size_t)y * c.pitch + x) = ingest_group(d, row, x, min(4, c.W - x));  // pitch % 4 == 0
+        for (int k = 0; k < 4; ++k) {
+            const int g = (blockIdx.x * 4 + k) * kIngestThreads + threadIdx.x;
+            if (g >= gpr) break;
+            const int x = g << 2;
+            *reinterpret_cast<float4*>(orow + x) = ingest_group(d, irow, x, min(4, c.W - x));  // pitch % 4 == 0
         }
     }
     trace_end(c, step, TR_INGEST);

@@ -506,6 +506,12 @@ int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaS
     return PVT_OK;
 }
 
+// k_ingest: (column blocks, rows, streams); a block covers 16 * 128 = 2048 pixels of a row on either path
+dim3 ingest_grid(const Ctx& d)
+{
+    return dim3((unsigned)((d.W + 16 * kIngestThreads - 1) / (16 * kIngestThreads)), (unsigned)d.H, (unsigned)d.max_streams);
+}
+
 // The kernels of one searched time step.  capturing: being recorded into a CUDA graph on c->compute (fork/join allowed).
 // profile (only while capturing): external event-record NODES around each kernel class, so the measured durations are
 // GPU-side and contain no host launch gaps.  Classes: ingest | statistics | search (k_ncc_search [+ tail reduction]) |
@@ -514,14 +520,12 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
 {
     const Ctx& d = p.d;
     profile = profile && capturing;
-    const int gpr = (d.W + 3) / 4;
-    const long long groups = (long long)gpr * d.H;
     if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
     if (p.roi_ingest) {
         const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
         k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
-        k_ingest<<<dim3((unsigned)((groups + 256 * kIngestGroups - 1) / (256 * kIngestGroups)), d.max_streams), 256, 0, c->compute>>>(d);
+        k_ingest<<<ingest_grid(d), kIngestThreads, 0, c->compute>>>(d);
     }
     if (profile) { int r = pnode(c, CLS_INGEST, 1, c->compute); if (r) return r; }
     { int r = dbg(c, "k_ingest"); if (r) return r; }
@@ -1049,6 +1053,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     if (cfg->max_templ_w <= 0 || cfg->max_templ_h <= 0 || cfg->max_templ_w > cfg->frame_w || cfg->max_templ_h > cfg->frame_h)
         return fail(PVT_ERR_INVALID, "template larger than the frame (ncc_cpu.cpp:9-10)");
     if (cfg->max_streams > 65535 || cfg->max_tracks > 65535) return fail(PVT_ERR_INVALID, "at most 65535 streams / tracks per context");
+    if (cfg->frame_h > 65535 || cfg->frame_w > (1 << 20)) return fail(PVT_ERR_INVALID, "frame larger than 1048576 x 65535");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -1261,9 +1266,7 @@ static int ingest_now(pvt_ctx* c, const pvt_frame* f)
     cudaError_t e = cudaMemcpyAsync(d.table + (size_t)slot * d.max_streams, row.data(), sizeof(FrameDesc) * d.max_streams,
                                     cudaMemcpyHostToDevice, c->compute);
     if (e == cudaSuccess) {
-        const int gpr = (d.W + 3) / 4;
-        const long long groups = (long long)gpr * d.H;
-        k_ingest<<<dim3((unsigned)((groups + 256 * kIngestGroups - 1) / (256 * kIngestGroups)), d.max_streams), 256, 0, c->compute>>>(d);
+        k_ingest<<<ingest_grid(d), kIngestThreads, 0, c->compute>>>(d);
         c->launches += 1;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
