@@ -92,7 +92,7 @@ def test_eps_formula_matches_the_reference_kernels(mode):
     seq = O.ncc_window_eps(f, t, 0, 0, ref.shape[1], ref.shape[0])
     _note(f"{mode}: |libpvt eps - reference kernel| max {np.abs(got - ref).max():.3e}; |oracle FP32-sequential restatement - reference kernel| max "
           f"{np.abs(seq - ref).max():.3e}; |float64 formula - reference kernel| max {np.abs(O.ncc_eps_exact(f, t, 0, 0, ref.shape[1], ref.shape[0]) - ref).max():.3e}")
-    assert np.abs(seq - ref).max() <= 5e-5, float(np.abs(seq - ref).max())
+    assert np.array_equal(seq, ref), float(np.abs(seq - ref).max())   # measured on B200: bit-identical
     # and the default formula is NOT what these kernels compute (flat template: OpenCV says 1 everywhere, the kernels ~0)
     flat = np.full((th, tw), 0.25, np.float32)
     rf = RG.ncc_match(mode, f, flat)
@@ -120,7 +120,20 @@ def test_eps_batched_and_1080p_against_the_reference():
     d = np.abs(got - ref)
     sig = Hp.window_sigma(g1, w, h, (0, 0, ref.shape[1], ref.shape[0]))
     _note(f"1080p const: |libpvt eps - reference kernel| max {d.max():.3e} (sigma_w >= 0.02: {d[sig >= 0.02].max():.3e})")
-    assert d[sig >= 0.02].max() <= Hp.TOL_SCORE and np.argmax(got) == np.argmax(ref), float(d.max())
+    # At N = 4096 pixels the reference kernel's own sequential FP32 sums (two passes, baseline_kernel.cu:34-60) sit up to ~2e-4
+    # from exact arithmetic (measured 2.15e-4 here; 2.2e-5 at N = 1280 above); libpvt's eps path stays within 2e-5 of the exact
+    # formula.  So at this size the gate between the two is the reference's noise, 5e-4, with identical peaks -- and the pin is the
+    # crop below, where the FP32-sequential restatement reproduces the reference kernel BIT FOR BIT.
+    assert d.max() <= 5e-4 and np.argmax(got) == np.argmax(ref), float(d.max())
+    crop = np.ascontiguousarray(g1[400:640, 800:1120])
+    rc = RG.ncc_match("naive", crop, t)
+    seq = O.ncc_window_eps(crop, t, 0, 0, rc.shape[1], rc.shape[0])
+    assert np.array_equal(seq, rc), float(np.abs(seq - rc).max())
+    gc = pvt.ncc_match_naive_cuda(crop, t, formula=pvt.FORMULA_EPS)
+    exact = O.ncc_eps_exact(crop, t, 0, 0, rc.shape[1], rc.shape[0])
+    _note(f"1080p crop 64x64: restatement == reference kernel bit-exact; |libpvt - float64 formula| max {np.abs(gc - exact).max():.3e}; "
+          f"|reference kernel - float64 formula| max {np.abs(rc - exact).max():.3e}")
+    assert np.abs(gc - exact).max() <= 2e-5 and np.argmax(gc) == np.argmax(rc)
     with pytest.raises(RuntimeError):                      # 72 x 72 > 4096 px: the reference asserts, libpvt does not
         RG.ncc_match("const", g1, g0[100:172, 100:172].copy())
     assert pvt.ncc_match_const(g1[:300, :300].copy(), g0[100:172, 100:172].copy(), formula=pvt.FORMULA_EPS).shape == (229, 229)
