@@ -66,7 +66,13 @@ typedef enum pvt_mode {
 
 typedef enum pvt_kernel {
     PVT_KERNEL_AUTO = 0,   /* production kernel (TMA-staged tile, register-blocked FP32) */
-    PVT_KERNEL_DIRECT = 1  /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
+    PVT_KERNEL_DIRECT = 1, /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
+    PVT_KERNEL_TC = 2      /* tensor-core search (tcgen05.mma kind::i8, exact integer cross term of the 16-bit fixed-point centred
+                            * template; scores within 1e-4 of the CPU path like the others, peaks identical).  For the throughput
+                            * shapes (many tracks / ROIs per GPU).  Must be chosen at pvt_create (it allocates an 8-bit gray plane);
+                            * needs 8-bit frames (BGR8 / GRAY8 -- a GRAYF32 frame is rejected), window width <= 256, template
+                            * height <= 129, window width + template width <= 306; the whole-frame pass of the lost-object mode
+                            * keeps the FP32 kernel. */
 } pvt_kernel;
 
 /* frame ingest (utils.hpp:5-14 toGrayF32).  FULL converts whole frames, as the reference does.  ROI converts only each

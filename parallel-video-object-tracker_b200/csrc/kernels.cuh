@@ -11,6 +11,7 @@
 namespace pvt {
 
 // defined in section (5), used earlier
+__device__ void write_digits(const Ctx& c, int track, TrackState& t, const float* s_t, double mean, int tw, int th);
 __device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th);
 __device__ void track_update(const Ctx& c, int track, unsigned long long step, bool stepped, float* s_t, double* red);
 
@@ -68,6 +69,13 @@ __device__ __forceinline__ float4 ingest_group(const FrameDesc& d, const unsigne
 // (3735 B + 19235 G + 16384, then + 9798 R: the 15-bit fixed point of cv::cvtColor, weights fit 16 bits) + shift + I2F +
 // FMUL, and two 32-byte stores (st.global.v8.f32: one full sector each).  Anything else takes the 4-pixel generic path.
 constexpr int kIngestThreads = 128;
+// the gray level behind a toGrayF32 value of a u8-sourced frame: f = fl32(g * fl32(1/255)) -> rint(f * 255) == g for g = 0..255
+__device__ __forceinline__ unsigned int gray8_of(float f) { return (unsigned int)__float2int_rn(f * 255.0f) & 255u; }
+__device__ __forceinline__ void store_gray8(const Ctx& c, int stream, int x, int y, const float4& o)
+{
+    *reinterpret_cast<unsigned int*>(c.gray8 + (size_t)stream * c.plane8 + (size_t)y * c.pitch8 + x) =
+        gray8_of(o.x) | (gray8_of(o.y) << 8) | (gray8_of(o.z) << 16) | (gray8_of(o.w) << 24);
+}
 __device__ __forceinline__ float gray_px(unsigned int w /* bytes: B G R x */)
 {
     unsigned int acc = __dp2a_lo((19235u << 16) | 3735u, w, 16384u);   // 3735 * B + 19235 * G + 16384
@@ -107,6 +115,13 @@ __global__ void __launch_bounds__(kIngestThreads) k_ingest(Ctx c)
                 o[4 * g + 2] = gray_px(__byte_perm(b, e, 0x0432));       // b2 b3 e0
                 o[4 * g + 3] = gray_px(e >> 8);                          // e1 e2 e3
             }
+            if (c.gray8) {   // tensor-core search: keep the gray levels themselves (exactly rint(f * 255))
+                unsigned int b[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    b[g] = gray8_of(o[4 * g]) | (gray8_of(o[4 * g + 1]) << 8) | (gray8_of(o[4 * g + 2]) << 16) | (gray8_of(o[4 * g + 3]) << 24);
+                *reinterpret_cast<uint4*>(c.gray8 + (size_t)stream * c.plane8 + (size_t)y * c.pitch8 + x) = make_uint4(b[0], b[1], b[2], b[3]);
+            }
             if ((c.pitch & 7) == 0) {
                 st_v8(orow + x, *reinterpret_cast<const float(*)[8]>(o));
                 st_v8(orow + x + 8, *reinterpret_cast<const float(*)[8]>(o + 8));
@@ -123,7 +138,9 @@ __global__ void __launch_bounds__(kIngestThreads) k_ingest(Ctx c)
             const int g = (blockIdx.x * 4 + k) * kIngestThreads + threadIdx.x;
             if (g >= gpr) break;
             const int x = g << 2;
-            *reinterpret_cast<float4*>(orow + x) = ingest_group(d, irow, x, min(4, c.W - x));  // pitch % 4 == 0
+            const float4 o4 = ingest_group(d, irow, x, min(4, c.W - x));
+            *reinterpret_cast<float4*>(orow + x) = o4;  // pitch % 4 == 0
+            if (c.gray8) store_gray8(c, stream, x, y, o4);
         }
     }
     trace_end(c, step, TR_INGEST);
@@ -161,13 +178,17 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
         const StageHdr h = c.stage_hdr[track];
         if (h.step == step && h.data == d.data && x0 >= h.x0 && x1 <= h.x1 && win[1] >= h.y0 && win[1] + rows <= h.y1) {
             const float* sp = c.stage + (size_t)track * c.stage_w * c.stage_h + (size_t)(y - h.y0) * c.stage_w + (x - h.x0);
-            *reinterpret_cast<float4*>(out) = *reinterpret_cast<const float4*>(sp);
+            const float4 o4 = *reinterpret_cast<const float4*>(sp);
+            *reinterpret_cast<float4*>(out) = o4;
+            if (c.gray8) store_gray8(c, t.stream, x, y, o4);
             trace_end(c, step, TR_INGEST);
             return;
         }
     }
     const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
-    *reinterpret_cast<float4*>(out) = ingest_group(d, row, x, min(4, c.W - x));
+    const float4 o4 = ingest_group(d, row, x, min(4, c.W - x));
+    *reinterpret_cast<float4*>(out) = o4;
+    if (c.gray8) store_gray8(c, t.stream, x, y, o4);
     trace_end(c, step, TR_INGEST);
 }
 
@@ -439,6 +460,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
             dnv = (double)(sd + 1e-6f) * tn;
         }
         dn[x] = dnv;
+        if (c.wsum) c.wsum[(size_t)track * c.Hmax * c.Wmax + (size_t)y * ww + x] = wsum;   // the tensor-core search removes its DC error with it
     }
     if (lane == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
@@ -1227,6 +1249,64 @@ __device__ void block_sum2(double& s, double& q, double* red /* 2 * 32 doubles *
     for (int i = 0; i < nw; ++i) { s += red[i]; q += red[32 + i]; }   // same order in every thread: identical result
 }
 
+// PVT_KERNEL_TC: the centred template tc = fl32(t - mean) in 16-bit fixed point, q = rint(tc * 2^k) with k the largest
+// power of two that keeps |q| <= 127 * 256, as two signed 8-bit digits q = 256 d1 + d0 (operand B of k_ncc_tc), plus what
+// the epilogue needs to undo the scale and the DC part of the rounding: 2^-k and (sum(q) 2^-k - sum(tc)) / N.
+__device__ void write_digits(const Ctx& c, int track, TrackState& t, const float* s_t, double mean, int tw, int th)
+{
+    __shared__ double r3[3][32];
+    const int n = tw * th, tid = threadIdx.x, nw = (blockDim.x + 31) >> 5, w = tid >> 5;
+    double mx = 0.0, st = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double v = (double)(float)((double)s_t[i] - mean);
+        mx = fmax(mx, fabs(v));
+        st += v;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        mx = fmax(mx, __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(mx), m), __shfl_xor_sync(0xffffffffu, __double2loint(mx), m)));
+        st += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(st), m), __shfl_xor_sync(0xffffffffu, __double2loint(st), m));
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { r3[0][w] = mx; r3[1][w] = st; }
+    __syncthreads();
+    mx = 0.0; st = 0.0;
+    for (int i = 0; i < nw; ++i) { mx = fmax(mx, r3[0][i]); st += r3[1][i]; }
+    int k = 0;
+    if (mx > 0.0) {
+        int e;
+        const double fr = frexp(32512.0 / mx, &e);    // 32512 / mx = fr * 2^e, fr in [0.5, 1)  ->  floor(log2) = e - 1
+        (void)fr;
+        k = e - 1;
+        if (k > 60) k = 60;
+    }
+    const double scale = ldexp(1.0, k), inv = ldexp(1.0, -k);
+    signed char* d0 = c.tdig + (size_t)track * 2 * c.mth * c.tpp;
+    signed char* d1 = d0 + (size_t)c.mth * c.tpp;
+    double sq = 0.0;
+    const int tpp = c.tpp;
+    for (int i = tid; i < th * tpp; i += blockDim.x) {
+        const int y = i / tpp, x = i - y * tpp;
+        int q = 0;
+        if (x < tw) q = __double2int_rn((double)(float)((double)s_t[y * tw + x] - mean) * scale);
+        const int hi = (q + 128) >> 8, lo = q - 256 * hi;
+        d0[(size_t)y * tpp + x] = (signed char)lo;
+        d1[(size_t)y * tpp + x] = (signed char)hi;
+        sq += (double)q;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+        sq += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(sq), m), __shfl_xor_sync(0xffffffffu, __double2loint(sq), m));
+    if ((tid & 31) == 0) r3[2][w] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        sq = 0.0;
+        for (int i = 0; i < nw; ++i) sq += r3[2][i];          // integers below 2^53: exact in any order
+        t.tc_inv = inv;
+        t.tc_dc = (sq * inv - st) / (double)n;
+    }
+}
+
 // statistics + centred chunk-major template from the template held in shared memory (s_t, th*tw floats)
 // (tw, th) = (t.w, t.h), passed in registers: callers sit behind a barrier, where re-reading them costs an L2 round trip
 __device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th)
@@ -1257,6 +1337,7 @@ __device__ void finish_template(const Ctx& c, int track, TrackState& t, const fl
         }
         t.tp = tpad;
     }
+    if (c.tdig) write_digits(c, track, t, s_t, mean, tw, th);
     // centred template, CHUNK-MAJOR: tc[(x / 8) * th * 8 + y * 8 + (x % 8)], columns >= tw are zero.
     // Element i = y * tpad + x per thread, consecutive lanes = consecutive x: conflict-free shared-memory reads (a thread per
     // 8-float chunk row read with a stride of tw floats between lanes: 32-way bank conflicts, 2.2 of the update's 6.7 us on
@@ -1429,3 +1510,5 @@ __global__ void k_hold(Ctx c)
 }
 
 }  // namespace pvt
+
+#include "ncc_tc.cuh"

@@ -125,6 +125,10 @@ struct pvt_ctx {
     int seq_ring_len = 0;
     bool seq_rows_valid = false;      // d.table rows [0, seq_ring_len) == seq_rows (any per-step submit invalidates it)
     std::vector<FrameDesc> seq_scratch;
+    TcCfg tc{};                       // PVT_KERNEL_TC: geometry of k_ncc_tc, its shared memory and the 4-D tensor map of the u8 gray plane
+    size_t tc_smem = 0;
+    CUtensorMap tmap8{};
+    bool tc_ready = false;            // created with PVT_KERNEL_TC (gray8 / digits / window sums allocated)
     bool host_ptr_is_dev = false;     // cudaDevAttrCanUseHostPointerForRegisteredMem: a pinned host pointer is its own device alias
 };
 
@@ -290,7 +294,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f)
 // ... of the local pass under the context's kernel choice (k_ncc_direct: ingest, 2 statistics, search, update)
 int kernels_per_step(const pvt_ctx* c)
 {
-    return c->params.kernel == PVT_KERNEL_DIRECT ? 5 : pass_kernels(c->tile, c->fringe);
+    return c->params.kernel != PVT_KERNEL_AUTO ? 5 : pass_kernels(c->tile, c->fringe);   // ingest, 2 statistics, search, update
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -391,6 +395,7 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     d.Wmax = d.W; d.Hmax = d.H;                         // upper bounds of the map (W - tw + 1) x (H - th + 1)
     d.VW = (d.Wmax + d.mtw - 1 + 7) & ~7;
     d.maps = nullptr; d.partial = nullptr; d.fringe_acc = nullptr; d.trace = nullptr;
+    d.wsum = nullptr;                                   // the whole-frame pass keeps the FP32 search (its window sums would not fit the local buffer)
     const size_t win = (size_t)d.Wmax * d.Hmax;
     { int r = dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
     { int r = dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
@@ -400,6 +405,53 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     int r = build_plan(c, g, sm_count, PVT_INGEST_FULL, false);
     if (r) return r;
     c->kps_global = 2;   // k_global_mark + k_step_advance; the conditional body's kernels (they only run while a track is lost) are not counted
+    return PVT_OK;
+}
+
+// PVT_KERNEL_TC: geometry of k_ncc_tc, its buffers (u8 gray plane, template digits, window sums) and the 4-D tensor map
+// (16 B, row, 16-pixel chunk, stream) whose box lands in shared memory chunk-major (ncc_tc.cuh)
+int setup_tc(pvt_ctx* c)
+{
+    Ctx& d = c->d;
+    TcCfg& g = c->tc;
+    const int NW = (d.Wmax + 15) & ~15;
+    g.AG = NW / 8;
+    g.KS = (d.Wmax + d.mtw - 1 + 15 + 31) / 32;
+    g.rows = 128 + d.mth - 1;
+    g.nblk = 4 * g.KS + g.AG;
+    g.tpp = (d.mtw + 15) & ~15;
+    g.mtiles = (d.Hmax + 127) / 128;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < 2 * NW) g.tmem_cols <<= 1;
+    if (NW > 256 || g.KS > kTcKMax || g.rows > 256)
+        return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: window width <= 256, template height <= 129 and window + template width <= 306 required");
+    auto smem_of = [&](int stages) {
+        return (size_t)16 * g.rows * 2 * g.KS + (size_t)stages * 2 * g.nblk * 128 + ((((size_t)2 * d.mth * (kTcPadL + g.tpp + kTcPadR)) + 15) & ~(size_t)15) +
+               sizeof(uint64_t) * (2 + 2 * stages) + 64;
+    };
+    g.stages = 4;
+    while (g.stages > 2 && smem_of(g.stages) > kSmemBudget - 1024) --g.stages;
+    c->tc_smem = smem_of(g.stages);
+    if (c->tc_smem > kSmemBudget - 1024) return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: tile does not fit shared memory");
+    { int r = raise_smem((const void*)k_ncc_tc, c->tc_smem); if (r) return r; }
+    d.pitch8 = (d.W + 15) & ~15;
+    d.plane8 = ((size_t)d.pitch8 * d.H + 255) & ~(size_t)255;
+    d.tpp = g.tpp;
+    { int r = dev_alloc(c, &d.gray8, d.plane8 * d.max_streams); if (r) return r; }
+    { int r = dev_alloc(c, &d.tdig, (size_t)d.max_tracks * 2 * d.mth * g.tpp); if (r) return r; }
+    { int r = dev_alloc(c, &d.wsum, (size_t)d.max_tracks * d.Wmax * d.Hmax, false); if (r) return r; }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    cuuint64_t dims[4] = {16, (cuuint64_t)d.H, (cuuint64_t)(d.pitch8 / 16), (cuuint64_t)d.max_streams};
+    cuuint64_t strides[3] = {(cuuint64_t)d.pitch8, 16, (cuuint64_t)d.plane8};
+    cuuint32_t box[4] = {16, (cuuint32_t)g.rows, (cuuint32_t)(2 * g.KS), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)fn)(&c->tmap8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d.gray8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled (u8 gray plane, 4-D) failed, CUresult " + std::to_string((int)r));
+    c->tc_ready = true;
     return PVT_OK;
 }
 
@@ -439,7 +491,7 @@ int validate_params(const pvt_params* p)
     if (p->mode == PVT_MODE_CPU)
         return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path (the CPU oracle lives in oracle/, test-only)");
     if (p->mode < PVT_MODE_NAIVE || p->mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
-    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_DIRECT) return fail(PVT_ERR_INVALID, "unknown kernel variant");
+    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TC) return fail(PVT_ERR_INVALID, "unknown kernel variant");
     if (p->ingest < PVT_INGEST_AUTO || p->ingest > PVT_INGEST_ROI) return fail(PVT_ERR_INVALID, "unknown ingest mode");
     if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
@@ -547,7 +599,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
 
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
-    const bool ksplit = c->params.kernel != PVT_KERNEL_DIRECT && p.tile.pj * p.tile.pd > 1;
+    const bool tc = c->params.kernel == PVT_KERNEL_TC && !d.global_pass;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
+    const bool ksplit = c->params.kernel == PVT_KERNEL_AUTO ? p.tile.pj * p.tile.pd > 1
+                                                             : (c->params.kernel == PVT_KERNEL_TC && d.global_pass && p.tile.pj * p.tile.pd > 1);
     const bool fork = capturing && ksplit;
     cudaStream_t sstats = c->compute;
     if (fork) {
@@ -564,7 +618,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
-    const bool fringe = c->params.kernel != PVT_KERNEL_DIRECT && p.fringe.colg + p.fringe.rowg > 0;
+    const bool fringe = !tc && c->params.kernel != PVT_KERNEL_DIRECT && p.fringe.colg + p.fringe.rowg > 0;
     const dim3 fgrid((unsigned)(p.fringe.colg + p.fringe.rowg), (unsigned)d.max_tracks, (unsigned)(p.fringe.defer ? p.tile.pd : 1));
     if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
@@ -585,7 +639,12 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
             { int r = dbg(c, "k_ncc_fringe"); if (r) return r; }
         }
     }
-    if (c->params.kernel == PVT_KERNEL_DIRECT) {
+    if (tc) {
+        if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
+        k_ncc_tc<<<(unsigned)(d.max_tracks * c->tc.mtiles), kTcThreads, c->tc_smem, c->compute>>>(d, c->tc, c->tmap8);
+        if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
+        if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
+    } else if (c->params.kernel == PVT_KERNEL_DIRECT) {
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else {
@@ -769,6 +828,8 @@ int check_frame(const pvt_ctx* c, const pvt_frame* f)
     if (f->memory != PVT_MEM_HOST && f->memory != PVT_MEM_DEVICE && f->memory != PVT_MEM_HOST_PINNED) return fail(PVT_ERR_INVALID, "unknown frame memory kind");
     if (f->step < frame_row_bytes(c, f->format)) return fail(PVT_ERR_INVALID, "frame.step smaller than one row");
     if (f->format == PVT_FMT_GRAYF32 && (f->step % 4 || ((size_t)f->data) % 4)) return fail(PVT_ERR_INVALID, "f32 frame not 4-byte aligned");
+    if (f->format == PVT_FMT_GRAYF32 && c->params.kernel == PVT_KERNEL_TC)
+        return fail(PVT_ERR_INVALID, "PVT_KERNEL_TC searches the 8-bit gray levels: GRAYF32 frames are not accepted by this context");
     return PVT_OK;
 }
 
@@ -1182,6 +1243,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CR(dev_alloc(c, &d.stage, (size_t)d.max_tracks * d.stage_w * d.stage_h));
         CR(dev_alloc(c, &d.stage_hdr, (size_t)d.max_tracks));
     }
+    if (params->kernel == PVT_KERNEL_TC) CR(setup_tc(c));
     c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
     if (c->templ_smem > 48u * 1024u) {
         CR(raise_smem((const void*)k_update, c->templ_smem));
@@ -1209,6 +1271,7 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
     if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
     if ((p->lost_frame_threshold > 0) != c->lost_mode) return fail(PVT_ERR_INVALID, "lost-object mode (lost_frame_threshold > 0) must be chosen at pvt_create");
     if (p->formula != c->params.formula) return fail(PVT_ERR_INVALID, "the score formula must be chosen at pvt_create (templates carry its statistics)");
+    if (p->kernel == PVT_KERNEL_TC && !c->tc_ready) return fail(PVT_ERR_INVALID, "PVT_KERNEL_TC must be chosen at pvt_create (it allocates the 8-bit gray plane and the template digits)");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->compute));
     const bool regraph = p->kernel != c->params.kernel || p->ingest != c->params.ingest;

@@ -63,6 +63,9 @@ struct TrackState {
     int lost_count;            // consecutive frames below the confidence threshold (lost_frame_count)
     int use_global;            // use_global_search: the track is searched over the whole frame ...
     unsigned long long global_since;   // ... from this time step on (the flag is set by the PREVIOUS step's update)
+    // tensor-core path (PVT_KERNEL_TC): the centred template in 16-bit fixed point q = rint(tc * 2^k) lives in Ctx.tdig
+    double tc_inv;             // 2^-k
+    double tc_dc;              // (sum(q) * 2^-k - sum(tc)) / N: the quantisation's DC part, taken out through the window sum
 };
 
 struct DevParams {
@@ -84,6 +87,12 @@ struct Ctx {
     int mtw, mth, mtp;         // template maxima: width, height, padded pitch
     int Wmax, Hmax, VW;        // window maxima (2*rx+1, 2*ry+1) and vsum row pitch
     float* gray;
+    unsigned char* gray8;      // PVT_KERNEL_TC: the 8-bit gray plane itself [streams][H][pitch8] (operand A of the tensor-core search); else NULL
+    int pitch8;                // bytes per row, multiple of 16
+    size_t plane8;             // bytes per plane, multiple of 16
+    signed char* tdig;         // PVT_KERNEL_TC: template digits [tracks][2][mth][tpp] (digit 0 = low byte), tpp = mtw rounded up to 16
+    int tpp;
+    double* wsum;              // PVT_KERNEL_TC: window sums [tracks][Hmax*Wmax] next to denom (k_rowsum)
     float* templ;
     float* templc;
     double* vsum;

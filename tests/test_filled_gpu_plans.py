@@ -90,7 +90,10 @@ def test_planner_gives_the_filled_plans_these_tests_are_about():
 
 # ---- GPU ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-def test_c5_64_streams_1080p_tail_split_and_fringe():
+@pytest.mark.parametrize("kernel", ["auto", "tc"])
+def test_c5_64_streams_1080p_tail_split_and_fringe(kernel):
+    """kernel "tc": the same case on the tensor-core search (k_ncc_tc; two 128-row tiles per track, band-aware MMAs, every
+    window-origin alignment 0..15 occurs among the 64 streams) -- same gates, same goldens."""
     sm = pvt.device_info(0)["sm_count"]
     plan = pvt.plan_query(64, FC.TW, FC.TH, FC.W, FC.H, FC.R, FC.R, sm_count=sm)
     assert plan["pj"] * plan["pd"] == 1 and plan["n_tail"] > 0 and plan["tail_parts"] >= 2 and plan["fringe"] == 3, plan
@@ -98,7 +101,8 @@ def test_c5_64_streams_1080p_tail_split_and_fringe():
     assert c5.crc() == _meta()["c5"]["frames_crc"], "synthetic c5 frames are not byte-identical to the golden run's"
     gold = Hp.golden("filled_c5_64x1080p.npz")
     n = c5.n_streams
-    with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, max_streams=n, max_tracks=n, keep_maps=1, search_radius_x=FC.R, search_radius_y=FC.R) as tr:
+    with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, max_streams=n, max_tracks=n, keep_maps=1, search_radius_x=FC.R, search_radius_y=FC.R,
+                     kernel=pvt.KERNEL_TC if kernel == "tc" else pvt.KERNEL_AUTO) as tr:
         f0 = c5.frames_at(0)
         templs, boxes = [], []
         for s in range(n):
@@ -128,7 +132,8 @@ def test_c5_64_streams_1080p_tail_split_and_fringe():
 
 
 @pytest.mark.gpu
-def test_c4_256_rois_one_stream_tail_split_and_fringe():
+@pytest.mark.parametrize("kernel", ["auto", "tc"])
+def test_c4_256_rois_one_stream_tail_split_and_fringe(kernel):
     sm = pvt.device_info(0)["sm_count"]
     plan = pvt.plan_query(256, FC.TW, FC.TH, FC.W, FC.H, FC.R, FC.R, sm_count=sm)
     assert plan["pj"] * plan["pd"] == 1 and plan["n_tail"] > 0 and plan["tail_parts"] >= 2 and plan["fringe"] == 3, plan
@@ -139,7 +144,8 @@ def test_c4_256_rois_one_stream_tail_split_and_fringe():
     n = len(rois)
     g0 = O.to_gray_f32(c4.frames[0])
     first_tail_track = plan["n_full"] // plan["ctas_per_track"]
-    with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, max_streams=1, max_tracks=n, keep_maps=1, search_radius_x=FC.R, search_radius_y=FC.R) as tr:
+    with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, max_streams=1, max_tracks=n, keep_maps=1, search_radius_x=FC.R, search_radius_y=FC.R,
+                     kernel=pvt.KERNEL_TC if kernel == "tc" else pvt.KERNEL_AUTO) as tr:
         for t, roi in enumerate(rois):
             tr.init_track(t, c4.frames[0] if t == 0 else None, roi)
         templs = [g0[r[1]:r[1] + FC.TH, r[0]:r[0] + FC.TW].copy() for r in rois]

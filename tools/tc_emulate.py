@@ -73,6 +73,38 @@ def tc_cross(gray_u8: np.ndarray, tc: np.ndarray, win, truncate=True) -> np.ndar
     return (acc.astype(np.float64) / (255.0 * SCALE)).astype(np.float32)
 
 
+def quantise_i8x2(tc: np.ndarray):
+    """The product kernel's template operand (kind::i8): q = round(tc * 2^k) with 2^k * max|tc| <= 127 * 256, split into two
+    signed 8-bit digits q = 256 * d1 + d0.  Returns (q as int64, 2^-k, sum(q) * 2^-k - sum(tc) in float64)."""
+    m = float(np.abs(tc).max())
+    if m == 0.0:
+        return np.zeros(tc.shape, np.int64), 1.0, 0.0
+    k = int(np.floor(np.log2(32512.0 / m)))
+    q = np.rint(tc.astype(np.float64) * 2.0 ** k).astype(np.int64)
+    d1 = (q + 128) >> 8
+    d0 = q - 256 * d1
+    assert d1.min() >= -128 and d1.max() <= 127 and d0.min() >= -128 and d0.max() <= 127
+    return q, 2.0 ** -k, float(q.sum()) * 2.0 ** -k - float(tc.astype(np.float64).sum())
+
+
+def i8_cross(gray_u8: np.ndarray, gray: np.ndarray, tc: np.ndarray, win, n_templ: int) -> np.ndarray:
+    """EXACT integer cross term of the quantised template (what int32 accumulation in TMEM gives, in any order), scaled by
+    the ingest constant fl32(1/255), with the quantisation's DC part removed through the window sum:
+        cc = c255 * 2^-k * sum g q  -  (wsum / N) * (sum(q) 2^-k - sum(tc))"""
+    x0, y0, ww, wh = win
+    th, tw = tc.shape
+    q, inv, dc = quantise_i8x2(tc)
+    G = gray_u8[y0:y0 + wh + th - 1, x0:x0 + ww + tw - 1].astype(np.int64)
+    W = np.lib.stride_tricks.sliding_window_view(G, (th, tw))
+    acc = np.einsum("yxij,ij->yx", W, q)                                   # exact in int64
+    g = gray.astype(np.float64)
+    S = np.zeros((g.shape[0] + 1, g.shape[1] + 1)); S[1:, 1:] = g.cumsum(0).cumsum(1)
+    ys, xs = np.arange(y0, y0 + wh)[:, None], np.arange(x0, x0 + ww)[None, :]
+    wsum = S[ys + th, xs + tw] - S[ys, xs + tw] - S[ys + th, xs] + S[ys, xs]
+    c255 = float(np.float32(1.0) / np.float32(255.0))
+    return (acc.astype(np.float64) * (c255 * inv) - wsum * (dc / n_templ)).astype(np.float32)
+
+
 def normalise(gray: np.ndarray, templ: np.ndarray, cc: np.ndarray, win) -> np.ndarray:
     """OpenCV TM_CCOEFF_NORMED finalisation with the cross term of the CENTRED template given."""
     x0, y0, ww, wh = win
@@ -101,14 +133,22 @@ def centred(templ):
     return (templ.astype(np.float64) - mean).astype(np.float32)
 
 
+MODEL = "f16x2"   # or "i8x2"
+
+
 def tc_map(frame_bgr, templ, win):
     g8 = O.bgr2gray(frame_bgr)
     gray = O.gray_to_f32(g8)
+    if MODEL == "i8x2":
+        return normalise(gray, templ, i8_cross(g8, gray, centred(templ), win, templ.size), win), gray
     return normalise(gray, templ, tc_cross(g8, centred(templ), win), win), gray
 
 
 def main():
-    out = {"maps": [], "clips": []}
+    global MODEL
+    if len(sys.argv) > 1:
+        MODEL = sys.argv[1]
+    out = {"model": MODEL, "maps": [], "clips": []}
     # ---- golden window maps (cv2 IPP-off is the exact formula)
     for name, k in [("small", 1), ("small", 7), ("lowtex", 2), ("border", 3), ("flat", 1), ("oddsize", 2), ("c2_1080p", 1)]:
         (c, tk) = Hp.clip(name)
@@ -155,7 +195,7 @@ def main():
                "final_template_bit_identical": bool(np.array_equal(templ, gold["templ"]))}
         out["clips"].append(rec)
         print(rec, flush=True)
-    with open(os.path.join(ROOT, "profiles", "tc_emulation_r2.json"), "w") as fh:
+    with open(os.path.join(ROOT, "profiles", "tc_emulation_%s_r2.json" % MODEL), "w") as fh:
         json.dump(out, fh, indent=1)
 
 
