@@ -198,7 +198,7 @@ REGIONS = 5   # the K-step timed region is repeated this many times; the median 
 
 
 def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=None, stream_ids=None, total_streams=None,
-            gather=None, e2e_leg=None):
+            gather=None, e2e_leg=None, tracker_kw=None):
     """All legs of one workload on this rank.  full=False: only the resident leg + the roofline pass (used for `extra`).
     wl / stream_ids / total_streams: a sharded workload (this rank's share of `total_streams` global streams);
     gather(records) -> all ranks' last-step records in global order (off the timed path); e2e_leg: force the pinned-host leg."""
@@ -217,7 +217,7 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
 
     def make_tracker(**kw):
         tr = pvt.Tracker(W, H, tw, th, max_streams=S, max_tracks=n_tracks, device=dev_index,
-                         search_radius_x=R, search_radius_y=R, **kw)
+                         search_radius_x=R, search_radius_y=R, **dict(tracker_kw or {}, **kw))
         t = 0
         for s in range(S):
             for j, roi in enumerate(rois_for(wl, scenes[s])):
@@ -306,6 +306,8 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
     T = tr.trace_get(16).astype(np.int64)
     tr.trace_enable(False)
     names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe", "ncc_tail_finalize"]
+    if not T[:, 2, 0].any():
+        names[1] = "winstats"          # k_winstats (one statistics kernel) stamps the first statistics slot only
     timeline = {nm: round(float(np.median(T[:, k, 1] - T[:, k, 0])) / 1e3, 2) for k, nm in enumerate(names) if T[:, k, 0].any()}
     # the search PHASE in the production graph: first start .. last end of k_ncc_search, k_ncc_fringe (which overlaps
     # the search: programmatic dependent launch, or a parallel branch in the K-split shape) and the tail reduction
@@ -468,7 +470,8 @@ def run_ours(args):
         return x
 
     K, Wm = args.steps, max(args.warmup, 3)
-    m = measure(pvt, torch, args.workload, rank, world, K, Wm, barrier, maxr, full=True)
+    tkw = {"kernel": pvt.KERNEL_TC} if args.kernel == "tc" else None
+    m = measure(pvt, torch, args.workload, rank, world, K, Wm, barrier, maxr, full=True, tracker_kw=tkw)
     wl = m["wl"]
     out = {
         "metric": "tracked_frames_per_s", "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -477,7 +480,7 @@ def run_ours(args):
         "run": {"ingest": m["ingest_mode"], "timed_regions": REGIONS, "regions_ms": m["regions_ms"], "regions_spread": m["regions_spread"],
                 "value_is": "median over the timed regions of (streams x K steps) / (max over ranks of the region's CUDA-event time)"},
         "ncc_gmacs_per_s": world * m["macs_per_step"] / (m["ms_per_step"] * 1e-3) / 1e9,
-        "roofline": m["roofline"], "ingest": m["ingest"], "kernel_ms_per_step": m["kernel_ms_per_step"],
+        "kernel": args.kernel, "roofline": m["roofline"], "ingest": m["ingest"], "kernel_ms_per_step": m["kernel_ms_per_step"],
         "device_timeline_us": m["device_timeline_us"], "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": m["clocks"],
         "conf_min": m["conf_min"], "batch4": m["batch4"], "prewarm_steps": m["prewarm_steps"],
     }
@@ -511,6 +514,24 @@ def run_ours(args):
                                 "regions_ms": e["regions_ms"],
                                 "ncc_gmacs_per_s": e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9, "roofline": e["roofline"],
                                 "kernel_ms_per_step": e["kernel_ms_per_step"], "device_timeline_us": e["device_timeline_us"], "ingest": e["ingest_mode"]}
+        # the tensor-core search (PVT_KERNEL_TC: tcgen05.mma kind::i8, csrc/ncc_tc.cuh) on the same filled-GPU workloads: useful
+        # MACs only (n_cand x tw x th -- the Toeplitz padding and the second 8-bit digit are not counted) over the kernel's time
+        for w2 in ("C4", "C5"):
+            try:
+                e = measure(pvt, torch, w2, 0, 1, 40, 6, barrier, maxr, full=False, tracker_kw={"kernel": pvt.KERNEL_TC})
+                fp = out["extra"][w2]
+                useful_tf = 2.0 * e["macs_per_step"] / (e["roofline"]["us_per_launch"] * 1e-6) / 1e12
+                out["extra"][w2 + "_tc"] = {
+                    "workload": WORKLOADS[w2]["desc"] + " -- PVT_KERNEL_TC", "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
+                    "regions_ms": e["regions_ms"], "ncc_gmacs_per_s": e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9,
+                    "search_kernel": {"kernel": "k_ncc_tc", "us_per_launch": e["roofline"]["us_per_launch"], "useful_macs_per_launch": e["macs_per_step"],
+                                      "useful_tflops": useful_tf, "x_fp32_peak": useful_tf / e["roofline"]["peak"],
+                                      "fp32_kernel_us_per_launch": fp["roofline"]["us_per_launch"],
+                                      "speedup_vs_fp32_kernel": fp["roofline"]["us_per_launch"] / e["roofline"]["us_per_launch"]},
+                    "speedup_step_vs_fp32": fp["ms_per_step"] / e["ms_per_step"],
+                    "kernel_ms_per_step": e["kernel_ms_per_step"], "device_timeline_us": e["device_timeline_us"], "ingest": e["ingest_mode"]}
+            except Exception as ex:   # an optional variant never takes the bench down
+                out["extra"][w2 + "_tc"] = {"unavailable": repr(ex)}
         out["extra"]["whole_frame_search"] = whole_frame_leg(pvt, torch, m)
         out["extra"]["map_operator"] = map_operator_leg(pvt, m)
         out["ref_gpu_baseline"] = ref_gpu_leg(m, out["extra"]["map_operator"])
@@ -700,6 +721,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tc"], help="tc: PVT_KERNEL_TC (tensor-core search) for the main workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the filled-GPU C4/C5 side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -357,6 +357,24 @@ __global__ void __launch_bounds__(1024) k_colprefix(Ctx c)
     if (lx == 0) { if (c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_COLPREFIX) * 2 + 1], gtime()); }
 }
 
+// OpenCV's normaliser of one candidate from its window sums (common_matchTemplate, TM_CCOEFF_NORMED), exactly in its operation
+// order, no contraction: wndMean2 = t*t; wndMean2 *= invArea; ...   (formula != 0: the reference CUDA kernels' eps variant)
+__device__ __forceinline__ double window_denom(double wsum, double wsq, double invArea, double tn, int formula)
+{
+    const double wm2 = __dmul_rn(__dmul_rn(wsum, wsum), invArea);
+    double diff2 = __dsub_rn(wsq, wm2);
+    if (diff2 < 0.0) diff2 = 0.0;
+    double lim = __dmul_rn(10.0 * (double)FLT_EPSILON, wsq);
+    if (lim > 0.5) lim = 0.5;
+    double dnv = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
+    if (formula) {
+        // baseline_kernel.cu:44-48: std = sqrtf(fmaxf(var, 1e-6f)); the score divides by (std + 1e-6f) * (templStd + 1e-6f) * N
+        const float sd = sqrtf(fmaxf((float)(diff2 * invArea), 1e-6f));
+        dnv = (double)(sd + 1e-6f) * tn;
+    }
+    return dnv;
+}
+
 __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per prefix row in smem */)
 {
     extern __shared__ double sm_d[];
@@ -447,24 +465,140 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
     for (int x = lane; x < ww; x += 32) {
         const double wsum = Ps[PH(x + tw)] - Ps[PH(x)];
         const double wsq = Pq[PH(x + tw)] - Pq[PH(x)];
-        // exactly OpenCV's operation order, no contraction: wndMean2 = t*t; wndMean2 *= invArea
-        const double wm2 = __dmul_rn(__dmul_rn(wsum, wsum), invArea);
-        double diff2 = __dsub_rn(wsq, wm2);
-        if (diff2 < 0.0) diff2 = 0.0;
-        double lim = __dmul_rn(10.0 * (double)FLT_EPSILON, wsq);
-        if (lim > 0.5) lim = 0.5;
-        double dnv = (diff2 <= lim) ? 0.0 : __dmul_rn(sqrt(diff2), tn);
-        if (c.formula) {
-            // baseline_kernel.cu:44-48: std = sqrtf(fmaxf(var, 1e-6f)); the score divides by (std + 1e-6f) * (templStd + 1e-6f) * N
-            const float sd = sqrtf(fmaxf((float)(diff2 * invArea), 1e-6f));
-            dnv = (double)(sd + 1e-6f) * tn;
-        }
-        dn[x] = dnv;
+        dn[x] = window_denom(wsum, wsq, invArea, tn, c.formula);
         if (c.wsum) c.wsum[(size_t)track * c.Hmax * c.Wmax + (size_t)y * ww + x] = wsum;   // the tensor-core search removes its DC error with it
     }
     if (lane == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
 #undef PH
+
+// k_winstats: the same statistics in ONE kernel and without the FP64 prefix arrays (k_colprefix + k_rowsum write and re-read
+// 2 x 8 B per tile pixel through L2/HBM, and are two dependent launches on the single-stream step).
+// A CTA (8 warps) owns NX x NY candidates of one track; its tile has NX + tw - 1 <= 256 columns.
+//   (A) thread = tile column: vertical box sums of the band's first candidate row, S = sum f, Q = sum f^2 over th rows (FP64,
+//       32 loads in flight per thread);
+//   (V) per group of 8 candidate rows: the column slides down, S += f[y + th] - f[y] (both rows fetched one group ahead), and
+//       leaves its 8 x (S, Q) in shared memory, one padded row per candidate row;
+//   (H) warp = candidate row (k_rowsum's scheme): a lane scans its 8 consecutive columns, one warp scan of the lane totals,
+//       the prefix row goes back to shared memory, box = P[x + tw] - P[x], OpenCV's normaliser (window_denom) -> denom.
+// Numerics: every partial sum of f (u8-sourced: multiples of 2^-31 below 2^21) is exact in double, so wsum is the same number
+// whatever the order -- bit-identical to OpenCV's whole-frame integral and to k_rowsum; wsq agrees to ~1e-15 relative.
+struct StatCfg {
+    int NX, NY;          // candidates per CTA along x (256 - (mtw - 1)) and along y
+    int xtiles, ybands;  // CTAs per track = xtiles * ybands
+};
+constexpr int kStatThreads = 256;
+constexpr int kStatRowD = kStatThreads + kStatThreads / 8 + 2;   // doubles per padded row: element i at i + (i >> 3), i = 0 .. 256
+__global__ void __launch_bounds__(kStatThreads, 3) k_winstats(Ctx c, StatCfg sc)
+{
+    __shared__ double sD[8][2][kStatRowD];          // [candidate row of the group][sum | sum of squares][padded prefix row]
+    pdl_trigger();
+    const int track = blockIdx.y;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    trace_begin(c, step, TR_COLPREFIX);
+    const DevParams P = *c.params;
+    int win[4];
+    search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (blockIdx.x == 0 && tid < 4) t.win[tid] = win[tid];
+    const int ww = win[2], wh = win[3], tw = t.w, th = t.h;
+    const int yb = blockIdx.x / sc.xtiles, xt = blockIdx.x - yb * sc.xtiles;
+    const int x0 = xt * sc.NX, y0 = yb * sc.NY;
+    if (x0 >= ww || y0 >= wh) return;
+    const int nx = min(sc.NX, ww - x0), ny = min(sc.NY, wh - y0);
+    const bool colok = tid < nx + tw - 1;
+    const size_t pitch = (size_t)c.pitch;
+    const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)(win[1] + y0) * pitch + win[0] + x0 + (colok ? tid : 0);
+    const double invArea = 1.0 / ((double)th * (double)tw), tn = t.templ_norm;
+    const int formula = c.formula;
+#define PH(i) ((i) + ((i) >> 3))
+    pdl_wait();   // latency shape: launched behind the ingest with a programmatic dependency; the gray plane is complete now
+    // the slide rows of the first group are requested together with the first column sums: one L2 round trip less
+    float vin[8], vout[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool need = k + 1 < ny;                           // the slide behind candidate row k
+        vin[k] = need ? __ldg(col + (size_t)(k + th) * pitch) : 0.f;
+        vout[k] = need ? __ldg(col + (size_t)k * pitch) : 0.f;
+    }
+    double S = 0.0, Q = 0.0;
+    {
+        const float* p = col;
+        for (int r = 0; r < th; r += 32, p += 32 * pitch) {      // 32 independent loads in flight per thread
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = (r + k < th) ? __ldg(p + (size_t)k * pitch) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const double d = (double)v[k];
+                S += d;
+                Q += d * d;
+            }
+        }
+    }
+    if (!colok) { S = 0.0; Q = 0.0; }
+    const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+    for (int yy0 = 0; yy0 < ny; yy0 += 8) {
+        // (V) this column's vertical box sums of candidate rows yy0 .. yy0 + 7
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sD[k][0][PH(tid + 1)] = S;
+            sD[k][1][PH(tid + 1)] = Q;
+            const double di = (double)vin[k], dq = (double)vout[k];
+            S += di - dq;                                       // exact (see above); zero where no slide is needed
+            Q += di * di - dq * dq;
+        }
+        if (!colok) { S = 0.0; Q = 0.0; }
+        // request the next group's slide rows now: they arrive while the warps scan this group
+        if (yy0 + 8 < ny) {
+            const float* pin = col + (size_t)(yy0 + 8 + th) * pitch;
+            const float* pout = col + (size_t)(yy0 + 8) * pitch;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool need = yy0 + 8 + k + 1 < ny;
+                vin[k] = need ? __ldg(pin + (size_t)k * pitch) : 0.f;
+                vout[k] = need ? __ldg(pout + (size_t)k * pitch) : 0.f;
+            }
+        }
+        __syncthreads();
+        // (H) warp wid: candidate row yy0 + wid
+        const int yy = yy0 + wid;
+        if (yy < ny) {                                          // warp-uniform
+            double* Ps = sD[wid][0];
+            double* Pq = sD[wid][1];
+            const int i0 = lane * 8;
+            double ls[8], lq[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { ls[k] = Ps[PH(i0 + k + 1)]; lq[k] = Pq[PH(i0 + k + 1)]; }
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { ls[k] += ls[k - 1]; lq[k] += lq[k - 1]; }
+            double is = ls[7], iq = lq[7];                      // inclusive warp scan of the lane totals
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double ns = shfl_up_f64(is, d), nq = shfl_up_f64(iq, d);
+                if (lane >= d) { is += ns; iq += nq; }
+            }
+            const double off_s = is - ls[7], off_q = iq - lq[7];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { Ps[PH(i0 + k + 1)] = off_s + ls[k]; Pq[PH(i0 + k + 1)] = off_q + lq[k]; }
+            if (lane == 0) { Ps[0] = 0.0; Pq[0] = 0.0; }
+            __syncwarp();
+            double* dn = c.denom + woff + (size_t)(y0 + yy) * ww + x0;
+            double* wsp = c.wsum ? c.wsum + woff + (size_t)(y0 + yy) * ww + x0 : nullptr;
+            for (int x = lane; x < nx; x += 32) {
+                const double wsum = Ps[PH(x + tw)] - Ps[PH(x)];
+                const double wsq = Pq[PH(x + tw)] - Pq[PH(x)];
+                dn[x] = window_denom(wsum, wsq, invArea, tn, formula);
+                if (wsp) wsp[x] = wsum;                         // the tensor-core search removes its DC error with it
+            }
+        }
+        __syncthreads();                                        // the next group overwrites the rows
+    }
+#undef PH
+    if (tid == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_COLPREFIX) * 2 + 1], gtime());   // one kernel: one slot
+}
 
 // OpenCV's final rule for TM_CCOEFF_NORMED (common_matchTemplate): never NaN, always in [-1, 1]
 __device__ __forceinline__ float ncc_finalize(float num_f32, double t, int flat_templ)

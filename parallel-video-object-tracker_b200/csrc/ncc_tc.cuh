@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // phase stamps of CTA 0 (pvt_trace_enable; tools/tc_timeline.py): FINALIZE slot = prologue done | MMAs all issued,
+    // FRINGE slot = image tile landed | , TAIL slot = all MMAs complete | epilogue done
+    unsigned long long* trc = (c.trace && blockIdx.x == 0) ? c.trace + (step % kRing) * 16 : nullptr;
+    if (trc && tid == 0) trc[TR_FINALIZE * 2] = gtime();
 
     // band of non-zero Toeplitz blocks: block d holds taps 8 (d - AG + 1) - s - o + [0, 16), s = 0..7
     // (a block is non-zero iff its s = 0 row reaches tap 0 and its s = 7 row starts at or before tap tw - 1)
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         const uint64_t bd0 = tc_desc(sb, 256, 128);
         const uint32_t id_full = tc_idesc(NW);
         mbar_wait(bar_tile, 0);
+        if (trc && lane == 0) trc[TR_FRINGE * 2] = gtime();
         for (int dy = 0; dy < u_th; ++dy) {
             const int st = dy % g.stages;
             mbar_wait(&full[st], (uint32_t)(dy / g.stages) & 1u);
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
             }
             __syncwarp();
         }
+        if (trc && lane == 0) trc[TR_FINALIZE * 2 + 1] = gtime();
     } else {
         // ===== Toeplitz block producers (128 threads) =====
         const int p = tid - 32;
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         // ===== epilogue: TMEM lane = candidate row; warp w may read lanes 32 (w % 4) .. + 31 =====
         mbar_wait(bar_done, 0);
         tc_fence_after();
+        if (trc && tid == 32) trc[TR_TAIL * 2] = gtime();
         const uint32_t tmem = *tmem_slot;
         const int q4 = warp & 3, y = row0 + q4 * 32 + lane;
         const bool rowok = y < wh;
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
             key = ok > key ? ok : key;
         }
         if (lane == 0 && key) atomicMax(&t.peak, key);
+        if (trc && tid == 32) trc[TR_TAIL * 2 + 1] = gtime();
     }
     tc_fence_before();
     __syncthreads();

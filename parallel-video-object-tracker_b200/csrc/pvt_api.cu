@@ -60,6 +60,7 @@ struct Pass {
     size_t ncc_smem = 0;
     int rowsum_warps = 8, rowsum_pw = 0;
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
+    StatCfg stat{};            // k_winstats (one statistics kernel); NX == 0: the two-kernel statistics (k_colprefix + k_rowsum)
     FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
@@ -86,6 +87,7 @@ struct pvt_ctx {
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
+    StatCfg stat{};            // k_winstats geometry (NX == 0: two-kernel statistics)
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;   // aux*: further branches inside the captured graph
     cudaEvent_t ev_join3 = nullptr;
@@ -156,6 +158,14 @@ int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
 // k_ncc_fringe geometry: tiles (of 8 candidates) per CTA and the largest K-split row-part count whose chain results
 // still fit its shared memory: strip | template | results [pd][chunks][8 * tpc].  Returns false when nothing fits
 // (then the thread-tile grid keeps the remainder and there is no fringe kernel).
+// the two-kernel statistics (k_colprefix + k_rowsum and their FP64 prefix arrays) are only kept for templates too wide for
+// k_winstats' one-column-per-thread tile, and behind PVT_STATS_LEGACY=1 for the before/after comparison in the tests
+bool stats_legacy(int mtw)
+{
+    const char* legacy = getenv("PVT_STATS_LEGACY");
+    return kStatThreads - (mtw - 1) < 32 || (legacy && *legacy == '1');
+}
+
 int fringe_strip_floats(int tpc, int mtp, int mth)
 {
     const int col = (tpc * 8 + mth - 1) * fringe_pitch(mtp), row = mth * fringe_pitch(tpc * 8 + mtp);
@@ -286,15 +296,16 @@ int raise_smem(const void* fn, size_t bytes)
 int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
 
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
-int pass_kernels(const TileCfg& t, const FringeCfg& f)
+int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st)
 {
-    return 4 + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
+    return (st.NX > 0 ? 3 : 4) + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
 
 // ... of the local pass under the context's kernel choice (k_ncc_direct: ingest, 2 statistics, search, update)
 int kernels_per_step(const pvt_ctx* c)
 {
-    return c->params.kernel != PVT_KERNEL_AUTO ? 5 : pass_kernels(c->tile, c->fringe);   // ingest, 2 statistics, search, update
+    // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
+    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat);
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -381,6 +392,29 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
     { int r_ = raise_smem((const void*)k_rowsum, (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double)); if (r_) return r_; }
     // k_colprefix: ~28 rows per thread (8 chunks for a 224-row tracker tile, up to 32 for full-frame maps)
     p.colprefix_chunks = std::max(1, std::min(32, (d.Hmax + d.mth - 1 + 27) / 28));
+    // k_winstats: a CTA of 256 threads owns one tile column per thread -> NX = 256 - (mtw - 1) candidates along x; NY candidate
+    // rows per CTA: tall bands when there are CTAs to spare (every band re-reads mth - 1 rows), short ones when a few tracks
+    // must spread over the GPU (the single-stream step waits for the slowest CTA)
+    p.stat = StatCfg{};
+    {
+        const int NX = kStatThreads - (d.mtw - 1);
+        if (!stats_legacy(d.mtw)) {
+            const int xt = (d.Wmax + NX - 1) / NX;
+            // bands: every band re-reads mth - 1 rows (the first column sums), so few tall bands do the least work -- but the CTAs
+            // run in waves of 3 per SM and a single-stream step waits for the slowest CTA.  Cost model in row units: a band
+            // costs mth row loads + ~3 units per candidate row (the horizontal scan and the normaliser) + a fixed part.
+            const long long slots = 3LL * sm_count;
+            int NY = d.Hmax;
+            double best = 1e300;
+            for (int nb = 1; nb <= std::max(1, (d.Hmax + 7) / 8); ++nb) {
+                const int ny = (d.Hmax + nb - 1) / nb, nbe = (d.Hmax + ny - 1) / ny;
+                const long long ctas = (long long)d.max_tracks * xt * nbe;
+                const double cost = (double)((ctas + slots - 1) / slots) * (d.mth + 3.0 * ny + 20.0);
+                if (cost < best) { best = cost; NY = ny; }
+            }
+            p.stat = StatCfg{NX, NY, xt, (d.Hmax + NY - 1) / NY};
+        }
+    }
     return encode_tmap(p.d, p.tile, &p.tmap);
 }
 
@@ -397,8 +431,11 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     d.maps = nullptr; d.partial = nullptr; d.fringe_acc = nullptr; d.trace = nullptr;
     d.wsum = nullptr;                                   // the whole-frame pass keeps the FP32 search (its window sums would not fit the local buffer)
     const size_t win = (size_t)d.Wmax * d.Hmax;
-    { int r = dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
-    { int r = dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
+    d.vsum = nullptr; d.vsq = nullptr;
+    if (stats_legacy(d.mtw)) {
+        { int r = dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
+        { int r = dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false); if (r) return r; }
+    }
     { int r = dev_alloc(c, &d.denom, (size_t)d.max_tracks * win, false); if (r) return r; }
     { int r = dev_alloc(c, &d.params, 1); if (r) return r; }
     { int r = dev_alloc(c, &d.stream_need, (size_t)d.max_streams); if (r) return r; }
@@ -530,7 +567,7 @@ Pass local_pass(const pvt_ctx* c)
 {
     Pass p;
     p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
-    p.colprefix_chunks = c->colprefix_chunks; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
+    p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
     return p;
 }
 Pass global_pass(const pvt_ctx* c)
@@ -611,10 +648,14 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     if (profile) { int r = pnode(c, CLS_STATS, 0, sstats); if (r) return r; }
     const bool pdl = capturing && !profile && p.pdl;   // programmatic edges: ingest ~> search / colprefix, colprefix ~> rowsum, search ~> finalize
-    { int r = launch_pdl(k_colprefix, dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats, pdl, d); if (r) return r; }
-    { int r = dbg(c, "k_colprefix"); if (r) return r; }
-    { int r = launch_pdl(k_rowsum, dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), dim3(p.rowsum_warps * 32),
-                         (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats, pdl, d, p.rowsum_pw); if (r) return r; }
+    if (p.stat.NX > 0) {
+        { int r = launch_pdl(k_winstats, dim3((unsigned)(p.stat.xtiles * p.stat.ybands), d.max_tracks), dim3(kStatThreads), 0, sstats, pdl, d, p.stat); if (r) return r; }
+    } else {
+        { int r = launch_pdl(k_colprefix, dim3((d.VW + 31) / 32, d.max_tracks), dim3(32, p.colprefix_chunks), 0, sstats, pdl, d); if (r) return r; }
+        { int r = dbg(c, "k_colprefix"); if (r) return r; }
+        { int r = launch_pdl(k_rowsum, dim3((d.Hmax + p.rowsum_warps - 1) / p.rowsum_warps, d.max_tracks), dim3(p.rowsum_warps * 32),
+                             (size_t)p.rowsum_warps * 2 * p.rowsum_pw * sizeof(double), sstats, pdl, d, p.rowsum_pw); if (r) return r; }
+    }
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
@@ -905,7 +946,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             if (r) return r;
             k_step_advance<<<1, 32, 0, c->compute>>>(gp.d);
             { int r2 = dbg(c, "k_step_advance"); if (r2) return r2; }
-            c->launches += c->kps_global + pass_kernels(gp.tile, gp.fringe);
+            c->launches += c->kps_global + pass_kernels(gp.tile, gp.fringe, gp.stat);
         }
     } else if (c->profiling) {
         // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
@@ -1187,8 +1228,10 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     CR(dev_alloc(c, &d.gray, d.plane * d.max_streams));
     CR(dev_alloc(c, &d.templ, (size_t)d.max_tracks * d.mth * d.mtw));
     CR(dev_alloc(c, &d.templc, (size_t)d.max_tracks * d.mth * d.mtp));
-    CR(dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));   // column prefix sums, tileH + 1 rows
-    CR(dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));
+    if (stats_legacy(d.mtw)) {
+        CR(dev_alloc(c, &d.vsum, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));   // column prefix sums, tileH + 1 rows
+        CR(dev_alloc(c, &d.vsq, (size_t)d.max_tracks * (d.Hmax + d.mth) * d.VW, false));
+    }
     CR(dev_alloc(c, &d.denom, (size_t)d.max_tracks * win, false));
     if (params->keep_maps) CR(dev_alloc(c, &d.maps, (size_t)d.max_tracks * win));
     CR(dev_alloc(c, &d.tracks, (size_t)d.max_tracks));
@@ -1232,7 +1275,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         lp.d = c->d;
         CR(build_plan(c, lp, prop.multiProcessorCount, params->ingest, true));
         c->d = lp.d; c->tile = lp.tile; c->tmap = lp.tmap; c->ncc_smem = lp.ncc_smem; c->rowsum_warps = lp.rowsum_warps;
-        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
+        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->stat = lp.stat; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
         c->roi_ingest = lp.roi_ingest;
     }
     c->kps = kernels_per_step(c);
