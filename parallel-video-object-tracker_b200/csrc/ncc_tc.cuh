@@ -24,17 +24,22 @@
 //     blocks per (template row, digit) that alias each other, inside a zero-filled run of blocks.
 //   * band-aware issue: a 32-column K-step only meets the candidates whose taps it holds; the MMA is issued for that
 //     sub-range (N' = 16..96 of 176 columns) through a column offset into D and a block offset into B.
-// Roles in the CTA (5 warps): warp 0 = TMA + MMA issue (one elected lane; every operand warp-uniform, see tc_probe.cu for
-// what a divergent issue loop costs), warps 1-4 build the Toeplitz blocks of the coming template rows into a ring of stages
-// (full / empty mbarriers; empty is signalled by tcgen05.commit) and afterwards run the epilogue: TMEM -> registers,
-// OpenCV's normalisation in FP64 with the denominators of k_rowsum, (score, index) key, warp max, atomicMax.
+// Roles in the CTA (9 warps): warp 0 = TMA + MMA issue (one elected lane; every operand warp-uniform, see tc_probe.cu for
+// what a divergent issue loop costs), warps 1-8 build the Toeplitz blocks of the coming template rows into a ring of stages
+// (full / empty mbarriers; empty is signalled by tcgen05.commit) and afterwards run the epilogue: TMEM -> registers (a warp
+// reads its lane quadrant, two warps per quadrant take alternate 16-column chunks), the window statistics of the chunk
+// staged through shared memory with coalesced cp.async (a lane owns a candidate ROW: read directly, every load would touch
+// 32 lines), OpenCV's normalisation in FP64 as 16 independent branch-free chains per thread, (score, index) key, warp max,
+// atomicMax.  (Round 2 timeline of one CTA, C5: prologue 3 us | 64 template rows of MMAs 48 us | epilogue 79 us with the
+// first version -- one warp per scheduler, a branchy FP64 chain and two uncoalesced loads per candidate.)
 #pragma once
 #include "pvt_device.cuh"
 
 namespace pvt {
 
 constexpr int kTcKMax = 10;        // K-steps (of 32 image columns) the issue code is unrolled for: Wmax + tw + 14 <= 320
-constexpr int kTcThreads = 160;
+constexpr int kTcThreads = 288;       // warp 0: TMA + MMA issue; warps 1-8: Toeplitz producers, then the epilogue (two warps per TMEM lane quadrant)
+constexpr int kTcEpiBytes = 8 * 2 * 32 * 17 * 8;   // epilogue staging: per warp [denom | wsum][32 rows][16 candidates + 1 pad] doubles, over the dead main-loop buffers
 constexpr int kTcPadL = 16, kTcPadR = 48;   // zero bytes left / right of a digit row in shared memory
 
 struct TcCfg {
@@ -94,6 +99,33 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
         : "memory");
 }
 
+__device__ __forceinline__ void cp_async8(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// num / t for normal operands without the library routine's slow-path branch (which keeps the compiler from interleaving the
+// 16 independent chains of an epilogue chunk): reciprocal seed, two Newton steps, quotient with one residual correction
+__device__ __forceinline__ double div_nr(double num, double t)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+    double e = __fma_rn(-t, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-t, y, 1.0);
+    y = __fma_rn(y, e, y);
+    const double q = __dmul_rn(num, y);
+    return __fma_rn(__fma_rn(-t, q, num), y, q);
+}
+// ncc_finalize's rule (OpenCV common_matchTemplate, TM_CCOEFF_NORMED) as selects: |num| < t -> num / t; < 1.125 t -> +-1; else 0
+__device__ __forceinline__ float ncc_finalize_sel(double num, double t)
+{
+    const double an = fabs(num);
+    const double q = div_nr(num, t > 0.0 ? t : 1.0);
+    const double one = num > 0.0 ? 1.0 : -1.0;
+    const double r = an < t ? q : (an < __dmul_rn(t, 1.125) ? one : 0.0);
+    return (float)r;
+}
+
 // candidates whose taps meet K-step kc (image-tile columns [32 kc, 32 kc + 32)), as a range of REVERSED 8-candidate groups
 // aligned to 16 columns: first group a0 (even) and group count n8 (even; 0 = the step holds no tap of any candidate)
 __device__ __forceinline__ void tc_band(int kc, int o, int tw, int ww, int AG, int* a0, int* n8)
@@ -128,7 +160,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
     unsigned char* sA = sm_tc;
     unsigned char* sB = sA + (size_t)CH * 2 * g.KS;
     unsigned char* sD = sB + (size_t)g.stages * 2 * blk_bytes;               // digits [2][mth][drow]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (((size_t)2 * c.mth * drow + 15) & ~(size_t)15));
+    size_t main_bytes = (size_t)(sD - sm_tc) + (((size_t)2 * c.mth * drow + 15) & ~(size_t)15);
+    if (main_bytes < (size_t)kTcEpiBytes) main_bytes = kTcEpiBytes;          // the epilogue staging reuses [0, kTcEpiBytes)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tc + main_bytes);
     uint64_t* bar_tile = bars;                                 // [0] image tile landed
     uint64_t* bar_done = bars + 1;                             // [1] all MMAs complete
     uint64_t* full = bars + 2;                                 // [stages] Toeplitz blocks of a template row written
@@ -139,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         if (lane == 0) {
             mbar_init(bar_tile, 1);
             mbar_init(bar_done, 1);
-            for (int s = 0; s < g.stages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < g.stages; ++s) { mbar_init(&full[s], (kTcThreads - 32) / 32); mbar_init(&empty[s], 1); }
             fence_mbar_init();
             mbar_arrive_expect_tx(bar_tile, (uint32_t)(CH * 2 * g.KS));
             tma_load_4d(sA, &tmap8, bar_tile, 0, t.win[1] + row0, t.win[0] >> 4, t.stream);
@@ -244,7 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         for (int dy = 0; dy < th; ++dy) {
             const int st = dy % g.stages;
             if (dy >= g.stages) mbar_wait(&empty[st], (uint32_t)(dy / g.stages - 1) & 1u);
-            for (int i = p; i < 2 * nb * 8; i += 128) {
+            for (int i = p; i < 2 * nb * 8; i += kTcThreads - 32) {
                 const int dg = i / (nb * 8), r = i - dg * nb * 8;
                 const int d = dlo_c + (r >> 3), s = r & 7;
                 const int off = kTcPadL + 8 * (d - g.AG + 1) - s - o;            // first tap of this block row, in the padded digit row
@@ -266,36 +300,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         tc_fence_after();
         if (trc && tid == 32) trc[TR_TAIL * 2] = gtime();
         const uint32_t tmem = *tmem_slot;
-        const int q4 = warp & 3, y = row0 + q4 * 32 + lane;
+        const int e = warp - 1, q4 = warp & 3, half = e >> 2;       // (quadrant, half) pairs are covered once by warps 1 .. 8
+        const int y = row0 + q4 * 32 + lane;
         const bool rowok = y < wh;
+        double* stg = reinterpret_cast<double*>(sm_tc) + (size_t)e * (2 * 32 * 17);   // [denom | wsum][row of the warp][17]
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;
-        const double* dn = c.denom + woff + (size_t)y * ww;
-        const double* ws = c.wsum + woff + (size_t)y * ww;
-        float* mp = c.params->keep_maps ? c.maps + woff + (size_t)y * ww : nullptr;
+        const double* dnb = c.denom + woff;
+        const double* wsb = c.wsum + woff;
+        float* mp = (c.params->keep_maps && rowok) ? c.maps + woff + (size_t)y * ww : nullptr;
         const int flat = t.flat;
         const double sc = (double)(1.0f / 255.0f) * t.tc_inv, dc = t.tc_dc;     // fl32(1/255): the ingest's own constant (utils.hpp:12)
         const int NW = g.AG * 8;
         unsigned long long key = 0ull;
-        for (int c0 = 0; c0 < NW; c0 += 16) {
+        for (int c0 = half * 16; c0 < NW; c0 += 32) {
+            // accumulator columns [c0, c0 + 16) = reversed candidate groups ga, ga - 1  ->  candidates [jb, jb + 16), jb = 8 (ga - 1)
+            const int jb = 8 * (g.AG - 2 - (c0 >> 3));
+            {
+                const int jc = min(jb + (lane & 15), ww - 1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {                      // a warp instruction covers two rows x 16 candidates (128 B each)
+                    const int r = 2 * i + (lane >> 4);
+                    const size_t o = (size_t)min(row0 + q4 * 32 + r, wh - 1) * ww + jc;
+                    cp_async8(stg + r * 17 + (lane & 15), dnb + o);
+                    cp_async8(stg + (32 + r) * 17 + (lane & 15), wsb + o);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             uint32_t hi[16], lo[16];
             const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
-            tc_ld16(ta + (uint32_t)NW, hi);                    // digit 1 accumulator
-            tc_ld16(ta, lo);                                   // digit 0
+            tc_ld16(ta + (uint32_t)NW, hi);                        // digit 1 accumulator
+            tc_ld16(ta, lo);                                       // digit 0
             tc_ld_wait();
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            double num[16], dn[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int jl = i < 8 ? 8 + i : i - 8;               // accumulator column -> position in the staged candidate range
+                const long long acc = (long long)(int)hi[i] * 256 + (long long)(int)lo[i];
+                const double cross = __dsub_rn(__dmul_rn((double)acc, sc), __dmul_rn(stg[(32 + lane) * 17 + jl], dc));
+                num[i] = (double)(float)cross;                      // the cross term is a float32 in cv::matchTemplate
+                dn[i] = stg[lane * 17 + jl];
+            }
+            float v[16];
+            if (flat == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = ncc_finalize_sel(num[i], dn[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = flat == 1 ? 1.0f : (float)(num[i] / dn[i]);   // 2: PVT_FORMULA_EPS, t > 0 always
+            }
             if (rowok) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int n = c0 + i, j = 8 * (g.AG - 1 - (n >> 3)) + (n & 7);   // accumulator column -> candidate x
+                    const int j = jb + (i < 8 ? 8 + i : i - 8);
                     if (j < ww) {
-                        const long long acc = (long long)(int)hi[i] * 256 + (long long)(int)lo[i];
-                        const double cross = __dsub_rn(__dmul_rn((double)acc, sc), __dmul_rn(__ldg(ws + j), dc));
-                        const float v = ncc_finalize((float)cross, __ldg(dn + j), flat);
-                        if (mp) mp[j] = v;
-                        const unsigned long long k2 = peak_key(v, (unsigned int)(y * ww + j));
+                        if (mp) mp[j] = v[i];
+                        const unsigned long long k2 = peak_key(v[i], (unsigned int)(y * ww + j));
                         key = k2 > key ? k2 : key;
                     }
                 }
             }
+            __syncwarp();                                          // the next chunk overwrites the staging rows
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {

@@ -463,8 +463,8 @@ int setup_tc(pvt_ctx* c)
     if (NW > 256 || g.KS > kTcKMax || g.rows > 256)
         return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: window width <= 256, template height <= 129 and window + template width <= 306 required");
     auto smem_of = [&](int stages) {
-        return (size_t)16 * g.rows * 2 * g.KS + (size_t)stages * 2 * g.nblk * 128 + ((((size_t)2 * d.mth * (kTcPadL + g.tpp + kTcPadR)) + 15) & ~(size_t)15) +
-               sizeof(uint64_t) * (2 + 2 * stages) + 64;
+        const size_t main_bytes = (size_t)16 * g.rows * 2 * g.KS + (size_t)stages * 2 * g.nblk * 128 + ((((size_t)2 * d.mth * (kTcPadL + g.tpp + kTcPadR)) + 15) & ~(size_t)15);
+        return std::max(main_bytes, (size_t)kTcEpiBytes) + sizeof(uint64_t) * (2 + 2 * stages) + 64;
     };
     g.stages = 4;
     while (g.stages > 2 && smem_of(g.stages) > kSmemBudget - 1024) --g.stages;
