@@ -51,7 +51,25 @@ struct TcCfg {
     int tpp;         // digit-row pitch in global memory (mtw rounded up to 16)
     int mtiles;      // ceil(Hmax / 128)
     int tmem_cols;   // power of two >= 2 * 8 * AG
+    int spin;        // 1: the ring's waits poll (mbarrier.test_wait) instead of suspending in try_wait
 };
+
+// ring waits: polling variant (the suspending try_wait of pvt_device.cuh wakes late when the producer / consumer chain is short)
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITP_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEP_%=;\n\t"
+        "bra WAITP_%=;\n\t"
+        "DONEP_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int spin)
+{
+    if (spin) mbar_wait_poll(bar, parity);
+    else mbar_wait(bar, parity);
+}
 
 // ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one()
@@ -244,7 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         if (trc && lane == 0) trc[TR_FRINGE * 2] = gtime();
         for (int dy = 0; dy < u_th; ++dy) {
             const int st = dy % g.stages;
-            mbar_wait(&full[st], (uint32_t)(dy / g.stages) & 1u);
+            tc_wait(&full[st], (uint32_t)(dy / g.stages) & 1u, g.spin);
             tc_fence_after();
             if (elect_one()) {
                 if (dy == 0) {
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         const int p = tid - 32;
         for (int dy = 0; dy < th; ++dy) {
             const int st = dy % g.stages;
-            if (dy >= g.stages) mbar_wait(&empty[st], (uint32_t)(dy / g.stages - 1) & 1u);
+            if (dy >= g.stages) tc_wait(&empty[st], (uint32_t)(dy / g.stages - 1) & 1u, g.spin);
             for (int i = p; i < 2 * nb * 8; i += kTcThreads - 32) {
                 const int dg = i / (nb * 8), r = i - dg * nb * 8;
                 const int d = dlo_c + (r >> 3), s = r & 7;

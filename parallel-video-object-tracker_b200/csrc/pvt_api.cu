@@ -467,6 +467,8 @@ int setup_tc(pvt_ctx* c)
         return std::max(main_bytes, (size_t)kTcEpiBytes) + sizeof(uint64_t) * (2 + 2 * stages) + 64;
     };
     g.stages = 4;
+    if (const char* e = getenv("PVT_TC_STAGES")) g.stages = std::max(2, std::min(16, atoi(e)));   // experiments
+    if (const char* e = getenv("PVT_TC_SPIN")) g.spin = atoi(e);
     while (g.stages > 2 && smem_of(g.stages) > kSmemBudget - 1024) --g.stages;
     c->tc_smem = smem_of(g.stages);
     if (c->tc_smem > kSmemBudget - 1024) return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: tile does not fit shared memory");

@@ -85,6 +85,15 @@ __device__ __forceinline__ void mma_f16_nomask(uint32_t d_tmem, uint64_t adesc, 
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void mma_i8_nomask(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(128) k_probe_rate(int M, Pattern pat, int reps
                         const uint32_t dcol = pat.distinct ? (uint32_t)((u & 1) * 256) : 0u;
                         if (f16 && (variant & 1)) mma_f16_nomask(tmem + dcol, ad + (uint64_t)(u & 3), bd + (uint64_t)(8 * (u & 3)), id, 1u);
                         else if (f16) mma_f16(tmem + dcol, ad + (uint64_t)(u & 3), bd + (uint64_t)(8 * (u & 3)), id, 1u);
+                        else if (variant & 1) mma_i8_nomask(tmem + dcol, ad + (uint64_t)(u & 3), bd + (uint64_t)(8 * (u & 3)), id, 1u);
                         else mma_i8(tmem + dcol, ad + (uint64_t)(u & 3), bd + (uint64_t)(8 * (u & 3)), id, 1u);
                     }
                 }
@@ -336,6 +346,9 @@ int main()
         {"i8  straight-line x8", 0, 4, 0, 128},
         {"i8  straight-line x8, waiters parked", 0, 6, 0, 128},
         {"i8  straight-line x8, parked, 2 accumulators", 0, 6, 1, 128},
+        {"i8  straight-line x8, parked, NO-MASK form", 0, 7, 0, 128},
+        {"i8  straight-line x8, parked, no-mask, 2 accum.", 0, 7, 1, 128},
+        {"i8  straight-line x8, parked, no-mask, M=64", 0, 7, 0, 64},
         {"i8  straight-line x8, parked, M=64", 0, 6, 0, 64},
         {"i8  straight-line x8, parked, SW128 layout type", 0, 14, 0, 128},
         {"f16 straight-line x8, parked, mask form", 1, 6, 0, 128},
@@ -343,7 +356,7 @@ int main()
     };
     for (auto& v : vs) {
         printf("  %-48s:", v.name);
-        for (int N : {16, 64, 128, 256}) {
+        for (int N : {16, 32, 64, 96, 128, 256}) {
             Pattern p{8, {N, N, N, N, N, N, N, N}, v.distinct};
             printf("  N=%d: %.1f", N, run_rate(sms, v.M, p, reps / 4, v.f16, nullptr, v.variant));
         }
