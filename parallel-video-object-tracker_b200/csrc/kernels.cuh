@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(256) k_rowsum(Ctx c, int pw /* doubles per pre
 struct StatCfg {
     int NX, NY;          // candidates per CTA along x (256 - (mtw - 1)) and along y
     int xtiles, ybands;  // CTAs per track = xtiles * ybands
+    int signal;          // != 0: every CTA that stored normalisers counts itself in TrackState.stats_done (k_step_fused waits for them)
 };
 constexpr int kStatThreads = 256;
 constexpr int kStatRowD = kStatThreads + kStatThreads / 8 + 2;   // doubles per padded row: element i at i + (i >> 3), i = 0 .. 256
@@ -597,6 +598,11 @@ __global__ void __launch_bounds__(kStatThreads, 3) k_winstats(Ctx c, StatCfg sc)
         __syncthreads();                                        // the next group overwrites the rows
     }
 #undef PH
+    if (sc.signal) {
+        __threadfence();                                        // this thread's normalisers are visible device-wide ...
+        __syncthreads();
+        if (tid == 0) atomicAdd(&t.stats_done, 1u);             // ... before the CTA counts as done
+    }
     if (tid == 0 && c.trace) atomicMax(&c.trace[((step % kRing) * 8 + TR_COLPREFIX) * 2 + 1], gtime());   // one kernel: one slot
 }
 
@@ -729,26 +735,12 @@ struct TileCfg {
     int cpt, n_full, n_tail, tail_ps;
 };
 
-template <int CY>
-__global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
+// The body of k_ncc_search (one CTA = 128 thread tiles of one track, or one K-split / tail part of them).  FUSED (k_step_fused):
+// a `return` only leaves this function -- the calling kernel goes on to the in-kernel second stage and the update.
+template <int CY, bool FUSED>
+__device__ __forceinline__ void ncc_search_body(const Ctx& c, const TileCfg& g, const CUtensorMap* tmap_p, unsigned char* sm_raw, TrackState& t,
+                                                unsigned long long step, int track, int blk, int part, int pj, int pd, int tail_k)
 {
-    extern __shared__ __align__(128) unsigned char sm_raw[];
-    // programmatic dependent launch: k_ncc_fringe (launched right behind this kernel in the throughput shape, and
-    // independent of its results) may start as soon as every CTA of this grid has been dispatched, i.e. it fills the
-    // SM slots that free up while the last round of search CTAs is still running
-    pdl_trigger();
-    int item = blockIdx.x, part = blockIdx.z, pj = g.pj, pd = g.pd, tail_k = -1;
-    if (g.tail_ps > 1 && item >= g.n_full) {           // a part of a tail item
-        tail_k = item - g.n_full;
-        item = g.n_full + tail_k / g.tail_ps;
-        part = tail_k - (tail_k / g.tail_ps) * g.tail_ps;
-        pj = g.tail_ps;
-        pd = 1;
-    }
-    const int track = item / g.cpt, blk = item - track * g.cpt;
-    TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
-    if (!track_stepped(c, t, step)) return;
     trace_begin(c, step, TR_NCC);
     // the window is derived here (not read from t.win): in K-split mode this kernel runs concurrently with the
     // statistics kernels, which are the ones that store it
@@ -810,7 +802,7 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         // the tile is fetched.  (Unsplit shape: launched behind k_rowsum, whose output only the epilogue needs: see below.)
         if (split) pdl_wait();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
-        tma_load_3d(s_tile, &tmap, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, tstream);
+        tma_load_3d(s_tile, tmap_p, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, tstream);
         for (int s = 0; s < 2 && s < nj; ++s) {
             mbar_arrive_expect_tx(&full[s], slice_bytes);
             bulk_load(s_templ + (size_t)s * sstride, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
@@ -956,6 +948,151 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g
         if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
     }
     trace_end(c, step, TR_NCC);
+}
+
+template <int CY>
+__global__ void __launch_bounds__(kTilesPerCta, 2) k_ncc_search(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    // programmatic dependent launch: k_ncc_fringe (launched right behind this kernel in the throughput shape, and
+    // independent of its results) may start as soon as every CTA of this grid has been dispatched, i.e. it fills the
+    // SM slots that free up while the last round of search CTAs is still running
+    pdl_trigger();
+    int item = blockIdx.x, part = blockIdx.z, pj = g.pj, pd = g.pd, tail_k = -1;
+    if (g.tail_ps > 1 && item >= g.n_full) {           // a part of a tail item
+        tail_k = item - g.n_full;
+        item = g.n_full + tail_k / g.tail_ps;
+        part = tail_k - (tail_k / g.tail_ps) * g.tail_ps;
+        pj = g.tail_ps;
+        pd = 1;
+    }
+    const int track = item / g.cpt, blk = item - track * g.cpt;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    ncc_search_body<CY, false>(c, g, &tmap, sm_raw, t, step, track, blk, part, pj, pd, tail_k);
+}
+
+// (3b') k_step_fused: search + second stage + update of the K-split (single-stream latency) shape in ONE launch.
+//   The K-split step used to be k_ncc_search -> k_ncc_finalize (whose last CTA runs the update): a kernel boundary and a second
+//   preamble on the critical path of every frame.  Here the search CTAs of a track (all co-resident: the planner only picks
+//   this kernel when they fit one wave with room to spare) store their partial cross terms, meet at an arrival counter, wait for
+//   the statistics kernel's completion count (k_winstats runs beside this kernel on a parallel graph branch), then EVERY CTA
+//   reduces a slice of the track's thread tiles in part order (coalesced float4 reads of the tile-major partial sums),
+//   normalises, and feeds the peak; the last CTA through the ticket runs track_update.  Spins are bounded (a device that
+//   cannot co-schedule the grid raises Ctx.fault -> PVT_ERR_CUDA at the next host sync instead of hanging).
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int target)
+{
+    if (ld_acquire_u32(p) >= target) return true;
+    const unsigned long long t0 = gtime();
+    while (ld_acquire_u32(p) < target)
+        if (gtime() - t0 > 200000000ull) return false;      // 0.2 s: six orders of magnitude above a step
+    return true;
+}
+
+template <int CY>
+__global__ void __launch_bounds__(kTilesPerCta, 2) k_step_fused(Ctx c, TileCfg g, const __grid_constant__ CUtensorMap tmap, StatCfg sc)
+{
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    __shared__ double red[64];
+    __shared__ int s_last;
+    pdl_trigger();
+    const int parts = g.pj * g.pd, nbx = g.n_full;                  // K-split plans have no tail items
+    const int item = blockIdx.x % nbx, part = blockIdx.x / nbx;
+    const int track = item / g.cpt, blk = item - track * g.cpt;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    const bool stepped = track_stepped(c, t, step);
+    const int n_ctas = g.cpt * parts;                               // CTAs of this track
+    const int tid = threadIdx.x;
+    if (stepped) {
+        ncc_search_body<CY, true>(c, g, &tmap, sm_raw, t, step, track, blk, part, g.pj, g.pd, -1);
+        pdl_wait();                                                  // every thread: the ingest's gray plane (the EMA reads it) is visible
+        int win[4];
+        {
+            const DevParams P = *c.params;
+            search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+        }
+        const int ww = win[2], wh = win[3];
+        __threadfence();                                             // this thread's partial sums are visible device-wide ...
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&t.arrive, 1u);                                // ... before the CTA counts as arrived
+            const unsigned int n_stat = (unsigned int)(((ww + sc.NX - 1) / sc.NX) * ((wh + sc.NY - 1) / sc.NY));
+            if (!spin_until(&t.arrive, (unsigned int)n_ctas) || !spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
+        }
+        __syncthreads();
+        trace_begin(c, step, TR_FINALIZE);
+        // second stage: units of one float4 (4 candidates of one row of a thread tile); CTA k takes units [k U, (k + 1) U)
+        const int tiles_track = g.cpt * kTilesPerCta, U_total = tiles_track * 2 * CY;
+        const int k = part * g.cpt + blk, U = (U_total + n_ctas - 1) / n_ctas;
+        const size_t plane4 = (size_t)c.max_tracks * tiles_track * (2 * CY);      // float4 per part
+        const float4* pbase = reinterpret_cast<const float4*>(c.partial) + (size_t)track * tiles_track * (2 * CY);
+        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+        const double* dn = c.denom + woff;
+        float* mp = c.params->keep_maps ? c.maps + woff : nullptr;
+        const int flat = t.flat;
+        unsigned long long key = 0ull;
+        for (int u = k * U + tid; u < min((k + 1) * U, U_total); u += kTilesPerCta) {
+            const int tile = u / (2 * CY), r = u - tile * (2 * CY), i = r >> 1, half = r & 1;
+            const int tb = tile / kTilesPerCta, band = tb / g.ctas_band, q = (tb - band * g.ctas_band) * kTilesPerCta + (tile - tb * kTilesPerCta);
+            const int col = q / g.GB, grp = band * g.GB + (q - col * g.GB);
+            const int y = grp * CY + i, x0 = col * 8 + half * 4;
+            if (col < g.C && x0 < ww && grp < g.G && y < wh) {
+                const float4* src = pbase + (size_t)tile * (2 * CY) + r;
+                double d4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d4[e] = x0 + e < ww ? __ldcg(dn + (size_t)y * ww + x0 + e) : 0.0;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p0 = 0; p0 < parts; p0 += 16) {             // 16 independent 16-byte loads in flight, added in part order
+                    float4 pv[16];
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) pv[b] = p0 + b < parts ? __ldcg(src + (size_t)(p0 + b) * plane4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int b = 0; b < 16; ++b)
+                        if (p0 + b < parts) { acc.x += pv[b].x; acc.y += pv[b].y; acc.z += pv[b].z; acc.w += pv[b].w; }
+                }
+                const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (x0 + e < ww) {
+                        const unsigned int idx = (unsigned int)(y * ww + x0 + e);
+                        const float v = ncc_finalize(a4[e], d4[e], flat);
+                        if (mp) mp[idx] = v;
+                        const unsigned long long k2 = peak_key(v, idx);
+                        key = k2 > key ? k2 : key;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            unsigned long long o = shfl_xor_u64(key, m);
+            key = o > key ? o : key;
+        }
+        if ((tid & 31) == 0 && key) atomicMax(&t.peak, key);
+    }
+    // the last CTA of this track (all peaks are in) performs the gate / EMA / state update
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int k = atomicAdd(&t.ticket, 1u);
+        s_last = (k == (unsigned int)n_ctas - 1u);
+        if (s_last) { t.ticket = 0u; t.arrive = 0u; t.stats_done = 0u; }   // everybody is past the waits
+    }
+    __syncthreads();
+    if (stepped) trace_end(c, step, TR_FINALIZE);
+    if (!s_last) return;
+    __threadfence();
+    if (c.trace && tid == 0) c.trace[((step % kRing) * 8 + TR_UPDATE) * 2] = gtime();
+    track_update(c, track, step, stepped, reinterpret_cast<float*>(sm_raw), red);
+    trace_end(c, step, TR_UPDATE);
 }
 
 // (3c) k_ncc_fringe: the candidates the thread-tile grid leaves out (TileCfg: the single column x = 8C and/or the
@@ -1336,7 +1473,7 @@ __global__ void __launch_bounds__(256) k_track_init(Ctx c, int track, int stream
         sm_f[i] = v;
     }
     if (threadIdx.x == 0) {
-        t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull; t.ticket = 0u;
+        t.active = 1; t.stream = stream; t.x = x; t.y = y; t.w = w; t.h = h; t.peak = 0ull; t.ticket = 0u; t.arrive = 0u; t.stats_done = 0u;
         t.lost_count = 0; t.use_global = 0; t.global_since = 0ull;
         t.win[0] = t.win[1] = t.win[2] = t.win[3] = 0;
     }
@@ -1543,6 +1680,7 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         }
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
+            t.arrive = 0u; t.stats_done = 0u;                   // k_winstats may count (StatCfg.signal) although this step's kernels did not wait
             if (c.lost_mode) {
                 // tracker_ghc/src/main.cpp:213-239: found -> reset the counter and go back to the local search (the box
                 // comes from a map position, so it is never outside the frame); else count the frame as lost.

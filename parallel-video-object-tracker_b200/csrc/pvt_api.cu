@@ -61,6 +61,8 @@ struct Pass {
     int rowsum_warps = 8, rowsum_pw = 0;
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     StatCfg stat{};            // k_winstats (one statistics kernel); NX == 0: the two-kernel statistics (k_colprefix + k_rowsum)
+    bool fused = false;        // K-split shape: k_step_fused (search + second stage + update in one launch) instead of k_ncc_search -> k_ncc_finalize
+    size_t fused_smem = 0;
     FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
@@ -88,6 +90,9 @@ struct pvt_ctx {
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest (pvt_params.ingest)
     int colprefix_chunks = 8;  // row chunks per 32-column strip in k_colprefix (blockDim.y)
     StatCfg stat{};            // k_winstats geometry (NX == 0: two-kernel statistics)
+    bool fused = false;        // k_step_fused (see Pass)
+    size_t fused_smem = 0;
+    unsigned int* h_fault = nullptr;   // mapped pinned word behind Ctx.fault
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;   // aux*: further branches inside the captured graph
     cudaEvent_t ev_join3 = nullptr;
@@ -296,8 +301,9 @@ int raise_smem(const void* fn, size_t bytes)
 int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
 
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
-int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st)
+int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false)
 {
+    if (fused) return 3;   // ingest, k_winstats, k_step_fused
     return (st.NX > 0 ? 3 : 4) + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
 
@@ -305,7 +311,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st)
 int kernels_per_step(const pvt_ctx* c)
 {
     // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
-    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat);
+    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused);
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -413,6 +419,24 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
                 if (cost < best) { best = cost; NY = ny; }
             }
             p.stat = StatCfg{NX, NY, xt, (d.Hmax + NY - 1) / NY};
+        }
+    }
+    // k_step_fused: the K-split step in one launch.  Its CTAs wait for each other inside the kernel, so every search CTA of
+    // the context must be resident at once, with room left for the statistics kernel beside them: at most one search CTA per
+    // SM on average (two fit), no fringe kernel, no lost-object pass, and the update's template must fit the CTA's shared memory.
+    p.fused = false;
+    p.fused_smem = std::max(p.ncc_smem, (size_t)d.mth * d.mtw * sizeof(float));
+    {
+        // Measured on B200 (C2, round 2): 34.0 us per step against 26.3 us for k_ncc_search -> k_ncc_finalize -- the kernel boundary
+        // it removes costs less than what it adds: a 128-thread update (10.2 us instead of 5.6 with 256 threads) and a second stage
+        // in which only ~54 threads per CTA have work (5.4 us instead of 3.1).  Kept behind PVT_FUSED=1, with its parity tests.
+        const char* nf = getenv("PVT_FUSED");
+        const long long search_ctas = (long long)d.max_tracks * p.tile.cpt * p.tile.pj * p.tile.pd;
+        if (allow_env && (nf && *nf == '1') && c->params.kernel == PVT_KERNEL_AUTO && !c->lost_mode && p.tile.pj * p.tile.pd > 1 &&
+            p.fringe.colg + p.fringe.rowg == 0 && p.stat.NX > 0 && search_ctas <= sm_count && p.fused_smem + 1024 <= kSmemBudget) {
+            p.fused = true;
+            p.stat.signal = 1;
+            { int r_ = raise_smem((const void*)k_step_fused<kCY>, p.fused_smem); if (r_) return r_; }
         }
     }
     return encode_tmap(p.d, p.tile, &p.tmap);
@@ -569,7 +593,7 @@ Pass local_pass(const pvt_ctx* c)
 {
     Pass p;
     p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
-    p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
+    p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fused = c->fused; p.fused_smem = c->fused_smem; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
     return p;
 }
 Pass global_pass(const pvt_ctx* c)
@@ -697,6 +721,21 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         // (K-split shape: the search directly follows the ingest on this stream and waits for it before fetching its tile.
         //  Unsplit shape: a plain dependency on k_rowsum -- starting the search during the statistics' tail was measured and
         //  lost 4 % on C4: k_ncc_fringe then has to wait for the whole search grid before it may read the normalisers)
+        const bool fused = p.fused && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass;
+        if (fused) {
+            // search + second stage + update in one launch; it waits for k_winstats (the other branch) through TrackState.stats_done
+            { int r = launch_pdl(k_step_fused<kCY>, dim3(nbx * (unsigned)parts), dim3(kTilesPerCta), p.fused_smem, c->compute, pdl && fork, d, p.tile, p.tmap, p.stat); if (r) return r; }
+            if (profile) {
+                for (int w = 0; w < 2; ++w) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
+                { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
+                { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
+            }
+            if (fork) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));   // the statistics branch ends inside this step
+            { int r = dbg(c, "k_step_fused"); if (r) return r; }
+            if (join3) CK(cudaStreamWaitEvent(c->compute, c->ev_join3, 0));
+            CK(cudaGetLastError());
+            return PVT_OK;
+        }
         { int r = launch_pdl(k_ncc_search<kCY>, dim3(nbx, 1, parts), dim3(kTilesPerCta), p.ncc_smem, c->compute, pdl && fork, d, p.tile, p.tmap); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (fringe_after) {
@@ -1124,6 +1163,7 @@ int pvt_destroy(pvt_ctx* c)
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_table) cudaFreeHost(c->h_table);
     if (c->h_results) cudaFreeHost(c->h_results);
+    if (c->h_fault) cudaFreeHost(c->h_fault);
     for (int i = 0; i < kRing; ++i) if (c->table_ev[i]) cudaEventDestroy(c->table_ev[i]);
     for (int i = 0; i < kStageDepth; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -1247,6 +1287,9 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
     d.macs_grid = d.macs + 1;
     c->d_macs = d.macs;
     CR(dev_alloc(c, &c->d_trace, (size_t)kRing * 16));
+    CKD(cudaHostAlloc((void**)&c->h_fault, 64, cudaHostAllocMapped));
+    *c->h_fault = 0u;
+    CKD(cudaHostGetDevicePointer((void**)&d.fault, c->h_fault, 0));
     CKD(cudaHostAlloc((void**)&c->h_table, sizeof(FrameDesc) * kRing * d.max_streams, cudaHostAllocDefault));
     CKD(cudaHostAlloc((void**)&c->h_results, sizeof(pvt_result) * kRing * d.max_tracks, cudaHostAllocDefault));
     for (int i = 0; i < kRing; ++i) CKD(cudaEventCreateWithFlags(&c->table_ev[i], cudaEventDisableTiming));
@@ -1277,7 +1320,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         lp.d = c->d;
         CR(build_plan(c, lp, prop.multiProcessorCount, params->ingest, true));
         c->d = lp.d; c->tile = lp.tile; c->tmap = lp.tmap; c->ncc_smem = lp.ncc_smem; c->rowsum_warps = lp.rowsum_warps;
-        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->stat = lp.stat; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
+        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->stat = lp.stat; c->fused = lp.fused; c->fused_smem = lp.fused_smem; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
         c->roi_ingest = lp.roi_ingest;
     }
     c->kps = kernels_per_step(c);
@@ -1332,12 +1375,22 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
     return upload_params(c);
 }
 
+// a bounded device-side wait gave up (k_step_fused could not see all its CTAs / the statistics arrive): report it, once
+#define FAULT_CHECK(c)                                                                                                        \
+    do {                                                                                                                      \
+        if ((c)->h_fault && *(volatile unsigned int*)(c)->h_fault) {                                                           \
+            *(c)->h_fault = 0u;                                                                                               \
+            return fail(PVT_ERR_CUDA, "k_step_fused: an in-kernel wait timed out (grid not co-scheduled); results of this step are invalid"); \
+        }                                                                                                                     \
+    } while (0)
+
 int pvt_sync(pvt_ctx* c)
 {
     if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->copy));
     CK(cudaStreamSynchronize(c->compute));
+    FAULT_CHECK(c);
     return PVT_OK;
 }
 
@@ -1630,6 +1683,7 @@ int pvt_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, pvt_result* resu
     } else {
         CK(cudaStreamSynchronize(c->compute));
     }
+    FAULT_CHECK(c);
     return PVT_OK;
 }
 

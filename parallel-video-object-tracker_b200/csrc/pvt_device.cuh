@@ -58,7 +58,9 @@ struct TrackState {
     double mean, templ_norm;   // mean_t, sigma_t * sqrt(N)   (EPS formula: (fl32(sigma_t + 1e-6) + 1e-6) * N)
     unsigned long long peak;   // packed (ordered score << 32 | ~index); 0 = empty
     int win[4];                // minTx, minTy, width, height of the current search window
-    unsigned int ticket;       // CTAs of k_ncc_finalize that are done with this track (last one runs the update)
+    unsigned int ticket;       // CTAs of k_ncc_finalize / k_step_fused that are done with this track (last one runs the update)
+    unsigned int arrive;       // k_step_fused: search CTAs of this track whose partial cross terms are stored (in-kernel barrier)
+    unsigned int stats_done;   // k_step_fused: k_winstats CTAs of this track that have stored their normalisers in this step
     // lost-object re-acquisition (tracker_ghc/src/main.cpp:143-144, 183-239); only used when Ctx.lost_mode != 0
     int lost_count;            // consecutive frames below the confidence threshold (lost_frame_count)
     int use_global;            // use_global_search: the track is searched over the whole frame ...
@@ -114,6 +116,7 @@ struct Ctx {
     unsigned long long* macs;  // algorithmic MACs searched so far (n_cand * tw * th per track per step)
     unsigned long long* macs_grid;  // the share of them inside k_ncc_search's thread-tile grid (gridW x gridH candidates)
     int gridW, gridH;          // 8 * TileCfg.C, kCY * TileCfg.G
+    unsigned int* fault;       // mapped host word: a bounded device-side wait gave up (k_step_fused) -> the next host sync returns PVT_ERR_CUDA
     unsigned long long* trace; // optional [kRing][8 kernels][2] globaltimer stamps (first CTA start, last CTA end); NULL = off
 };
 

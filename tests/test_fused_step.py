@@ -1,0 +1,122 @@
+"""k_step_fused -- the K-split (single-stream latency) step in ONE launch: search CTAs store their partial cross terms, meet at an
+in-kernel arrival counter, wait for k_winstats' completion count, reduce the parts in the same fixed order as k_ncc_finalize,
+and the last CTA runs the update (opt-in, PVT_FUSED=1: measured slower than the two-kernel path on B200, see csrc/pvt_api.cu).
+Same arithmetic in the same order as the two-kernel path, so everything
+must be BIT-identical to it, and identical to the cv2 goldens like every other path.
+Reference semantics: tracker/src/main.cpp:135-161."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as Hp
+from tools import synth
+
+pvt = importlib.import_module("parallel-video-object-tracker_b200")
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        for k, v in self.kw.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def run_clip(frames, roi, R, fused, n_tracks=1, keep_maps=0):
+    H, W = frames.shape[1:3]
+    with env(PVT_FUSED="1" if fused else None):
+        with pvt.Tracker(W, H, roi[2], roi[3], max_tracks=n_tracks, keep_maps=keep_maps, search_radius_x=R, search_radius_y=R) as tr:
+            for t in range(n_tracks):
+                tr.init_track(t, frames[0] if t == 0 else None, (roi[0] + 3 * t, roi[1] + 2 * t, roi[2], roi[3]))
+            l0 = tr.launch_count()
+            recs, maps = [], []
+            for k in range(1, len(frames)):
+                recs.append(tr.step([frames[k]]).copy())
+                if keep_maps:
+                    maps.append([tr.window_map(t)[0].copy() for t in range(n_tracks)])
+            per_step = (tr.launch_count() - l0) / (len(frames) - 1)
+            templ = [tr.get_state(t)[1].copy() for t in range(n_tracks)]
+    return np.stack(recs), maps, templ, per_step
+
+
+def records_of(res):
+    return np.stack([res["x"], res["y"], res["w"], res["h"], res["conf"].astype(np.float64), res["moved"], res["updated"]], 1).astype(np.float64)
+
+
+@pytest.mark.parametrize("name", ["small", "lowtex", "lost", "fade", "border", "flat", "oddsize", "c1_standin", "c2_1080p"])
+def test_fused_clip_vs_cv2_golden_and_two_kernel_path(name):
+    (c, tk) = Hp.clip(name)
+    g = Hp.golden(f"clip_{name}.npz")
+    R = tk.get("rx", 80)
+    if tk.get("ry", R) != R:
+        pytest.skip("unequal radii: covered by the random-geometry sweep")
+    frames, roi = c["frames"], c["roi"]
+    a, _, ta, ka = run_clip(frames, roi, R, True)
+    b, _, tb, kb = run_clip(frames, roi, R, False)
+    # ingest + k_winstats + k_step_fused   vs   ... + k_ncc_search + k_ncc_finalize.  (The planner only fuses when every search
+    # CTA fits one wave with room to spare: always for the headline 1080p geometry, not for every small clip.)
+    assert kb == 4 and ka in (3, 4) and (ka == 3 or name != "c2_1080p"), (ka, kb)
+    for f in ("x", "y", "moved", "updated", "searched", "valid"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(a["conf"].view(np.uint32), b["conf"].view(np.uint32))       # same sums in the same order: same bits
+    assert np.array_equal(ta[0], tb[0])
+    Hp.check_records(records_of(a[:, 0]), g["records"], name + " (fused)")
+    assert np.array_equal(ta[0], g["templ"]), f"{name}: final template not bit-identical to the golden"
+
+
+@pytest.mark.parametrize("W,H,tw,th,R,n_tracks", [(320, 240, 32, 32, 80, 1), (640, 480, 48, 40, 60, 2), (1920, 1080, 64, 64, 80, 1),
+                                                  (400, 300, 24, 24, 100, 1), (1280, 720, 64, 64, 80, 2)])
+def test_fused_maps_bit_identical_to_two_kernel_path(W, H, tw, th, R, n_tracks):
+    c = synth.make_clip(synth.ClipSpec(seed=11 + tw + n_tracks, W=W, H=H, tw=tw, th=th, n_frames=5, R=R))
+    frames, roi = c["frames"], c["roi"]
+    a, ma, ta, ka = run_clip(frames, roi, R, True, n_tracks, keep_maps=1)
+    b, mb, tb, kb = run_clip(frames, roi, R, False, n_tracks, keep_maps=1)
+    assert kb >= 4
+    if ka != 3:
+        pytest.skip("the planner did not choose k_step_fused for this geometry (%s kernels per step)" % ka)
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(a["conf"].view(np.uint32), b["conf"].view(np.uint32))
+    for k in range(len(ma)):
+        for t in range(n_tracks):
+            assert np.array_equal(ma[k][t].view(np.uint32), mb[k][t].view(np.uint32)), (k, t)
+    for t in range(n_tracks):
+        assert np.array_equal(ta[t], tb[t])
+
+
+def test_fused_async_sequence_and_inactive_track():
+    """resident frame ring through pvt_submit_sequence (multi-step graphs), one of two track slots never initialised"""
+    c = synth.make_clip(synth.ClipSpec(seed=5, W=640, H=480, tw=32, th=32, n_frames=20, R=80, period=20))
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    out = {}
+    for fused in (True, False):
+        with env(PVT_FUSED="1" if fused else None):
+            with pvt.Tracker(W, H, 32, 32, max_tracks=2, search_radius_x=80, search_radius_y=80) as tr:
+                tr.init_track(0, frames[0], roi)
+                ring = [[pvt.host_frame(frames[(k + 1) % 20])] for k in range(20)]
+                res = tr.submit_sequence(40, ring, collect_every=20, want_results=True)
+                tr.sync()
+                out[fused] = (np.array(res), tr.get_state(0)[1].copy())
+    a, b = out[True], out[False]
+    for f in ("x", "y", "moved", "updated", "searched", "valid"):
+        assert np.array_equal(a[0][f], b[0][f]), f
+    assert np.array_equal(a[0]["conf"][:, 0].view(np.uint32), b[0]["conf"][:, 0].view(np.uint32))
+    assert np.array_equal(a[1], b[1])
+    truth = c["truth"]
+    for i in range(40):
+        assert (a[0][i][0]["x"], a[0][i][0]["y"]) == tuple(truth[(i + 1) % 20]), i
+        assert a[0][i][1]["valid"] == 0
