@@ -803,6 +803,7 @@ __device__ __forceinline__ void ncc_search_body(const Ctx& c, const TileCfg& g, 
         if (split) pdl_wait();
         mbar_arrive_expect_tx(&bars[0], (uint32_t)(g.boxW * g.boxH) * 4u);
         tma_load_3d(s_tile, tmap_p, &bars[0], win[0] - xs + (c_lo + j0) * 8, win[1] + row0 + d0, tstream);
+        if (split && c.trace && blockIdx.x == 0 && part == 0) c.trace[((step % kRing) * 8 + TR_FRINGE) * 2] = gtime();      // K-split phase stamps of CTA 0:
         for (int s = 0; s < 2 && s < nj; ++s) {
             mbar_arrive_expect_tx(&full[s], slice_bytes);
             bulk_load(s_templ + (size_t)s * sstride, gtempl + ((size_t)(j0 + s) * th + d0) * 8, slice_bytes, &full[s]);
@@ -823,6 +824,8 @@ __device__ __forceinline__ void ncc_search_body(const Ctx& c, const TileCfg& g, 
     }
 
     const float* base = s_tile + (size_t)(gl * CY) * P + (col - c_lo) * 8;
+    const bool stamp = split && c.trace && blockIdx.x == 0 && part == 0 && threadIdx.x == 0;   // tile requested | landed, loop done | partial sums stored
+    if (stamp) c.trace[((step % kRing) * 8 + TR_FRINGE) * 2 + 1] = gtime();
 
     float acc[CY][8];
 #pragma unroll
@@ -894,6 +897,7 @@ __device__ __forceinline__ void ncc_search_body(const Ctx& c, const TileCfg& g, 
     }
 
     unsigned long long key = 0ull;
+    if (stamp) c.trace[((step % kRing) * 8 + TR_TAIL) * 2] = gtime();
     if (active) {
         const size_t woff = (size_t)track * c.Hmax * c.Wmax;
         if (split) {
@@ -947,6 +951,7 @@ __device__ __forceinline__ void ncc_search_body(const Ctx& c, const TileCfg& g, 
         }
         if ((threadIdx.x & 31) == 0 && key) atomicMax(&t.peak, key);
     }
+    if (stamp) c.trace[((step % kRing) * 8 + TR_TAIL) * 2 + 1] = gtime();
     trace_end(c, step, TR_NCC);
 }
 
@@ -1095,6 +1100,268 @@ __global__ void __launch_bounds__(kTilesPerCta, 2) k_step_fused(Ctx c, TileCfg g
     trace_end(c, step, TR_UPDATE);
 }
 
+__device__ __forceinline__ void cp_async4(float* dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// (3b'') k_ncc_local: the single-stream (latency) search with the K-split INSIDE the CTA -- no partial sums in global memory, no
+//   second-stage kernel, no statistics kernel.  A CTA owns a patch of 8 x (CY * TR) candidates of one track (TR thread tiles
+//   stacked in y) and holds everything the patch needs in shared memory: its (CY*TR + th - 1) x (8 + tp) corner of the gray
+//   plane and the whole centred template.  Thread = (thread tile tr, row part pdx, chunk part pjx): the same 8 x CY register
+//   tile, loop and accumulation order as a K-split part of k_ncc_search (part = pdx * PJ + pjx covers template rows
+//   [th pdx / PD, th (pdx+1) / PD) of chunks [nchunk pjx / PJ, ...)), so the scores are BIT-identical to the K-split path with
+//   pj = PJ, pd = PD.  The parts meet in shared memory and are added in part order; before the loop all warps compute the
+//   patch's window statistics from the same tile (FP64 column sums sliding down, then added along x: wsum exact, wsq to
+//   ~1e-15 like k_winstats) -- the normalisers never leave the SM.  Per step: k_ingest_roi ~> k_ncc_local -> k_update.
+//   Why: measured on B200 (C2), a K-split search CTA spends 8.9 of its 12 us in the FMA loop because ONE warp per scheduler
+//   issues an FFMA only every ~2.4 cycles (two co-resident warps reach 87 % of the pipe); here every SM runs 8 warps, and the
+//   3 us second stage plus a kernel boundary disappear.
+struct LocalCfg {
+    int TR;              // thread tiles (of CY candidate rows) per CTA; the patch is 8 x CY*TR candidates
+    int PJ, PD;          // parts inside the CTA along the template's 8-column chunks and along its rows
+    int bx, by;          // CTAs per track along x (ceil(Wmax / 8)) and y (ceil(ceil(Hmax / CY) / TR))
+    int P;               // tile pitch in floats (8 + mtp rounded up to == 4 mod 8)
+    int tileH;           // CY * TR + mth - 1
+    int TS;              // template chunk stride in floats (mth * 8 + 4)
+    int nfma;            // TR * PJ * PD threads run the FMA loop (the CTA is that rounded up to a warp)
+};
+constexpr int kLocalRed = 8 * kCY + 4;   // floats per thread in the reduction buffer (44: conflict-free float4 stores)
+
+template <int CY>
+__global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
+{
+    extern __shared__ __align__(16) unsigned char sm_loc[];
+    pdl_trigger();
+    const int per_track = g.bx * g.by;
+    const int track = blockIdx.x / per_track, b = blockIdx.x - track * per_track;
+    const int byi = b / g.bx, bxi = b - byi * g.bx;
+    TrackState& t = c.tracks[track];
+    const unsigned long long step = *c.step;
+    if (!track_stepped(c, t, step)) return;
+    trace_begin(c, step, TR_NCC);
+    int win[4];
+    {
+        const DevParams P = *c.params;
+        search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    }
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (b == 0 && tid < 4) t.win[tid] = win[tid];               // k_update reads it (k_colprefix / k_winstats store it in the other shapes)
+    const int ww = win[2], wh = win[3], tw = t.w, th = t.h, tp = t.tp, nchunk = tp >> 3;
+    const int px0 = 8 * bxi, py0 = CY * g.TR * byi;               // patch origin inside the window
+    if (px0 >= ww || py0 >= wh) return;                           // clamped window: CTA-uniform
+    const int nrow = min(CY * g.TR, wh - py0);                    // candidate rows of this patch
+    const int P = g.P;
+    float* s_tile = reinterpret_cast<float*>(sm_loc);             // [tileH][P]
+    float* s_t = s_tile + (size_t)g.tileH * P;                    // [chunks][TS]
+    float* s_red = s_t + (size_t)(c.mtp >> 3) * g.TS;             // [nfma][44] partial sums; before that: the statistics warp's scratch
+    double* s_dn = reinterpret_cast<double*>(s_red + (size_t)g.nfma * kLocalRed);   // [CY * TR * 8] normalisers
+    pdl_wait();                                                    // the ingest's gray plane is complete
+    {
+        // tile: rows [py0, py0 + nrow + th - 1), columns [px0, px0 + 8 + tp) of the window's corner of the gray plane.  The window
+        // origin has no alignment: aligned 16-byte loads from the origin rounded down to 4 pixels, scattered as scalars (the
+        // shift costs nothing); zeros outside the frame (they only meet masked candidates / zero template columns)
+        const int ax0 = win[0] + px0, ay0 = win[1] + py0, tw_used = 8 + tp, th_used = nrow + th - 1;
+        const int gx0 = ax0 & ~3, nvec = (ax0 + tw_used - gx0 + 3) >> 2;
+        const float* src = c.gray + (size_t)t.stream * c.plane + (size_t)ay0 * c.pitch + gx0;
+        const int total = th_used * nvec;
+        for (int i0 = tid; i0 < total; i0 += 4 * (int)blockDim.x) {
+            float4 v[4];
+            int rr[4], xx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                          // four independent loads in flight per thread
+                const int i = i0 + k * (int)blockDim.x;
+                rr[k] = -1;
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) {
+                    const int r = i / nvec, q = i - r * nvec;
+                    rr[k] = r; xx[k] = gx0 + 4 * q;
+                    if (ay0 + r < c.H && xx[k] + 4 <= c.pitch) v[k] = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * c.pitch) + q);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (rr[k] >= 0) {
+                    const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int x = xx[k] + e - ax0;
+                        if (x >= 0 && x < tw_used) s_tile[rr[k] * P + x] = (xx[k] + e < c.W) ? e4[e] : 0.f;
+                    }
+                }
+            }
+        }
+        const float4* tsrc = reinterpret_cast<const float4*>(c.templc + (size_t)track * c.mth * c.mtp);
+        const int nq = th * 2;                                     // float4 per chunk
+        for (int i = tid; i < nchunk * nq; i += blockDim.x) {
+            const int j = i / nq, q = i - j * nq;
+            cp_async16(reinterpret_cast<float4*>(s_t + (size_t)j * g.TS) + q, tsrc + (size_t)j * nq + q);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // phase stamps of CTA 0 (pvt_trace_enable; tools/timeline.py): FRINGE slot = staged | FMA loop done, TAIL slot = statistics done | reduced
+    unsigned long long* trc = (c.trace && blockIdx.x == 0) ? c.trace + (step % kRing) * 16 : nullptr;
+    if (trc && tid == 0) trc[TR_FRINGE * 2] = gtime();
+
+    {
+        // ---- the patch's window statistics from the tile in shared memory, by all warps (scratch: the reduction buffer, which is
+        // unused until barrier A).  FP64 adds have ~40 cycles of latency here and one warp issues them slowly (a dedicated
+        // statistics warp beside the FMA loop took 10 - 13 us), so the work is cut into short chains over all 256 threads:
+        // (1) three partial column sums per tile column, (2) the column's box sum sliding down the patch's candidate rows,
+        // (3) one thread per candidate adds its tw column sums with four accumulators and applies OpenCV's normaliser.
+        const int ncol = 8 + tw - 1, seg = (th + 2) / 3;
+        double* cS = reinterpret_cast<double*>(s_red);            // [nrow][ncol] vertical box sums of f
+        double* cQ = cS + (size_t)nrow * ncol;                     // ... of f^2
+        double* part = cQ + (size_t)nrow * ncol;                   // [3][ncol][2]
+        for (int w = tid; w < 3 * ncol; w += blockDim.x) {
+            const int sgi = w / ncol, col = w - sgi * ncol, r0 = sgi * seg, r1 = min(th, r0 + seg);
+            double S0 = 0.0, S1 = 0.0, Q0 = 0.0, Q1 = 0.0;
+            int r = r0;
+            for (; r + 1 < r1; r += 2) {
+                const double a = (double)s_tile[r * P + col], b2 = (double)s_tile[(r + 1) * P + col];
+                S0 += a; Q0 += a * a;
+                S1 += b2; Q1 += b2 * b2;
+            }
+            if (r < r1) { const double a = (double)s_tile[r * P + col]; S0 += a; Q0 += a * a; }
+            part[(size_t)w * 2] = S0 + S1;
+            part[(size_t)w * 2 + 1] = Q0 + Q1;
+        }
+        __syncthreads();
+        if (trc && tid == 0) trc[TR_COLPREFIX * 2] = gtime();
+        for (int col = tid; col < ncol; col += blockDim.x) {
+            double S = part[(size_t)col * 2] + part[(size_t)(ncol + col) * 2] + part[(size_t)(2 * ncol + col) * 2];
+            double Q = part[(size_t)col * 2 + 1] + part[(size_t)(ncol + col) * 2 + 1] + part[(size_t)(2 * ncol + col) * 2 + 1];
+            for (int y = 0; y < nrow; ++y) {
+                cS[(size_t)y * ncol + col] = S;
+                cQ[(size_t)y * ncol + col] = Q;
+                if (y + 1 < nrow) {
+                    const double di = (double)s_tile[(y + th) * P + col], dq = (double)s_tile[y * P + col];
+                    S += di - dq;                                 // exact: sums of u8-sourced f fit a double (k_winstats)
+                    Q += di * di - dq * dq;
+                }
+            }
+        }
+        __syncthreads();
+        if (trc && tid == 0) trc[TR_COLPREFIX * 2 + 1] = gtime();
+        const double invArea = 1.0 / ((double)th * (double)tw), tn = t.templ_norm;
+        for (int idx = tid; idx < nrow * 8; idx += blockDim.x) {
+            const double* rs = cS + (size_t)(idx >> 3) * ncol + (idx & 7);
+            const double* rq = cQ + (size_t)(idx >> 3) * ncol + (idx & 7);
+            double S[4] = {0.0, 0.0, 0.0, 0.0}, Q[4] = {0.0, 0.0, 0.0, 0.0};
+            int k = 0;
+            for (; k + 3 < tw; k += 4) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) { S[m] += rs[k + m]; Q[m] += rq[k + m]; }
+            }
+            for (; k < tw; ++k) { S[0] += rs[k]; Q[0] += rq[k]; }
+            s_dn[idx] = window_denom((S[0] + S[1]) + (S[2] + S[3]), (Q[0] + Q[1]) + (Q[2] + Q[3]), invArea, tn, c.formula);
+        }
+        // (no barrier needed here: the scratch is next written behind barrier A, s_dn next read behind barrier B)
+    }
+    if (trc && tid == 0) trc[TR_TAIL * 2] = gtime();
+
+    float acc[CY][8];
+#pragma unroll
+    for (int i = 0; i < CY; ++i)
+#pragma unroll
+        for (int cx = 0; cx < 8; ++cx) acc[i][cx] = 0.f;
+    if (tid < g.nfma) {
+        const int pjx = tid % g.PJ, pdx = (tid / g.PJ) % g.PD, tr = tid / (g.PJ * g.PD);
+        const int d0 = (th * pdx) / g.PD, d1 = (th * (pdx + 1)) / g.PD, nd = d1 - d0;
+        const int j0 = (nchunk * pjx) / g.PJ, j1 = nd > 0 ? (nchunk * (pjx + 1)) / g.PJ : j0;
+        if (tr * CY < nrow) {
+            const float* base = s_tile + (size_t)(tr * CY + d0) * P;
+            for (int j = j0; j < j1; ++j) {
+                const float* st = s_t + (size_t)j * g.TS + d0 * 8;
+                const float* fb = base + j * 8;
+                float racc[CY][8], w[CY][16];
+#pragma unroll
+                for (int i = 0; i < CY; ++i)
+#pragma unroll
+                    for (int cx = 0; cx < 8; ++cx) racc[i][cx] = 0.f;
+#pragma unroll
+                for (int r = 0; r < CY - 1; ++r) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 a = *reinterpret_cast<const float4*>(fb + r * P + 4 * v);
+                        w[r][4 * v] = a.x; w[r][4 * v + 1] = a.y; w[r][4 * v + 2] = a.z; w[r][4 * v + 3] = a.w;
+                    }
+                }
+#pragma unroll 1
+                for (int e0 = 0; e0 < nd; e0 += CY) {
+#pragma unroll
+                    for (int u = 0; u < CY; ++u) {
+                        const int e = e0 + u;                      // template row d0 + e
+                        if (e < nd) {
+                            float(&wn)[16] = w[(u + CY - 1) % CY];
+                            const float* pr = fb + (size_t)(e + CY - 1) * P;
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const float4 a = *reinterpret_cast<const float4*>(pr + 4 * v);
+                                wn[4 * v] = a.x; wn[4 * v + 1] = a.y; wn[4 * v + 2] = a.z; wn[4 * v + 3] = a.w;
+                            }
+                            float tt[8];
+                            {
+                                const float4 a = *reinterpret_cast<const float4*>(st + e * 8);
+                                const float4 bq = *reinterpret_cast<const float4*>(st + e * 8 + 4);
+                                tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w; tt[4] = bq.x; tt[5] = bq.y; tt[6] = bq.z; tt[7] = bq.w;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                                for (int i = 0; i < CY; ++i)
+#pragma unroll
+                                    for (int cx = 0; cx < 8; ++cx) racc[i][cx] = fmaf(w[(u + i) % CY][k + cx], tt[k], racc[i][cx]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CY; ++i)
+#pragma unroll
+                    for (int cx = 0; cx < 8; ++cx) acc[i][cx] += racc[i][cx];
+            }
+        }
+    }
+    if (trc && tid == 0) trc[TR_FRINGE * 2 + 1] = gtime();
+    __syncthreads();                                               // (A) statistics done: the scratch becomes the reduction buffer
+    if (tid < g.nfma) {
+        float4* po = reinterpret_cast<float4*>(s_red + (size_t)tid * kLocalRed);
+#pragma unroll
+        for (int i = 0; i < CY; ++i) {
+            po[2 * i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+    }
+    __syncthreads();                                               // (B)
+    unsigned long long key = 0ull;
+    if (tid < nrow * 8) {
+        const int y = tid >> 3, x = tid & 7, tr = y / CY, i = y - tr * CY;
+        if (px0 + x < ww) {
+            float a = 0.f;
+            const int parts = g.PJ * g.PD;
+            const float* src = s_red + (size_t)(tr * parts) * kLocalRed + i * 8 + x;
+            for (int p = 0; p < parts; ++p) a += src[(size_t)p * kLocalRed];    // part order: p = pdx * PJ + pjx, as k_ncc_finalize adds them
+            const unsigned int idx = (unsigned int)((py0 + y) * ww + px0 + x);
+            const float v = ncc_finalize(a, s_dn[tid], t.flat);
+            if (c.params->keep_maps) c.maps[(size_t)track * c.Hmax * c.Wmax + idx] = v;
+            key = peak_key(v, idx);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(key, m);
+        key = o > key ? o : key;
+    }
+    if (lane == 0 && key) atomicMax(&t.peak, key);
+    if (trc && tid == 0) trc[TR_TAIL * 2 + 1] = gtime();
+    trace_end(c, step, TR_NCC);
+}
+
 // (3c) k_ncc_fringe: the candidates the thread-tile grid leaves out (TileCfg: the single column x = 8C and/or the
 //      single row y = CY*G -- both exist for the default 161 x 161 window), register-blocked like the search itself.
 //      A thread owns 8 consecutive candidates of the fringe row (8 x 1 tile) or of the fringe column (1 x 8 tile) and ONE
@@ -1130,14 +1397,6 @@ struct FringeCfg {
                          //    normalises, so the kernel needs no window statistics and runs beside them and the search
 };
 
-__device__ __forceinline__ void cp_async4(float* dst, const float* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void load8(float (&d)[8], const float* p)
 {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);

@@ -63,6 +63,8 @@ struct Pass {
     StatCfg stat{};            // k_winstats (one statistics kernel); NX == 0: the two-kernel statistics (k_colprefix + k_rowsum)
     bool fused = false;        // K-split shape: k_step_fused (search + second stage + update in one launch) instead of k_ncc_search -> k_ncc_finalize
     size_t fused_smem = 0;
+    LocalCfg local{};          // latency shape: k_ncc_local (K-split and window statistics inside the CTA); TR == 0: not used
+    size_t local_smem = 0;
     FringeCfg fringe{};        // CTAs of k_ncc_fringe per track (candidates outside the thread-tile grid); all 0 = none
     size_t fringe_smem = 0;
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
@@ -92,6 +94,8 @@ struct pvt_ctx {
     StatCfg stat{};            // k_winstats geometry (NX == 0: two-kernel statistics)
     bool fused = false;        // k_step_fused (see Pass)
     size_t fused_smem = 0;
+    LocalCfg local{};          // k_ncc_local (see Pass)
+    size_t local_smem = 0;
     unsigned int* h_fault = nullptr;   // mapped pinned word behind Ctx.fault
     size_t templ_smem = 0;     // th*tw floats of dynamic shared memory for the update / init kernels
     cudaStream_t compute = nullptr, copy = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;   // aux*: further branches inside the captured graph
@@ -301,8 +305,9 @@ int raise_smem(const void* fn, size_t bytes)
 int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
 
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
-int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false)
+int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false, bool local = false)
 {
+    if (local) return 3;   // ingest, k_ncc_local, k_update
     if (fused) return 3;   // ingest, k_winstats, k_step_fused
     return (st.NX > 0 ? 3 : 4) + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
@@ -311,7 +316,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool f
 int kernels_per_step(const pvt_ctx* c)
 {
     // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
-    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused);
+    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0);
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -437,6 +442,47 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
             p.fused = true;
             p.stat.signal = 1;
             { int r_ = raise_smem((const void*)k_step_fused<kCY>, p.fused_smem); if (r_) return r_; }
+        }
+    }
+    // k_ncc_local: when one wave of CTAs (<= one per SM) covers every track's window with patches of 8 x 5 TR candidates, the
+    // K-split and the window statistics move inside the CTA (kernels.cuh).  Plan: the TR with the fewest template rows per thread.
+    p.local = LocalCfg{};
+    {
+        const char* nl = getenv("PVT_NO_LOCAL");
+        const bool want = allow_env && !(nl && *nl == '1') && c->params.kernel == PVT_KERNEL_AUTO && !c->lost_mode && !d.global_pass &&
+                          p.tile.pj * p.tile.pd > 1 && !getenv("PVT_PLAN");
+        const int nch = d.mtp / 8, Gall = (d.Hmax + kCY - 1) / kCY, bx = (d.Wmax + 7) / 8;
+        double best = 1e300;
+        for (int TR = 1; want && TR * kCY * 8 <= 256; ++TR) {
+            const int by = (Gall + TR - 1) / TR;
+            if ((long long)d.max_tracks * bx * by > sm_count) continue;
+            for (int PJ = nch; PJ >= 1; --PJ) {
+                if (nch % PJ) continue;
+                const int PD = std::min(std::min(d.mth, 32), 256 / (TR * PJ));   // 256 threads keep 255 registers (288 would be allocated as 12 warps: 168)
+                if (PD < 1) continue;
+                const int nfma = TR * PJ * PD, threads = 32 * ((nfma + 31) / 32);
+                if (threads > 256 || TR * kCY * 8 > threads) continue;
+                LocalCfg g{};
+                g.TR = TR; g.PJ = PJ; g.PD = PD; g.bx = bx; g.by = by; g.nfma = nfma;
+                g.P = 8 + d.mtp;
+                while (g.P % 8 != 4) ++g.P;
+                g.tileH = kCY * TR + d.mth - 1;
+                g.TS = d.mth * 8 + 4;
+                const size_t red_bytes = (size_t)nfma * kLocalRed * 4;
+                if ((size_t)(2 * kCY * TR + 6) * (8 + d.mtw - 1) * 8 > red_bytes) continue;   // the statistics scratch lives in the reduction buffer
+                const size_t smem = (size_t)g.tileH * g.P * 4 + (size_t)nch * g.TS * 4 + red_bytes + (size_t)kCY * TR * 8 * 8 + 64;
+                if (smem + 1024 > kSmemBudget) continue;
+                const double rows = (double)((d.mth + PD - 1) / PD + kCY - 1) * (nch / PJ);   // per-thread template rows incl. the window preload
+                if (rows < best) { best = rows; p.local = g; p.local_smem = smem; }
+            }
+        }
+        if (p.local.TR > 0) {
+            { int r_ = raise_smem((const void*)k_ncc_local<kCY>, p.local_smem); if (r_) return r_; }
+            d.gridW = 8 * p.local.bx;
+            d.gridH = kCY * p.local.TR * p.local.by;
+            if (getenv("PVT_DEBUG_PLAN"))
+                fprintf(stderr, "[pvt] local plan: TR=%d PJ=%d PD=%d ctas/track=%dx%d threads=%d P=%d smem=%zu\n", p.local.TR, p.local.PJ, p.local.PD,
+                        p.local.bx, p.local.by, 32 * ((p.local.nfma + 31) / 32), p.local.P, p.local_smem);
         }
     }
     return encode_tmap(p.d, p.tile, &p.tmap);
@@ -593,7 +639,7 @@ Pass local_pass(const pvt_ctx* c)
 {
     Pass p;
     p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
-    p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fused = c->fused; p.fused_smem = c->fused_smem; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
+    p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fused = c->fused; p.fused_smem = c->fused_smem; p.local = c->local; p.local_smem = c->local_smem; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
     return p;
 }
 Pass global_pass(const pvt_ctx* c)
@@ -660,6 +706,23 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         }
     }
 
+    if (p.local.TR > 0 && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass) {
+        // latency shape, K-split and statistics inside the CTA: ingest ~> k_ncc_local -> k_update
+        const bool pdl_l = capturing && !profile && p.pdl;
+        const unsigned threads = 32u * (unsigned)((p.local.nfma + 31) / 32);
+        if (profile) { int r = pnode(c, CLS_STATS, 0, c->compute); if (r) return r; r = pnode(c, CLS_STATS, 1, c->compute); if (r) return r; }
+        if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
+        { int r = launch_pdl(k_ncc_local<kCY>, dim3((unsigned)(d.max_tracks * p.local.bx * p.local.by)), dim3(threads), p.local_smem, c->compute, pdl_l, d, p.local); if (r) return r; }
+        if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
+        { int r = dbg(c, "k_ncc_local"); if (r) return r; }
+        if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
+        k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
+        if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
+        { int r = dbg(c, "k_update"); if (r) return r; }
+        if (join3) CK(cudaStreamWaitEvent(c->compute, c->ev_join3, 0));
+        CK(cudaGetLastError());
+        return PVT_OK;
+    }
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
     const bool tc = c->params.kernel == PVT_KERNEL_TC && !d.global_pass;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
@@ -1320,7 +1383,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         lp.d = c->d;
         CR(build_plan(c, lp, prop.multiProcessorCount, params->ingest, true));
         c->d = lp.d; c->tile = lp.tile; c->tmap = lp.tmap; c->ncc_smem = lp.ncc_smem; c->rowsum_warps = lp.rowsum_warps;
-        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->stat = lp.stat; c->fused = lp.fused; c->fused_smem = lp.fused_smem; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
+        c->rowsum_pw = lp.rowsum_pw; c->colprefix_chunks = lp.colprefix_chunks; c->stat = lp.stat; c->fused = lp.fused; c->fused_smem = lp.fused_smem; c->local = lp.local; c->local_smem = lp.local_smem; c->fringe = lp.fringe; c->fringe_smem = lp.fringe_smem;
         c->roi_ingest = lp.roi_ingest;
     }
     c->kps = kernels_per_step(c);

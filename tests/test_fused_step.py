@@ -39,7 +39,7 @@ class env:
 
 def run_clip(frames, roi, R, fused, n_tracks=1, keep_maps=0):
     H, W = frames.shape[1:3]
-    with env(PVT_FUSED="1" if fused else None):
+    with env(PVT_FUSED="1" if fused else None, PVT_NO_LOCAL="1"):
         with pvt.Tracker(W, H, roi[2], roi[3], max_tracks=n_tracks, keep_maps=keep_maps, search_radius_x=R, search_radius_y=R) as tr:
             for t in range(n_tracks):
                 tr.init_track(t, frames[0] if t == 0 else None, (roi[0] + 3 * t, roi[1] + 2 * t, roi[2], roi[3]))
@@ -104,7 +104,7 @@ def test_fused_async_sequence_and_inactive_track():
     H, W = frames.shape[1:3]
     out = {}
     for fused in (True, False):
-        with env(PVT_FUSED="1" if fused else None):
+        with env(PVT_FUSED="1" if fused else None, PVT_NO_LOCAL="1"):
             with pvt.Tracker(W, H, 32, 32, max_tracks=2, search_radius_x=80, search_radius_y=80) as tr:
                 tr.init_track(0, frames[0], roi)
                 ring = [[pvt.host_frame(frames[(k + 1) % 20])] for k in range(20)]

@@ -25,13 +25,19 @@ T = T[8:]                                     # skip the first steps
 t0 = T[:, 0, 0:1]
 print("%s: %.2f us/step (events); step-to-step %.2f us (trace)" % (wname, 1e3 * ms / 64, np.median(np.diff(T[:, 0, 0])) / 1e3))
 prev_end = None
+local = T[:, 7, 0].any() and T[:, 6, 0].any() and not T[:, 4, 0].any()
 for k, nm in enumerate(names):
-    if not T[:, k, 0].any(): continue
+    if not T[:, k, 0].any() or (local and k in (1, 6, 7)): continue
     st = np.median(T[:, k, 0] - T[:, 0, 0]) / 1e3; en = np.median(T[:, k, 1] - T[:, 0, 0]) / 1e3
     print("  %-13s start %7.2f  end %7.2f  dur %6.2f us  gap-before %6.2f" % (nm, st, en, en - st, st - prev_end if prev_end is not None else 0.0))
     prev_end = en
-if T[:, 7, 0].any():
-    b = T[:, 5, 0]
-    print("  DBGU update: EMA-done +%.2f  finish_template-done +%.2f (from update start)" % tuple(np.median(x - b) / 1e3 for x in (T[:, 7, 0], T[:, 7, 1])))
+if T[:, 7, 0].any() and T[:, 6, 0].any() and not T[:, 4, 0].any():
+    b = T[:, 3, 0]
+    print("  k_ncc_local, CTA 0 (from the kernel's first CTA start): staged +%.2f | column partials +%.2f | column slides +%.2f | statistics done +%.2f | FMA loop done +%.2f | reduced, peak sent +%.2f us" %
+          tuple(np.median(x - b) / 1e3 for x in (T[:, 6, 0], T[:, 1, 0], T[:, 1, 1], T[:, 7, 0], T[:, 6, 1], T[:, 7, 1])))
+elif T[:, 7, 0].any() and T[:, 6, 0].any():
+    b = T[:, 3, 0]
+    print("  K-split search, CTA 0 (from the kernel's first CTA start): tile requested +%.2f | landed +%.2f | loop done +%.2f | partial sums stored +%.2f us" %
+          tuple(np.median(x - b) / 1e3 for x in (T[:, 6, 0], T[:, 6, 1], T[:, 7, 0], T[:, 7, 1])))
 nxt = np.median(T[1:, 0, 0] - T[:-1, 5, 1]) / 1e3
 print("  gap to next step's ingest: %.2f us" % nxt)
