@@ -155,22 +155,23 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     pdl_trigger();
     const int track = blockIdx.y;
     const TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
-    if (!t.active || !track_owned(c, t, step)) return;
-    const FrameDesc d = c.table[table_row(c, step) + t.stream];
-    if (!d.valid) return;
-    trace_begin(c, step, TR_INGEST);
+    unsigned long long step;
+    FrameDesc d;
+    const bool stepped = track_stepped_ld(c, t, step, &d);        // all of the preamble's loads go out before the first branch
     const DevParams P = *c.params;
+    const int bx_ = t.x, by_ = t.y, btw = t.w, bth = t.h, bstream = t.stream;
+    if (!stepped) return;
+    trace_begin(c, step, TR_INGEST);
     int win[4];
-    search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
-    const int x0 = win[0] & ~3, x1 = min(c.W, win[0] + win[2] + t.w - 1), rows = win[3] + t.h - 1;
+    search_window(bx_, by_, btw, bth, c.W - btw + 1, c.H - bth + 1, P.rx, P.ry, win);
+    const int x0 = win[0] & ~3, x1 = min(c.W, win[0] + win[2] + btw - 1), rows = win[3] + bth - 1;
     const int gpr = (x1 - x0 + 3) >> 2;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (c.stage && gid < 4) c.stage_hdr[track].win[gid] = win[gid];   // for k_prefetch_roi, which runs behind this kernel
     if (c.stage && gid == 0) c.stage_hdr[track].cur_step = step;
     if (gid >= gpr * rows) return;
     const int r = gid / gpr, x = x0 + ((gid - r * gpr) << 2), y = win[1] + r;
-    float* out = c.gray + (size_t)t.stream * c.plane + (size_t)y * c.pitch + x;
+    float* out = c.gray + (size_t)bstream * c.plane + (size_t)y * c.pitch + x;
     // Did k_prefetch_roi stage this tile during the previous step (pinned host rings)?  Then it is a device-to-device copy
     // of already converted pixels; the zero-copy read over PCIe happened off the critical path.
     // (Only inside a sequence over a pinned ring, whose frames the caller keeps unchanged: SeqDesc.prefetch.)
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
             const float* sp = c.stage + (size_t)track * c.stage_w * c.stage_h + (size_t)(y - h.y0) * c.stage_w + (x - h.x0);
             const float4 o4 = *reinterpret_cast<const float4*>(sp);
             *reinterpret_cast<float4*>(out) = o4;
-            if (c.gray8) store_gray8(c, t.stream, x, y, o4);
+            if (c.gray8) store_gray8(c, bstream, x, y, o4);
             trace_end(c, step, TR_INGEST);
             return;
         }
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
     const unsigned char* row = (const unsigned char*)d.data + (size_t)y * d.step;
     const float4 o4 = ingest_group(d, row, x, min(4, c.W - x));
     *reinterpret_cast<float4*>(out) = o4;
-    if (c.gray8) store_gray8(c, t.stream, x, y, o4);
+    if (c.gray8) store_gray8(c, bstream, x, y, o4);
     trace_end(c, step, TR_INGEST);
 }
 
@@ -496,23 +497,26 @@ __global__ void __launch_bounds__(kStatThreads, 3) k_winstats(Ctx c, StatCfg sc)
     pdl_trigger();
     const int track = blockIdx.y;
     TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
-    if (!track_stepped(c, t, step)) return;
-    trace_begin(c, step, TR_COLPREFIX);
+    unsigned long long step;
+    const bool stepped = track_stepped_ld(c, t, step);            // all of the preamble's loads go out before the first branch
     const DevParams P = *c.params;
+    const int bx_ = t.x, by_ = t.y, tw = t.w, th = t.h, tstream = t.stream;
+    const double tn = t.templ_norm;
+    if (!stepped) return;
+    trace_begin(c, step, TR_COLPREFIX);
     int win[4];
-    search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
+    search_window(bx_, by_, tw, th, c.W - tw + 1, c.H - th + 1, P.rx, P.ry, win);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (blockIdx.x == 0 && tid < 4) t.win[tid] = win[tid];
-    const int ww = win[2], wh = win[3], tw = t.w, th = t.h;
+    const int ww = win[2], wh = win[3];
     const int yb = blockIdx.x / sc.xtiles, xt = blockIdx.x - yb * sc.xtiles;
     const int x0 = xt * sc.NX, y0 = yb * sc.NY;
     if (x0 >= ww || y0 >= wh) return;
     const int nx = min(sc.NX, ww - x0), ny = min(sc.NY, wh - y0);
     const bool colok = tid < nx + tw - 1;
     const size_t pitch = (size_t)c.pitch;
-    const float* col = c.gray + (size_t)t.stream * c.plane + (size_t)(win[1] + y0) * pitch + win[0] + x0 + (colok ? tid : 0);
-    const double invArea = 1.0 / ((double)th * (double)tw), tn = t.templ_norm;
+    const float* col = c.gray + (size_t)tstream * c.plane + (size_t)(win[1] + y0) * pitch + win[0] + x0 + (colok ? tid : 0);
+    const double invArea = 1.0 / ((double)th * (double)tw);
     const int formula = c.formula;
 #define PH(i) ((i) + ((i) >> 3))
     pdl_wait();   // latency shape: launched behind the ingest with a programmatic dependency; the gray plane is complete now
@@ -1129,6 +1133,9 @@ struct LocalCfg {
     int tileH;           // CY * TR + mth - 1
     int TS;              // template chunk stride in floats (mth * 8 + 4)
     int nfma;            // TR * PJ * PD threads run the FMA loop (the CTA is that rounded up to a warp)
+    int gstats;          // 1: the normalisers come from k_winstats, which runs beside this kernel on SMs the plan leaves free
+                         //    (TrackState.stats_done counts its CTAs); 0: computed here from the tile, before the loop
+    int sNX, sNY;        // k_winstats' tile (StatCfg) -> how many of its CTAs store normalisers for a (clamped) window
 };
 constexpr int kLocalRed = 8 * kCY + 4;   // floats per thread in the reduction buffer (44: conflict-free float4 stores)
 
@@ -1141,17 +1148,17 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
     const int track = blockIdx.x / per_track, b = blockIdx.x - track * per_track;
     const int byi = b / g.bx, bxi = b - byi * g.bx;
     TrackState& t = c.tracks[track];
-    const unsigned long long step = *c.step;
-    if (!track_stepped(c, t, step)) return;
+    unsigned long long step;
+    const bool stepped = track_stepped_ld(c, t, step);            // all of the preamble's loads go out before the first branch
+    const DevParams PP = *c.params;
+    const int bx_ = t.x, by_ = t.y, tw = t.w, th = t.h, tp = t.tp, tstream = t.stream;
+    if (!stepped) return;
     trace_begin(c, step, TR_NCC);
     int win[4];
-    {
-        const DevParams P = *c.params;
-        search_window(t.x, t.y, t.w, t.h, c.W - t.w + 1, c.H - t.h + 1, P.rx, P.ry, win);
-    }
+    search_window(bx_, by_, tw, th, c.W - tw + 1, c.H - th + 1, PP.rx, PP.ry, win);
     const int tid = threadIdx.x, lane = tid & 31;
     if (b == 0 && tid < 4) t.win[tid] = win[tid];               // k_update reads it (k_colprefix / k_winstats store it in the other shapes)
-    const int ww = win[2], wh = win[3], tw = t.w, th = t.h, tp = t.tp, nchunk = tp >> 3;
+    const int ww = win[2], wh = win[3], nchunk = tp >> 3;
     const int px0 = 8 * bxi, py0 = CY * g.TR * byi;               // patch origin inside the window
     if (px0 >= ww || py0 >= wh) return;                           // clamped window: CTA-uniform
     const int nrow = min(CY * g.TR, wh - py0);                    // candidate rows of this patch
@@ -1160,6 +1167,16 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
     float* s_t = s_tile + (size_t)g.tileH * P;                    // [chunks][TS]
     float* s_red = s_t + (size_t)(c.mtp >> 3) * g.TS;             // [nfma][44] partial sums; before that: the statistics warp's scratch
     double* s_dn = reinterpret_cast<double*>(s_red + (size_t)g.nfma * kLocalRed);   // [CY * TR * 8] normalisers
+    {
+        // the centred template does not depend on this step's frame: on its way before the wait for the ingest
+        const float4* tsrc = reinterpret_cast<const float4*>(c.templc + (size_t)track * c.mth * c.mtp);
+        const int nq = th * 2;                                     // float4 per chunk
+        for (int i = tid; i < nchunk * nq; i += blockDim.x) {
+            const int j = i / nq, q = i - j * nq;
+            cp_async16(reinterpret_cast<float4*>(s_t + (size_t)j * g.TS) + q, tsrc + (size_t)j * nq + q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     pdl_wait();                                                    // the ingest's gray plane is complete
     {
         // tile: rows [py0, py0 + nrow + th - 1), columns [px0, px0 + 8 + tp) of the window's corner of the gray plane.  The window
@@ -1167,13 +1184,13 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
         // shift costs nothing); zeros outside the frame (they only meet masked candidates / zero template columns)
         const int ax0 = win[0] + px0, ay0 = win[1] + py0, tw_used = 8 + tp, th_used = nrow + th - 1;
         const int gx0 = ax0 & ~3, nvec = (ax0 + tw_used - gx0 + 3) >> 2;
-        const float* src = c.gray + (size_t)t.stream * c.plane + (size_t)ay0 * c.pitch + gx0;
+        const float* src = c.gray + (size_t)tstream * c.plane + (size_t)ay0 * c.pitch + gx0;
         const int total = th_used * nvec;
-        for (int i0 = tid; i0 < total; i0 += 4 * (int)blockDim.x) {
-            float4 v[4];
-            int rr[4], xx[4];
+        for (int i0 = tid; i0 < total; i0 += 8 * (int)blockDim.x) {
+            float4 v[8];
+            int rr[8], xx[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                          // four independent loads in flight per thread
+            for (int k = 0; k < 8; ++k) {                          // eight independent loads in flight per thread: one round trip for a C2 patch
                 const int i = i0 + k * (int)blockDim.x;
                 rr[k] = -1;
                 v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1184,7 +1201,7 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 if (rr[k] >= 0) {
                     const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
@@ -1195,20 +1212,14 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
                 }
             }
         }
-        const float4* tsrc = reinterpret_cast<const float4*>(c.templc + (size_t)track * c.mth * c.mtp);
-        const int nq = th * 2;                                     // float4 per chunk
-        for (int i = tid; i < nchunk * nq; i += blockDim.x) {
-            const int j = i / nq, q = i - j * nq;
-            cp_async16(reinterpret_cast<float4*>(s_t + (size_t)j * g.TS) + q, tsrc + (size_t)j * nq + q);
-        }
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     // phase stamps of CTA 0 (pvt_trace_enable; tools/timeline.py): FRINGE slot = staged | FMA loop done, TAIL slot = statistics done | reduced
     unsigned long long* trc = (c.trace && blockIdx.x == 0) ? c.trace + (step % kRing) * 16 : nullptr;
     if (trc && tid == 0) trc[TR_FRINGE * 2] = gtime();
 
-    {
+    if (!g.gstats) {
         // ---- the patch's window statistics from the tile in shared memory, by all warps (scratch: the reduction buffer, which is
         // unused until barrier A).  FP64 adds have ~40 cycles of latency here and one warp issues them slowly (a dedicated
         // statistics warp beside the FMA loop took 10 - 13 us), so the work is cut into short chains over all 256 threads:
@@ -1337,17 +1348,23 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
             po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         }
     }
+    if (g.gstats && tid == 0) {                                    // k_winstats (the other graph branch) has stored this window's normalisers?
+        const unsigned int n_stat = (unsigned int)(((ww + g.sNX - 1) / g.sNX) * ((wh + g.sNY - 1) / g.sNY));
+        if (!spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
+    }
     __syncthreads();                                               // (B)
     unsigned long long key = 0ull;
     if (tid < nrow * 8) {
         const int y = tid >> 3, x = tid & 7, tr = y / CY, i = y - tr * CY;
         if (px0 + x < ww) {
+            const unsigned int idx = (unsigned int)((py0 + y) * ww + px0 + x);
+            const double dnv = g.gstats ? __ldcg(c.denom + (size_t)track * c.Hmax * c.Wmax + idx) : s_dn[tid];   // on its way during the sums
             float a = 0.f;
             const int parts = g.PJ * g.PD;
             const float* src = s_red + (size_t)(tr * parts) * kLocalRed + i * 8 + x;
+#pragma unroll 8
             for (int p = 0; p < parts; ++p) a += src[(size_t)p * kLocalRed];    // part order: p = pdx * PJ + pjx, as k_ncc_finalize adds them
-            const unsigned int idx = (unsigned int)((py0 + y) * ww + px0 + x);
-            const float v = ncc_finalize(a, s_dn[tid], t.flat);
+            const float v = ncc_finalize(a, dnv, t.flat);
             if (c.params->keep_maps) c.maps[(size_t)track * c.Hmax * c.Wmax + idx] = v;
             key = peak_key(v, idx);
         }
@@ -1890,15 +1907,30 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
     // tracker_ghc semantics (Ctx.lost_mode): a step is a local pass followed by a whole-frame pass; a track is reported
     // by the pass that owns it (read before this call changes the track's mode)
     const bool owned = track_owned(c, t, step);
+    // Everything this function needs from global memory that does not depend on the peak goes out HERE, before the first
+    // branch (loads behind `if (stepped)` are a further dependent L2 round trip on the step's critical path): the parameters,
+    // the peak, the track's fields -- and the first batch of the OLD template, whose addresses are known (used only if the EMA runs).
+    const DevParams P = *c.params;
+    const int tw = t.w, th = t.h, tstream = t.stream, ox = t.x, oy = t.y;
+    float* const tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    float tv0[16];
+    {
+        const int n0 = tw * th, stride0 = blockDim.x;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int i = threadIdx.x + k * stride0;
+            tv0[k] = (stepped && i < n0) ? tp_[i] : 0.f;
+        }
+    }
+    // k_update launched behind the search with a programmatic dependency (k_ncc_local shape): everything above ran while the
+    // search was still computing; the peak and the window are the search's results.  (A no-op in every other launch.)
+    pdl_wait();
+    const unsigned long long key = *((volatile unsigned long long*)&t.peak);
+    const int ww = t.win[2], wh = t.win[3], w0x = t.win[0], w0y = t.win[1];
     if (stepped) {
-        const DevParams P = *c.params;
-        const unsigned long long key = *((volatile unsigned long long*)&t.peak);
         const float val = unord_f32((unsigned int)(key >> 32));
         const unsigned int idx = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
-        // every field of the track this function needs, read in ONE batch with the peak (nothing below re-reads t.* behind a
-        // barrier: each such read is a dependent L2 round trip on the step's critical path)
-        const int ww = t.win[2], wh = t.win[3], tw = t.w, th = t.h, tstream = t.stream, ox = t.x, oy = t.y;
-        const int bx = t.win[0] + (int)(idx % (unsigned int)ww), by = t.win[1] + (int)(idx / (unsigned int)ww);
+        const int bx = w0x + (int)(idx % (unsigned int)ww), by = w0y + (int)(idx / (unsigned int)ww);
         const double best = (double)val;
         const bool moved = best >= P.min_conf;
         const bool updated = moved && best >= P.strong_conf;
@@ -1907,7 +1939,6 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
         if (updated) {
             const int n = tw * th;
             const double alpha = 1.0 - P.lr, beta = P.lr;
-            float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
             const float* g = c.gray + (size_t)tstream * c.plane + (size_t)ny * c.pitch + nx;
             // one batch of 32 loads per thread covers a 64 x 64 template with 256 threads: one L2 round trip, then the EMA.
             // (row, column) of pixel i advance incrementally: no division per element
@@ -1919,7 +1950,7 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
                 for (int k = 0; k < 16; ++k) {
                     const int i = i0 + k * stride;
                     pv[k] = i < n ? g[(size_t)r * c.pitch + col] : 0.f;
-                    tv[k] = i < n ? tp_[i] : 0.f;
+                    tv[k] = i0 == (int)threadIdx.x ? tv0[k] : (i < n ? tp_[i] : 0.f);   // first batch: prefetched above
                     col += dr; r += dq;
                     if (col >= tw) { col -= tw; r += 1; }
                 }
@@ -1984,9 +2015,10 @@ __global__ void __launch_bounds__(256) k_update(Ctx c)
     extern __shared__ float sm_f[];
     __shared__ double red[64];
     const int track = blockIdx.x;
-    const unsigned long long step = *c.step;
+    unsigned long long step;
+    const bool stepped = track_stepped_ld(c, c.tracks[track], step);
     trace_begin(c, step, TR_UPDATE);
-    track_update(c, track, step, track_stepped(c, c.tracks[track], step), sm_f, red);
+    track_update(c, track, step, stepped, sm_f, red);
     trace_end(c, step, TR_UPDATE);
 }
 

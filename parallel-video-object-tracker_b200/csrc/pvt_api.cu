@@ -305,9 +305,9 @@ int raise_smem(const void* fn, size_t bytes)
 int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
 
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
-int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false, bool local = false)
+int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false, bool local = false, int extra_local = 0)
 {
-    if (local) return 3;   // ingest, k_ncc_local, k_update
+    if (local) return 3 + extra_local;   // ingest, [k_winstats,] k_ncc_local, k_update
     if (fused) return 3;   // ingest, k_winstats, k_step_fused
     return (st.NX > 0 ? 3 : 4) + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
@@ -316,7 +316,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool f
 int kernels_per_step(const pvt_ctx* c)
 {
     // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
-    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0);
+    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0, c->local.gstats);
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -452,10 +452,16 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
         const bool want = allow_env && !(nl && *nl == '1') && c->params.kernel == PVT_KERNEL_AUTO && !c->lost_mode && !d.global_pass &&
                           p.tile.pj * p.tile.pd > 1 && !getenv("PVT_PLAN");
         const int nch = d.mtp / 8, Gall = (d.Hmax + kCY - 1) / kCY, bx = (d.Wmax + 7) / 8;
+        // statistics: from k_winstats running beside the search on SMs the plan leaves free (one per statistics CTA in the worst
+        // placement: nothing can wait for a CTA that has no room), else inside the search CTAs before their loop (+4.6 us on C2)
+        const char* ls = getenv("PVT_LOCAL_STATS");
+        const long long stat_ctas = p.stat.NX > 0 ? (long long)d.max_tracks * p.stat.xtiles * p.stat.ybands : (1LL << 40);
         double best = 1e300;
-        for (int TR = 1; want && TR * kCY * 8 <= 256; ++TR) {
+        for (int pass_g = 1; want && pass_g >= 0 && p.local.TR == 0; --pass_g)
+        for (int TR = 1; TR * kCY * 8 <= 256; ++TR) {
+            if (pass_g && ls && *ls == '1') break;
             const int by = (Gall + TR - 1) / TR;
-            if ((long long)d.max_tracks * bx * by > sm_count) continue;
+            if ((long long)d.max_tracks * bx * by + (pass_g ? stat_ctas : 0) > sm_count) continue;
             for (int PJ = nch; PJ >= 1; --PJ) {
                 if (nch % PJ) continue;
                 const int PD = std::min(std::min(d.mth, 32), 256 / (TR * PJ));   // 256 threads keep 255 registers (288 would be allocated as 12 warps: 168)
@@ -464,6 +470,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
                 if (threads > 256 || TR * kCY * 8 > threads) continue;
                 LocalCfg g{};
                 g.TR = TR; g.PJ = PJ; g.PD = PD; g.bx = bx; g.by = by; g.nfma = nfma;
+                g.gstats = pass_g; g.sNX = std::max(p.stat.NX, 1); g.sNY = std::max(p.stat.NY, 1);
                 g.P = 8 + d.mtp;
                 while (g.P % 8 != 4) ++g.P;
                 g.tileH = kCY * TR + d.mth - 1;
@@ -480,8 +487,9 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
             { int r_ = raise_smem((const void*)k_ncc_local<kCY>, p.local_smem); if (r_) return r_; }
             d.gridW = 8 * p.local.bx;
             d.gridH = kCY * p.local.TR * p.local.by;
+            if (p.local.gstats) p.stat.signal = 1;
             if (getenv("PVT_DEBUG_PLAN"))
-                fprintf(stderr, "[pvt] local plan: TR=%d PJ=%d PD=%d ctas/track=%dx%d threads=%d P=%d smem=%zu\n", p.local.TR, p.local.PJ, p.local.PD,
+                fprintf(stderr, "[pvt] local plan: gstats=%d TR=%d PJ=%d PD=%d ctas/track=%dx%d threads=%d P=%d smem=%zu\n", p.local.gstats, p.local.TR, p.local.PJ, p.local.PD,
                         p.local.bx, p.local.by, 32 * ((p.local.nfma + 31) / 32), p.local.P, p.local_smem);
         }
     }
@@ -692,7 +700,12 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     { int r = dbg(c, "k_ingest"); if (r) return r; }
     // pinned host rings: stage the next step's pixels beside this step (a branch that joins before the box moves)
     bool join3 = false;
-    if (d.stage && p.roi_ingest && !d.global_pass && p.prefetch) {
+    // (k_ncc_local with its statistics on a parallel branch fills all but a few SMs with one CTA each: a prefetch CTA that lands on
+    //  an SM first keeps a search CTA out until it has finished its PCIe reads -- measured: e2e 37.3k -> 31.3k frames/s.  There the
+    //  prefetch is launched BEHIND k_winstats on the statistics branch instead: by then every search CTA has its SM.)
+    const bool local_gs = p.local.TR > 0 && p.local.gstats && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass;
+    const bool pf_on_stats_branch = local_gs && capturing && d.stage && p.roi_ingest && p.prefetch;
+    if (d.stage && p.roi_ingest && !d.global_pass && p.prefetch && !pf_on_stats_branch) {
         const dim3 pgrid(24, (unsigned)d.max_tracks);   // small on purpose: see k_prefetch_roi
         if (capturing) {
             CK(cudaEventRecord(c->ev_fork, c->compute));
@@ -710,15 +723,28 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         // latency shape, K-split and statistics inside the CTA: ingest ~> k_ncc_local -> k_update
         const bool pdl_l = capturing && !profile && p.pdl;
         const unsigned threads = 32u * (unsigned)((p.local.nfma + 31) / 32);
+        const bool forkl = capturing && p.local.gstats;
+        cudaStream_t sst = forkl ? c->aux : c->compute;
+        if (forkl) {
+            CK(cudaEventRecord(c->ev_fork, c->compute));
+            CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+        }
+        // (profiling graph: no event nodes on the statistics branch -- they delay k_winstats, and the search would be timed waiting for it)
         if (profile) { int r = pnode(c, CLS_STATS, 0, c->compute); if (r) return r; r = pnode(c, CLS_STATS, 1, c->compute); if (r) return r; }
+        if (p.local.gstats) { int r = launch_pdl(k_winstats, dim3((unsigned)(p.stat.xtiles * p.stat.ybands), d.max_tracks), dim3(kStatThreads), 0, sst, pdl_l, d, p.stat); if (r) return r; }
+        if (pf_on_stats_branch) k_prefetch_roi<<<dim3(24, (unsigned)d.max_tracks), 256, 0, c->aux>>>(d, c->prefetch_delay_ns);
+        if (forkl) CK(cudaEventRecord(c->ev_join, c->aux));
         if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
         { int r = launch_pdl(k_ncc_local<kCY>, dim3((unsigned)(d.max_tracks * p.local.bx * p.local.by)), dim3(threads), p.local_smem, c->compute, pdl_l, d, p.local); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_ncc_local"); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
+        // (a programmatic edge search ~> update -- the update's CTA starts early, prefetches the old template and blocks in
+        //  griddepcontrol.wait -- was measured: the step went 21.6 -> 23.4 us, the early CTA slows the search it shares the GPU with)
         k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_update"); if (r) return r; }
+        if (forkl) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));   // the statistics branch ends inside this step
         if (join3) CK(cudaStreamWaitEvent(c->compute, c->ev_join3, 0));
         CK(cudaGetLastError());
         return PVT_OK;

@@ -152,6 +152,26 @@ __device__ __forceinline__ bool track_stepped(const Ctx& c, const TrackState& t,
     return c.table[table_row(c, step) + t.stream].valid != 0;
 }
 
+// track_stepped with every independent load issued before the first branch: *step, the sequence descriptor and the track's
+// fields go out together (one L2 round trip), the frame-table entry follows (a second one).  The branchy form above walks
+// t.active -> *step -> lost-mode fields -> SeqDesc -> table[..].valid as a chain of up to five dependent round trips -- on the
+// single-stream step that is 1 - 2 us in front of every kernel.  (An inactive slot has stream 0: the speculative table read is in range.)
+__device__ __forceinline__ bool track_stepped_ld(const Ctx& c, const TrackState& t, unsigned long long& step_out, FrameDesc* fd = nullptr)
+{
+    const unsigned long long s = *c.step;
+    const SeqDesc q = *c.seq;
+    const int active = t.active, stream = t.stream, ug = t.use_global;
+    const unsigned long long gs = t.global_since;
+    step_out = s;
+    const size_t row = (size_t)(q.row0 + (int)((s - q.step0 + (unsigned long long)q.phase) % (unsigned long long)q.ring_len)) * c.max_streams;
+    int valid;
+    if (fd) { *fd = c.table[row + stream]; valid = fd->valid; }
+    else valid = c.table[row + stream].valid;
+    const bool glob = active && ug && gs <= s;
+    const bool owned = !c.lost_mode || (glob == (c.global_pass != 0));
+    return active && owned && valid != 0;
+}
+
 // monotone float -> uint map (larger float <=> larger uint); -0 is folded into +0 first so that it
 // ties with +0 exactly like a float comparison in cv::minMaxLoc
 __device__ __forceinline__ unsigned int ord_f32(float v)

@@ -38,9 +38,15 @@ def run(frames, roi, R, n_tracks=1, **e):
 def test_local_c2_geometry_vs_ksplit_same_parts_and_oracle():
     c = synth.make_clip(synth.ClipSpec(seed=21, W=1920, H=1080, tw=64, th=64, n_frames=4, R=80))
     frames, roi = c["frames"], c["roi"]
-    a, ma, ta, ka = run(frames, roi, 80, PVT_NO_LOCAL=None, PVT_PLAN=None)
+    a, ma, ta, ka = run(frames, roi, 80, PVT_NO_LOCAL=None, PVT_PLAN=None, PVT_LOCAL_STATS="1")   # statistics inside the CTA: TR 5, 8 x 6 parts
     b, mb, tb, kb = run(frames, roi, 80, PVT_NO_LOCAL="1", PVT_PLAN="33,8,6,0")   # K-split with the local plan's parts (8 chunks x 6 row parts)
-    assert ka == 3 and kb == 4, (ka, kb)
+    a2, ma2, ta2, ka2 = run(frames, roi, 80, PVT_NO_LOCAL=None, PVT_PLAN=None)    # default: statistics from k_winstats beside the search (TR 6, 8 x 5 parts)
+    b2, mb2, tb2, kb2 = run(frames, roi, 80, PVT_NO_LOCAL="1", PVT_PLAN="33,8,5,0")
+    assert ka2 == 4 and kb2 == 4
+    assert np.array_equal(a2["conf"].view(np.uint32), b2["conf"].view(np.uint32)) and np.array_equal(ta2[0], tb2[0])
+    for k in range(len(ma2)):
+        assert np.array_equal(ma2[k][0][0].view(np.uint32), mb2[k][0][0].view(np.uint32))   # same normalisers, same sums: same bits
+    assert ka in (3, 4) and kb == 4, (ka, kb)
     for f in ("x", "y", "moved", "updated"):
         assert np.array_equal(a[f], b[f]), f
     assert np.array_equal(ta[0], tb[0])
@@ -66,12 +72,13 @@ GEOMS = [(320, 240, 32, 32, 80, 1), (400, 300, 37, 29, 40, 1), (640, 360, 100, 2
 
 
 @pytest.mark.parametrize("W,H,tw,th,R,n_tracks", GEOMS)
-def test_local_equals_default_ksplit_path(W, H, tw, th, R, n_tracks):
+@pytest.mark.parametrize("stats", ["winstats", "in_cta"])
+def test_local_equals_default_ksplit_path(W, H, tw, th, R, n_tracks, stats):
     c = synth.make_clip(synth.ClipSpec(seed=31 + tw + n_tracks, W=W, H=H, tw=tw, th=th, n_frames=5, R=R))
     frames, roi = c["frames"], c["roi"]
-    a, ma, ta, ka = run(frames, roi, R, n_tracks, PVT_NO_LOCAL=None)
+    a, ma, ta, ka = run(frames, roi, R, n_tracks, PVT_NO_LOCAL=None, PVT_LOCAL_STATS="1" if stats == "in_cta" else None)
     b, mb, tb, kb = run(frames, roi, R, n_tracks, PVT_NO_LOCAL="1")
-    if ka != 3 or kb == 3:
+    if ka != (3 if stats == "in_cta" else 4) or kb != 4:
         pytest.skip("no k_ncc_local plan for this geometry (%s / %s kernels per step)" % (ka, kb))
     for f in ("x", "y", "moved", "updated", "searched", "valid"):
         assert np.array_equal(a[f], b[f]), f

@@ -20,6 +20,8 @@ pytestmark = pytest.mark.gpu
 def one_map(frames, roi, R, legacy, **kw):
     H, W = frames.shape[1:3]
     old = os.environ.pop("PVT_STATS_LEGACY", None)
+    old_nl = os.environ.get("PVT_NO_LOCAL")
+    os.environ["PVT_NO_LOCAL"] = "1"      # both runs on the K-split search with the same plan: only the statistics kernels differ
     if legacy:
         os.environ["PVT_STATS_LEGACY"] = "1"
     try:
@@ -29,6 +31,9 @@ def one_map(frames, roi, R, legacy, **kw):
             m, win = tr.window_map(0)
     finally:
         os.environ.pop("PVT_STATS_LEGACY", None)
+        os.environ.pop("PVT_NO_LOCAL", None)
+        if old_nl is not None:
+            os.environ["PVT_NO_LOCAL"] = old_nl
         if old is not None:
             os.environ["PVT_STATS_LEGACY"] = old
     return m, win, res
