@@ -1136,6 +1136,7 @@ struct LocalCfg {
     int gstats;          // 1: the normalisers come from k_winstats, which runs beside this kernel on SMs the plan leaves free
                          //    (TrackState.stats_done counts its CTAs); 0: computed here from the tile, before the loop
     int sNX, sNY;        // k_winstats' tile (StatCfg) -> how many of its CTAs store normalisers for a (clamped) window
+    int update;          // 1: the track's last CTA (ticket) runs track_update; 0: k_update follows as its own launch
 };
 constexpr int kLocalRed = 8 * kCY + 4;   // floats per thread in the reduction buffer (44: conflict-free float4 stores)
 
@@ -1152,7 +1153,13 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
     const bool stepped = track_stepped_ld(c, t, step);            // all of the preamble's loads go out before the first branch
     const DevParams PP = *c.params;
     const int bx_ = t.x, by_ = t.y, tw = t.w, th = t.h, tp = t.tp, tstream = t.stream;
-    if (!stepped) return;
+    __shared__ double red_u[64];
+    __shared__ int s_last;
+    if (!stepped) {
+        // no search for this track in this step: its first CTA still reports it (and takes part in advancing the step)
+        if (g.update && b == 0) track_update(c, track, step, false, reinterpret_cast<float*>(sm_loc), red_u);
+        return;
+    }
     trace_begin(c, step, TR_NCC);
     int win[4];
     search_window(bx_, by_, tw, th, c.W - tw + 1, c.H - th + 1, PP.rx, PP.ry, win);
@@ -1377,6 +1384,23 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
     if (lane == 0 && key) atomicMax(&t.peak, key);
     if (trc && tid == 0) trc[TR_TAIL * 2 + 1] = gtime();
     trace_end(c, step, TR_NCC);
+    if (!g.update) return;
+    // the last CTA of this track through the ticket (all peaks are in) runs the gate / EMA / state update: no k_update launch,
+    // no kernel boundary between the peak and the update (~2 us on B200).  CTAs outside a clamped window left early and do not count.
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int n_cta = (unsigned int)(((ww + 7) >> 3) * ((wh + CY * g.TR - 1) / (CY * g.TR)));
+        const unsigned int k = atomicAdd(&t.ticket, 1u);
+        s_last = (k == n_cta - 1u);
+        if (s_last) t.ticket = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (c.trace && tid == 0) c.trace[((step % kRing) * 8 + TR_UPDATE) * 2] = gtime();
+    track_update(c, track, step, true, reinterpret_cast<float*>(sm_loc), red_u);
+    trace_end(c, step, TR_UPDATE);
 }
 
 // (3c) k_ncc_fringe: the candidates the thread-tile grid leaves out (TileCfg: the single column x = 8C and/or the

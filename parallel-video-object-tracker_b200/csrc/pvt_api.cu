@@ -307,7 +307,7 @@ int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
 int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false, bool local = false, int extra_local = 0)
 {
-    if (local) return 3 + extra_local;   // ingest, [k_winstats,] k_ncc_local, k_update
+    if (local) return 2 + extra_local;   // ingest, [k_winstats,] k_ncc_local [, k_update]: extra_local counts the optional ones
     if (fused) return 3;   // ingest, k_winstats, k_step_fused
     return (st.NX > 0 ? 3 : 4) + ((t.pj * t.pd > 1) ? 1 : (t.tail_ps > 1 ? 2 : 1)) + (f.colg + f.rowg > 0 ? 1 : 0);
 }
@@ -316,7 +316,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool f
 int kernels_per_step(const pvt_ctx* c)
 {
     // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
-    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0, c->local.gstats);
+    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0, c->local.gstats + (c->local.update ? 0 : 1));
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -471,13 +471,16 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
                 LocalCfg g{};
                 g.TR = TR; g.PJ = PJ; g.PD = PD; g.bx = bx; g.by = by; g.nfma = nfma;
                 g.gstats = pass_g; g.sNX = std::max(p.stat.NX, 1); g.sNY = std::max(p.stat.NY, 1);
+                // update inside the kernel (last CTA of the track): measured 22.2 us per C2 step against 21.6 us with k_update as
+                // its own launch (one-shot code behind a ticket runs slower than the boundary it saves): opt-in, PVT_LOCAL_UPDATE=1
+                { const char* lu = getenv("PVT_LOCAL_UPDATE"); g.update = (lu && *lu == '1') ? 1 : 0; }
                 g.P = 8 + d.mtp;
                 while (g.P % 8 != 4) ++g.P;
                 g.tileH = kCY * TR + d.mth - 1;
                 g.TS = d.mth * 8 + 4;
                 const size_t red_bytes = (size_t)nfma * kLocalRed * 4;
                 if ((size_t)(2 * kCY * TR + 6) * (8 + d.mtw - 1) * 8 > red_bytes) continue;   // the statistics scratch lives in the reduction buffer
-                const size_t smem = (size_t)g.tileH * g.P * 4 + (size_t)nch * g.TS * 4 + red_bytes + (size_t)kCY * TR * 8 * 8 + 64;
+                const size_t smem = std::max((size_t)g.tileH * g.P * 4 + (size_t)nch * g.TS * 4 + red_bytes + (size_t)kCY * TR * 8 * 8 + 64, (size_t)d.mth * d.mtw * 4);
                 if (smem + 1024 > kSmemBudget) continue;
                 const double rows = (double)((d.mth + PD - 1) / PD + kCY - 1) * (nch / PJ);   // per-thread template rows incl. the window preload
                 if (rows < best) { best = rows; p.local = g; p.local_smem = smem; }
@@ -738,6 +741,13 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         { int r = launch_pdl(k_ncc_local<kCY>, dim3((unsigned)(d.max_tracks * p.local.bx * p.local.by)), dim3(threads), p.local_smem, c->compute, pdl_l, d, p.local); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_ncc_local"); if (r) return r; }
+        if (p.local.update) {   // the update ran inside k_ncc_local (last CTA of each track)
+            if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
+            if (forkl) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));
+            if (join3) CK(cudaStreamWaitEvent(c->compute, c->ev_join3, 0));
+            CK(cudaGetLastError());
+            return PVT_OK;
+        }
         if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
         // (a programmatic edge search ~> update -- the update's CTA starts early, prefetches the old template and blocks in
         //  griddepcontrol.wait -- was measured: the step went 21.6 -> 23.4 us, the early CTA slows the search it shares the GPU with)
