@@ -308,12 +308,18 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
     names = ["ingest", "colprefix", "rowsum", "ncc_search", "ncc_finalize", "update", "ncc_fringe", "ncc_tail_finalize"]
     if not T[:, 2, 0].any():
         names[1] = "winstats"          # k_winstats (one statistics kernel) stamps the first statistics slot only
-    timeline = {nm: round(float(np.median(T[:, k, 1] - T[:, k, 0])) / 1e3, 2) for k, nm in enumerate(names) if T[:, k, 0].any()}
+    search_kernel, kernels_per_step = tr.search_kind()
+    phase_slots = ()
+    if search_kernel in ("k_ncc_local", "k_ncc_tc") or search_kernel.startswith("k_ncc_search+"):
+        phase_slots = (6, 7) if search_kernel != "k_ncc_tc" else (4, 6, 7)   # these kernels use spare slots for CTA-0 phase stamps
+    names[3] = search_kernel.split("+")[0]
+    timeline = {nm: round(float(np.median(T[:, k, 1] - T[:, k, 0])) / 1e3, 2) for k, nm in enumerate(names)
+                if T[:, k, 0].any() and k not in phase_slots}
     # the search PHASE in the production graph: first start .. last end of k_ncc_search, k_ncc_fringe (which overlaps
     # the search: programmatic dependent launch, or a parallel branch in the K-split shape) and the tail reduction
-    ph = [k for k in (3, 6, 7) if T[:, k, 0].any()]
+    ph = [k for k in (3, 6, 7) if T[:, k, 0].any() and k not in phase_slots]
     phase_us = float(np.median(np.max(T[:, ph, 1], axis=1) - np.min(T[:, ph, 0], axis=1))) / 1e3
-    if T[:, 6, 0].any():
+    if T[:, 6, 0].any() and 6 not in phase_slots:
         timeline["ncc_fringe_start_after_search_start"] = round(float(np.median(T[:, 6, 0] - T[:, 3, 0])) / 1e3, 2)
         timeline["ncc_fringe_end_after_search_end"] = round(float(np.median(T[:, 6, 1] - T[:, 3, 1])) / 1e3, 2)
     timeline["step_to_step"] = round(float(np.median(np.diff(T[:, 0, 0]))) / 1e3, 2)
@@ -335,15 +341,20 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
         "value": value, "ms_per_step": ms / K, "launches": int(launches), "clocks": clocks, "conf_min": conf_min, "prewarm_steps": prewarm,
         "regions_ms": [round(r, 5) for r in regions], "regions_spread": (max(regions) - min(regions)) / ms, "gathered": gathered,
         "macs_per_step": macs_per_launch, "n_tracks": n_tracks, "wl": wl, "ingest_mode": ingest_mode,
-        "roofline": {"kernel": "k_ncc_search", "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": ncc_tf / fp32_peak, "traffic": ncu_traffic(wname)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
+        "roofline": {"kernel": search_kernel, "kernels_per_step": kernels_per_step, "bound": "fp32", "achieved": ncc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": ncc_tf / fp32_peak,
+                     # the same kernel inside the production multi-step graph, warm (device globaltimer: first CTA start .. last CTA end)
+                     "us_per_launch_in_graph": float(np.median(T[:, 3, 1] - T[:, 3, 0])) / 1e3,
+                     "frac_in_graph": 2.0 * kmacs_per_launch / max(float(np.median(T[:, 3, 1] - T[:, 3, 0])) * 1e-9, 1e-12) / 1e12 / fp32_peak,
+                     "traffic": ncu_traffic(wname)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
                      "traffic_source": ncu_traffic(wname)[1],
                      "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
                      "peak_measured": 0.985 * fp32_peak, "frac_of_measured": ncc_tf / (0.985 * fp32_peak),
                      "peak_measured_source": "tools/microbench.cu on B200: dependent-free FFMA stream sustains 98.5 % of nominal "
                                              "(profiles/microbench_r1.log); MEASURED_PEAKS.json has no FP32 entry",
                      "us_per_launch": ncc_s * 1e6, "macs_per_launch": kmacs_per_launch,
-                     "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps; "
+                     "how": "CUDA event-record nodes around the kernel inside the step's graph, identical pass of %d steps launched one "
+                            "by one (cold: the production graphs run 16 steps per launch -- us_per_launch_in_graph); "
                             "MACs = candidates of the kernel's thread-tile grid x tw x th" % Kp,
                      "search_phase": {"what": "first start .. last end of k_ncc_search, the overlapping k_ncc_fringe and the tail reduction in the "
                                               "production graph (device globaltimer stamps), all MACs of the step",

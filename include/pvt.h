@@ -253,6 +253,10 @@ PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);
 PVT_API int pvt_trace_enable(pvt_ctx* ctx, int on);
 PVT_API int pvt_trace_get(pvt_ctx* ctx, uint64_t* out, int max_steps);
 PVT_API int64_t pvt_launch_count(pvt_ctx* ctx); /* kernels launched by this context so far (graph nodes counted per launch) */
+/* which search kernel the context's plan runs per step (pvt_create decides from the geometry): writes its name into `name`
+ * ("k_ncc_search", "k_ncc_search+k_ncc_finalize" (K-split), "k_step_fused", "k_ncc_local", "k_ncc_tc", "k_ncc_direct") and
+ * returns the number of kernels one searched step launches. */
+PVT_API int pvt_search_kind(pvt_ctx* ctx, char* name, int name_bytes);
 /* device time of everything submitted between pvt_timer_start and pvt_timer_stop, CUDA events on the context's stream */
 PVT_API int pvt_timer_start(pvt_ctx* ctx);
 PVT_API int pvt_timer_stop(pvt_ctx* ctx, double* ms);

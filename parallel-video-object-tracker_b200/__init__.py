@@ -40,6 +40,7 @@ SYMBOLS = [
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
     "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query", "pvt_ncc_match_batched_f",
+    "pvt_search_kind",
 ]
 
 
@@ -102,6 +103,8 @@ def lib():
     L.pvt_last_error.restype = C.c_char_p
     L.pvt_launch_count.restype = C.c_int64
     L.pvt_launch_count.argtypes = [C.c_void_p]
+    L.pvt_search_kind.restype = C.c_int
+    L.pvt_search_kind.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.pvt_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.POINTER(Config)]
     L.pvt_destroy.argtypes = [C.c_void_p]
     L.pvt_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
@@ -365,6 +368,12 @@ class Tracker:
 
     def launch_count(self) -> int:
         return int(lib().pvt_launch_count(self._h))
+
+    def search_kind(self):
+        """(name of the search kernel this context's plan runs, kernels per searched step)."""
+        buf = C.create_string_buffer(64)
+        n = _ck(lib().pvt_search_kind(self._h, buf, 64))
+        return buf.value.decode(), n
 
     def timer_start(self):
         _ck(lib().pvt_timer_start(self._h))

@@ -2041,6 +2041,19 @@ int pvt_trace_get(pvt_ctx* c, uint64_t* out, int max_steps)
 
 int64_t pvt_launch_count(pvt_ctx* c) { return c ? c->launches : 0; }
 
+int pvt_search_kind(pvt_ctx* c, char* name, int name_bytes)
+{
+    if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");
+    const char* k = "k_ncc_search";
+    if (c->params.kernel == PVT_KERNEL_TC) k = "k_ncc_tc";
+    else if (c->params.kernel == PVT_KERNEL_DIRECT) k = "k_ncc_direct";
+    else if (c->local.TR > 0) k = "k_ncc_local";
+    else if (c->fused) k = "k_step_fused";
+    else if (c->tile.pj * c->tile.pd > 1) k = "k_ncc_search+k_ncc_finalize";
+    if (name && name_bytes > 0) { std::strncpy(name, k, (size_t)name_bytes - 1); name[name_bytes - 1] = 0; }
+    return c->kps;
+}
+
 int pvt_timer_start(pvt_ctx* c)
 {
     if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");

@@ -14,13 +14,20 @@ want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_tmem.sum", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]
+want_sub = ["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"]
 with open(out, "w") as f:
     f.write(f"# summary of {rep.split('/')[-1]} (ncu --set full --clock-control none --import-source on)\n")
     for w in want:
         for i, h in enumerate(hdr):
             if h == w:
                 f.write(f"{w:72s} {units[i]:16s} {[r[i] for r in data]}\n")
+    for w in want_sub:
+        for i, h in enumerate(hdr):
+            if h.endswith(w):
+                f.write(f"{h:72s} {units[i]:16s} {[r[i] for r in data]}\n")
     rows = list(csv.reader(io.StringIO(src)))
     secs, cur = [], None
     for r in rows:
@@ -50,4 +57,11 @@ with open(out, "w") as f:
         tma = [r[ix["Source"]].strip() for r in d if any(t in r[ix["Source"]] for t in ("UTMALDG", "UBLKCP", "SYNCS"))]
         f.write("\n# TMA / bulk-copy / mbarrier instructions in the SASS\n")
         for t in tma[:12]: f.write("  " + t + "\n")
+        tc = collections.Counter()
+        for r in d:
+            o = opc(r[ix["Source"]])
+            if o.startswith("UTC") or o in ("LDTM", "STTM"): tc[r[ix["Source"]].strip().split("(")[0][:60].split(",")[0].split(" [")[0]] += I(r, "Instructions Executed")
+        if tc:
+            f.write("\n# tensor-core / tensor-memory instructions executed (tcgen05: UTC*MMA, UTCBAR = commit, LDTM = tcgen05.ld)\n")
+            for k, v in tc.most_common(12): f.write(f"  {k:44s} {v:12d}\n")
 print(open(out).read())
