@@ -244,6 +244,12 @@ PVT_API int pvt_ncc_match_batched_f(int device, int formula, int n, const float*
 PVT_API int pvt_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y,
                            int32_t out[16]);
 
+/* The sink side of the reference loop (tracker/src/main.cpp:166  cv::rectangle(frame, bbox, {0,255,0}, 2)): paint the boxes
+ * (n x {x, y, w, h}) onto a BGR8 frame, in place, with cv::rectangle's thickness-2 pixel coverage (bit-identical to OpenCV 4.13).
+ * frame->memory says where the pixels live: device frames are painted where they are; host frames make the round trip through
+ * a staging buffer.  Boxes must lie inside the frame (the tracker's always do); bgr = {b, g, r}; NULL = the reference's green {0, 255, 0}. */
+PVT_API int pvt_draw_boxes(pvt_ctx* ctx, const pvt_frame* frame, int n, const int32_t* boxes_xywh, const uint8_t* bgr);
+
 /* measurement hooks */
 PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA events, plain stream launches */
 PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);

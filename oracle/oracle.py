@@ -210,3 +210,19 @@ def track_clip_ghc(frames: np.ndarray, roi, rx=60, ry=60, min_conf=0.40, global_
         raise ValueError(f"orc_track_clip_ghc rc={rc}")
     out = np.array([(r.x, r.y, r.w, r.h, r.conf, r.moved, r.updated, r.searched, r.lost_count, r.use_global) for r in recs], np.float64)
     return out, templ
+
+
+def draw_rectangle(img: np.ndarray, box, bgr=(0, 255, 0)) -> np.ndarray:
+    """tracker/src/main.cpp:166  cv::rectangle(frame, bbox, {0,255,0}, 2) for a box inside the frame, restated: the 3-pixel band
+    around the lines (x0,y0)-(x1,y1), x1 = x+w-1, y1 = y+h-1, minus the four outer corner pixels (pinned to cv2 4.13.0 in
+    tests/test_oracle_golden.py).  Paints in place and returns img."""
+    H, W = img.shape[:2]
+    x, y, w, h = (int(v) for v in box)
+    x0, y0, x1, y1 = x, y, x + w - 1, y + h - 1
+    ys, xs = np.mgrid[max(0, y0 - 1):min(H, y1 + 2), max(0, x0 - 1):min(W, x1 + 2)]
+    hole = (xs >= x0 + 2) & (xs <= x1 - 2) & (ys >= y0 + 2) & (ys <= y1 - 2)
+    corner = ((xs == x0 - 1) | (xs == x1 + 1)) & ((ys == y0 - 1) | (ys == y1 + 1))
+    m = ~hole & ~corner
+    img[ys[m], xs[m]] = np.asarray(bgr, img.dtype)
+    return img
+

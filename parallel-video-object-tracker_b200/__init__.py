@@ -40,7 +40,7 @@ SYMBOLS = [
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
     "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query", "pvt_ncc_match_batched_f",
-    "pvt_search_kind",
+    "pvt_search_kind", "pvt_draw_boxes",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
     L.pvt_last_error.restype = C.c_char_p
     L.pvt_launch_count.restype = C.c_int64
     L.pvt_launch_count.argtypes = [C.c_void_p]
+    L.pvt_draw_boxes.restype = C.c_int
+    L.pvt_draw_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p]
     L.pvt_search_kind.restype = C.c_int
     L.pvt_search_kind.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.pvt_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.POINTER(Config)]
@@ -368,6 +370,14 @@ class Tracker:
 
     def launch_count(self) -> int:
         return int(lib().pvt_launch_count(self._h))
+
+    def draw_boxes(self, frame, boxes, bgr=None):
+        """main.cpp:166: cv::rectangle(frame, bbox, {0,255,0}, 2) for every box, in place.  frame: HxWx3 u8 numpy array or a Frame."""
+        f = frame if isinstance(frame, Frame) else host_frame(frame)
+        b = np.ascontiguousarray(np.asarray(boxes, np.int32).reshape(-1, 4))
+        col = (C.c_uint8 * 3)(*bgr) if bgr is not None else None
+        _ck(lib().pvt_draw_boxes(self._h, C.byref(f), len(b), b.ctypes.data_as(C.POINTER(C.c_int32)), col))
+        return frame
 
     def search_kind(self):
         """(name of the search kernel this context's plan runs, kernels per searched step)."""

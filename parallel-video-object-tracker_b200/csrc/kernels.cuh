@@ -1344,6 +1344,22 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
                     for (int cx = 0; cx < 8; ++cx) acc[i][cx] += racc[i][cx];
             }
         }
+    } else if (g.gstats) {
+        // the CTA's spare threads (behind the FMA threads in its last warp) wait for k_winstats' completion count and bring the
+        // patch's normalisers into shared memory WHILE the others compute: the acquire poll and the loads are two L2 round trips
+        // (~1.3 us) that used to sit between the loop and the peak
+        const int nsp = (int)blockDim.x - g.nfma, sp = tid - g.nfma;
+        const int l0 = max(0, g.nfma - (tid & ~31));                // first spare lane of this warp: it polls for the warp's spare lanes
+        if (lane == l0) {
+            const unsigned int n_stat = (unsigned int)(((ww + g.sNX - 1) / g.sNX) * ((wh + g.sNY - 1) / g.sNY));
+            if (!spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
+        }
+        __syncwarp(0xffffffffu << l0);
+        const double* dng = c.denom + (size_t)track * c.Hmax * c.Wmax;
+        for (int idx = sp; idx < nrow * 8; idx += nsp) {
+            const int y = idx >> 3, x = idx & 7;
+            s_dn[idx] = px0 + x < ww ? __ldcg(dng + (size_t)(py0 + y) * ww + px0 + x) : 0.0;
+        }
     }
     if (trc && tid == 0) trc[TR_FRINGE * 2 + 1] = gtime();
     __syncthreads();                                               // (A) statistics done: the scratch becomes the reduction buffer
@@ -1355,7 +1371,8 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
             po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         }
     }
-    if (g.gstats && tid == 0) {                                    // k_winstats (the other graph branch) has stored this window's normalisers?
+    const bool dn_staged = !g.gstats || g.nfma < (int)blockDim.x;  // normalisers already in s_dn (own statistics, or the spare threads')
+    if (!dn_staged && tid == 0) {                                  // no spare thread in this plan: wait here
         const unsigned int n_stat = (unsigned int)(((ww + g.sNX - 1) / g.sNX) * ((wh + g.sNY - 1) / g.sNY));
         if (!spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
     }
@@ -1365,7 +1382,7 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
         const int y = tid >> 3, x = tid & 7, tr = y / CY, i = y - tr * CY;
         if (px0 + x < ww) {
             const unsigned int idx = (unsigned int)((py0 + y) * ww + px0 + x);
-            const double dnv = g.gstats ? __ldcg(c.denom + (size_t)track * c.Hmax * c.Wmax + idx) : s_dn[tid];   // on its way during the sums
+            const double dnv = dn_staged ? s_dn[tid] : __ldcg(c.denom + (size_t)track * c.Hmax * c.Wmax + idx);
             float a = 0.f;
             const int parts = g.PJ * g.PD;
             const float* src = s_red + (size_t)(tr * parts) * kLocalRed + i * 8 + x;
@@ -2094,6 +2111,32 @@ __global__ void k_hold(Ctx c)
     }
     __syncthreads();
     if (threadIdx.x == 0) *c.step = step + 1ull;
+}
+
+// =============================================================================================
+// (6) overlay: the sink side of the loop, tracker/src/main.cpp:166  cv::rectangle(frame, bbox, {0,255,0}, 2)
+//     cv::rectangle(Rect) with thickness 2 on an 8-bit image paints the 3-pixel band around the lines (x0,y0)-(x1,y1),
+//     x1 = x + w - 1, y1 = y + h - 1, minus the four outer corner pixels (round line caps): the outer box [x0-1, x1+1] x
+//     [y0-1, y1+1] without its hole [x0+2, x1-2] x [y0+2, y1-2] and its four corners, clipped to the image
+//     (pinned to cv2 4.13.0 by tests/test_overlay.py).  One thread per pixel of the outer box; grid.y = box.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_overlay(unsigned char* img, size_t step, int W, int H, const int* boxes, int nbox, int b, int g, int r)
+{
+    const int k = blockIdx.y;
+    if (k >= nbox) return;
+    const int x = boxes[4 * k], y = boxes[4 * k + 1], w = boxes[4 * k + 2], h = boxes[4 * k + 3];
+    if (w <= 0 || h <= 0) return;
+    const int x0 = x, y0 = y, x1 = x + w - 1, y1 = y + h - 1;
+    const int ow = x1 - x0 + 3, oh = y1 - y0 + 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ow * oh; i += gridDim.x * blockDim.x) {
+        const int px = x0 - 1 + i % ow, py = y0 - 1 + i / ow;
+        if (px < 0 || py < 0 || px >= W || py >= H) continue;
+        const bool hole = px >= x0 + 2 && px <= x1 - 2 && py >= y0 + 2 && py <= y1 - 2;
+        const bool corner = (px == x0 - 1 || px == x1 + 1) && (py == y0 - 1 || py == y1 + 1);
+        if (hole || corner) continue;
+        unsigned char* q = img + (size_t)py * step + 3 * px;
+        q[0] = (unsigned char)b; q[1] = (unsigned char)g; q[2] = (unsigned char)r;
+    }
 }
 
 }  // namespace pvt

@@ -1981,6 +1981,47 @@ int pvt_ncc_match(int device, int mode, const float* frame, int fw, int fh, size
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------------
+int pvt_draw_boxes(pvt_ctx* c, const pvt_frame* f, int n, const int32_t* boxes, const uint8_t* bgr)
+{
+    if (!c || !f) return fail(PVT_ERR_INVALID, "ctx / frame is NULL");
+    if (n < 0 || (n > 0 && !boxes)) return fail(PVT_ERR_INVALID, "boxes is NULL");
+    if (f->format != PVT_FMT_BGR8) return fail(PVT_ERR_INVALID, "pvt_draw_boxes paints BGR8 frames (main.cpp:166 draws on the decoded frame)");
+    if (!f->data || f->step < (size_t)c->cfg.frame_w * 3) return fail(PVT_ERR_INVALID, "frame.data is NULL or frame.step smaller than one row");
+    if (n == 0) return PVT_OK;
+    const int W = c->cfg.frame_w, H = c->cfg.frame_h;
+    // the tracker's boxes always lie inside the frame (they come from a map position); OpenCV clips lines that leave the image
+    // before it thickens them, which changes their caps -- that case is not restated, so it is rejected rather than painted differently
+    for (int i = 0; i < n; ++i) {
+        const int32_t* b = boxes + 4 * i;
+        if (b[2] <= 0 || b[3] <= 0 || b[0] < 0 || b[1] < 0 || b[0] + b[2] > W || b[1] + b[3] > H)
+            return fail(PVT_ERR_INVALID, "pvt_draw_boxes: box " + std::to_string(i) + " is empty or leaves the frame");
+    }
+    CK(cudaSetDevice(c->cfg.device));
+    { int r = pvt_sync(c); if (r) return r; }
+    int* d_boxes = nullptr;
+    CK(cudaMalloc(&d_boxes, sizeof(int) * 4 * (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(d_boxes, boxes, sizeof(int) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->compute);
+    unsigned char* img = (unsigned char*)f->data;
+    size_t step = f->step;
+    void* stage = nullptr;
+    if (e == cudaSuccess && f->memory != PVT_MEM_DEVICE) {   // host frame: round trip through a staging buffer
+        e = cudaMalloc(&stage, (size_t)W * 3 * H);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(stage, (size_t)W * 3, f->data, f->step, (size_t)W * 3, H, cudaMemcpyHostToDevice, c->compute);
+        img = (unsigned char*)stage; step = (size_t)W * 3;
+    }
+    if (e == cudaSuccess) {
+        const int b = bgr ? bgr[0] : 0, g = bgr ? bgr[1] : 255, r = bgr ? bgr[2] : 0;
+        k_overlay<<<dim3(8, (unsigned)n), 256, 0, c->compute>>>(img, step, W, H, d_boxes, n, b, g, r);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && stage) e = cudaMemcpy2DAsync((void*)f->data, f->step, stage, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
+    cudaFree(d_boxes);
+    if (stage) cudaFree(stage);
+    if (e != cudaSuccess) return fail(PVT_ERR_CUDA, std::string("pvt_draw_boxes: ") + cudaGetErrorString(e));
+    return PVT_OK;
+}
+
 int pvt_profile_enable(pvt_ctx* c, int on)
 {
     if (!c) return fail(PVT_ERR_INVALID, "ctx is NULL");

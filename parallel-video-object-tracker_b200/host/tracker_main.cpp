@@ -6,7 +6,9 @@
 // Differences forced by this image (no OpenCV C++, no video codecs):
 //   * input is a raw BGR clip instead of ../data/car.mp4:   magic "PVTBGR1\n", int32 W, H, N, then N*H*W*3 bytes
 //   * the ROI comes from --roi x,y,w,h instead of cv::selectROI (main.cpp:63; the reference has no default ROI)
-//   * instead of an annotated .mp4 the per-frame bbox/confidence goes to --out FILE as CSV (main.cpp:166 only draws it)
+//   * instead of an annotated .mp4 (no encoder here) the per-frame bbox/confidence goes to --out FILE as CSV, and --video-out FILE
+//     writes the annotated frames -- cv::rectangle(frame, bbox, {0,255,0}, 2) of main.cpp:166, painted by pvt_draw_boxes with
+//     OpenCV's pixel coverage -- as a raw clip in the input's own container ("PVTBGR1\n", W, H, N, frames)
 //   * --gpu-formula (new) scores with the eps formula of the reference's CUDA kernels (pvt_formula) instead of the --cpu path's
 //   * --cpu is rejected: the library has no CPU path (the reference's CPU mode is restated in oracle/, test-only)
 #include <chrono>
@@ -30,7 +32,7 @@ static const double TEMPLATE_UPDATE_LR = 0.10;
 
 int main(int argc, char** argv)
 {
-    std::string mode = NCC_MODE, input, out_csv;
+    std::string mode = NCC_MODE, input, out_csv, out_video;
     int batch = BATCH_SIZE;
     pvt::Rect bbox;
     bool have_roi = false, gpu_formula = false;
@@ -43,6 +45,7 @@ int main(int argc, char** argv)
         else if (arg.rfind("--batch=", 0) == 0) { mode = "batch"; batch = std::max(1, std::atoi(arg.substr(8).c_str())); }
         else if (arg == "--roi" && i + 1 < argc) { have_roi = std::sscanf(argv[++i], "%d,%d,%d,%d", &bbox.x, &bbox.y, &bbox.width, &bbox.height) == 4; }
         else if (arg == "--out" && i + 1 < argc) out_csv = argv[++i];
+        else if (arg == "--video-out" && i + 1 < argc) out_video = argv[++i];
         else if (arg == "--gpu-formula") gpu_formula = true;
         else if (arg[0] != '-') input = arg;
     }
@@ -89,6 +92,13 @@ int main(int argc, char** argv)
 
         std::ofstream csv;
         if (!out_csv.empty()) { csv.open(out_csv); csv << "frame,x,y,w,h,conf,moved,updated,searched\n"; }
+        std::ofstream vout;                                   // cv::VideoWriter writer(...)  main.cpp:76-82
+        if (!out_video.empty()) {
+            vout.open(out_video, std::ios::binary);
+            if (!vout) { std::cerr << " Cannot open video writer.\n"; pvt_destroy(ctx); return -1; }
+            const int32_t hdr[3] = {W, H, N - 1};
+            vout.write("PVTBGR1\n", 8); vout.write((const char*)hdr, 12);
+        }
         int frame_count = 0;
         double t_tot = 0.0;
         auto t_start = std::chrono::steady_clock::now();
@@ -99,6 +109,11 @@ int main(int argc, char** argv)
             pvt::check(pvt_step(ctx, 1, &fr, &r));  // main.cpp:98-161 on the GPU
             t_tot += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
             bbox.x = r.x; bbox.y = r.y;
+            if (vout.is_open()) {                             // cv::rectangle(frame, bbox, {0,255,0}, 2); writer.write(frame);  main.cpp:166-167
+                const int32_t box[4] = {r.x, r.y, r.w, r.h};
+                pvt::check(pvt_draw_boxes(ctx, &fr, 1, box, nullptr));
+                vout.write((const char*)frame.data(), (std::streamsize)frame.size());
+            }
             if (csv.is_open()) csv << k << ',' << r.x << ',' << r.y << ',' << r.w << ',' << r.h << ',' << r.conf << ',' << (int)r.moved << ',' << (int)r.updated << ',' << (int)r.searched << "\n";
             frame_count++;
         }
