@@ -1344,22 +1344,6 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
                     for (int cx = 0; cx < 8; ++cx) acc[i][cx] += racc[i][cx];
             }
         }
-    } else if (g.gstats) {
-        // the CTA's spare threads (behind the FMA threads in its last warp) wait for k_winstats' completion count and bring the
-        // patch's normalisers into shared memory WHILE the others compute: the acquire poll and the loads are two L2 round trips
-        // (~1.3 us) that used to sit between the loop and the peak
-        const int nsp = (int)blockDim.x - g.nfma, sp = tid - g.nfma;
-        const int l0 = max(0, g.nfma - (tid & ~31));                // first spare lane of this warp: it polls for the warp's spare lanes
-        if (lane == l0) {
-            const unsigned int n_stat = (unsigned int)(((ww + g.sNX - 1) / g.sNX) * ((wh + g.sNY - 1) / g.sNY));
-            if (!spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
-        }
-        __syncwarp(0xffffffffu << l0);
-        const double* dng = c.denom + (size_t)track * c.Hmax * c.Wmax;
-        for (int idx = sp; idx < nrow * 8; idx += nsp) {
-            const int y = idx >> 3, x = idx & 7;
-            s_dn[idx] = px0 + x < ww ? __ldcg(dng + (size_t)(py0 + y) * ww + px0 + x) : 0.0;
-        }
     }
     if (trc && tid == 0) trc[TR_FRINGE * 2 + 1] = gtime();
     __syncthreads();                                               // (A) statistics done: the scratch becomes the reduction buffer
@@ -1371,8 +1355,9 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
             po[2 * i + 1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         }
     }
-    const bool dn_staged = !g.gstats || g.nfma < (int)blockDim.x;  // normalisers already in s_dn (own statistics, or the spare threads')
-    if (!dn_staged && tid == 0) {                                  // no spare thread in this plan: wait here
+    // (measured and dropped: the spare lanes behind the FMA threads of the last warp polling the statistics count and staging the
+    //  normalisers during the loop -- the divergent halves of that warp run one after the other: peak +15.1 instead of +10.8 us)
+    if (g.gstats && tid == 0) {                                    // k_winstats (the other graph branch) has stored this window's normalisers?
         const unsigned int n_stat = (unsigned int)(((ww + g.sNX - 1) / g.sNX) * ((wh + g.sNY - 1) / g.sNY));
         if (!spin_until(&t.stats_done, n_stat)) { *c.fault = 1u; __threadfence_system(); }
     }
@@ -1382,7 +1367,7 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
         const int y = tid >> 3, x = tid & 7, tr = y / CY, i = y - tr * CY;
         if (px0 + x < ww) {
             const unsigned int idx = (unsigned int)((py0 + y) * ww + px0 + x);
-            const double dnv = dn_staged ? s_dn[tid] : __ldcg(c.denom + (size_t)track * c.Hmax * c.Wmax + idx);
+            const double dnv = g.gstats ? __ldcg(c.denom + (size_t)track * c.Hmax * c.Wmax + idx) : s_dn[tid];   // on its way during the sums
             float a = 0.f;
             const int parts = g.PJ * g.PD;
             const float* src = s_red + (size_t)(tr * parts) * kLocalRed + i * 8 + x;

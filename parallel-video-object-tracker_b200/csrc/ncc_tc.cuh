@@ -242,22 +242,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         const int u_o = __shfl_sync(0xffffffffu, o, 0), u_tw = __shfl_sync(0xffffffffu, tw, 0), u_ww = __shfl_sync(0xffffffffu, ww, 0);
         const int u_th = __shfl_sync(0xffffffffu, th, 0);
         const int NW = g.AG * 8;
-        // per K-step: A descriptor (template row 0), B descriptor offset (16-byte units from a run's start), D column, idesc
+        // per K-step: A descriptor (template row 0), B descriptor offset (16-byte units from a stage's start), D column, idesc.
+        // BOTH DIGITS IN ONE MMA: the blocks of the two digits are interleaved in the ring (block d of digit dg at 2 d + dg), so
+        // the N index a'' = 2 a' + dg walks candidate group a', digit dg at the same 128-byte stride (SBO 128) and a 16-column
+        // K block advances 4 blocks (LBO 512); the accumulator holds (group, digit, 8 candidates) = 16 a' + 8 dg + s.  One MMA of
+        // N = 16 n8 instead of two of N = 8 n8: the instruction's fixed cost (~94 - 120 cycles for any N <= 128, tools/tc_probe.cu) is
+        // paid half as often.
+        // (a band of more than 16 candidate groups -- templates wider than ~96 pixels -- exceeds N = 256 and is issued in two segments)
         uint64_t ad[kTcKMax];
-        uint32_t boff[kTcKMax], dcol[kTcKMax], idn[kTcKMax];
-        bool on[kTcKMax];
+        uint32_t boff[kTcKMax][2], dcol[kTcKMax][2], idn[kTcKMax][2];
+        bool on[kTcKMax][2];
 #pragma unroll
         for (int kc = 0; kc < kTcKMax; ++kc) {
             int a0 = 0, n8 = 0;
             if (kc < g.KS) tc_band(kc, u_o, u_tw, u_ww, g.AG, &a0, &n8);
-            on[kc] = n8 > 0;
             ad[kc] = tc_desc(sa + (uint32_t)(2 * kc) * (uint32_t)CH, (uint32_t)CH, 128);
-            boff[kc] = (uint32_t)(4 * kc + a0) * 8u;
-            dcol[kc] = (uint32_t)a0 * 8u;
-            idn[kc] = tc_idesc(n8 * 8);
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg) {
+                const int b0 = a0 + 16 * sg, nn = min(16, n8 - 16 * sg);
+                on[kc][sg] = nn > 0;
+                boff[kc][sg] = (uint32_t)(8 * kc + 2 * b0) * 8u;
+                dcol[kc][sg] = (uint32_t)b0 * 16u;
+                idn[kc][sg] = tc_idesc(max(nn, 2) * 16);
+            }
         }
-        const uint64_t bd0 = tc_desc(sb, 256, 128);
-        const uint32_t id_full = tc_idesc(NW);
+        const uint64_t bd0 = tc_desc(sb, 512, 128);
+        const uint32_t id_half = tc_idesc(NW);                  // first template row: AG / 2 groups x 2 digits x 8 = NW columns per half
         mbar_wait(bar_tile, 0);
         if (trc && lane == 0) trc[TR_FRINGE * 2] = gtime();
         for (int dy = 0; dy < u_th; ++dy) {
@@ -265,24 +275,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
             tc_wait(&full[st], (uint32_t)(dy / g.stages) & 1u, g.spin);
             tc_fence_after();
             if (elect_one()) {
+                const uint64_t bst = bd0 + (uint64_t)((uint32_t)(st * 2 * blk_bytes) >> 4);
                 if (dy == 0) {
-                    // first template row: full-width rectangles, the first one overwrites -> every accumulator column is
-                    // initialised (zero blocks outside the band contribute nothing)
+                    // first template row: full-width rectangles (in two halves of AG / 2 candidate groups: N <= 256), the first
+                    // one of each half overwrites -> every accumulator column is initialised (zero blocks outside the band
+                    // contribute nothing)
 #pragma unroll
-                    for (int dg = 0; dg < 2; ++dg)
+                    for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
                         for (int kc = 0; kc < kTcKMax; ++kc)
                             if (kc < g.KS)
-                                tc_mma(tmem + (uint32_t)(dg * NW), ad[kc], bd0 + (uint64_t)((uint32_t)((st * 2 + dg) * blk_bytes) >> 4) + (uint64_t)(4 * kc * 8),
-                                       id_full, kc > 0 ? 1u : 0u);
+                                tc_mma(tmem + (uint32_t)(hf * NW), ad[kc], bst + (uint64_t)((8 * kc + hf * g.AG) * 8), id_half, kc > 0 ? 1u : 0u);
                 } else {
 #pragma unroll
-                    for (int dg = 0; dg < 2; ++dg)
+                    for (int kc = 0; kc < kTcKMax; ++kc)
 #pragma unroll
-                        for (int kc = 0; kc < kTcKMax; ++kc)
-                            if (on[kc])
-                                tc_mma(tmem + (uint32_t)(dg * NW) + dcol[kc], ad[kc] + (uint64_t)dy,
-                                       bd0 + (uint64_t)((uint32_t)((st * 2 + dg) * blk_bytes) >> 4) + (uint64_t)boff[kc], idn[kc], 1u);
+                        for (int sg = 0; sg < 2; ++sg)
+                            if (on[kc][sg]) tc_mma(tmem + dcol[kc][sg], ad[kc] + (uint64_t)dy, bst + (uint64_t)boff[kc][sg], idn[kc][sg], 1u);
                 }
                 tc_commit(&empty[st]);                         // arrives when the MMAs that read this stage have completed
                 if (dy == u_th - 1) tc_commit(bar_done);
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
                     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
                     v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
                 }
-                *reinterpret_cast<uint4*>(sB + (size_t)(st * 2 + dg) * blk_bytes + (size_t)d * 128 + s * 16) = v;
+                *reinterpret_cast<uint4*>(sB + (size_t)(st * 2) * blk_bytes + (size_t)(2 * d + dg) * 128 + s * 16) = v;   // digits interleaved
             }
             fence_async_smem();                                // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -345,9 +354,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             uint32_t hi[16], lo[16];
-            const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
-            tc_ld16(ta + (uint32_t)NW, hi);                        // digit 1 accumulator
-            tc_ld16(ta, lo);                                       // digit 0
+            {
+                // accumulator columns: group a' = c0 / 8 at [16 a', 16 a' + 16) = 8 x digit 0, then 8 x digit 1; the next group follows
+                uint32_t v1[16], v2[16];
+                const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(2 * c0);
+                tc_ld16(ta, v1);
+                tc_ld16(ta + 16u, v2);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { lo[i] = v1[i]; hi[i] = v1[8 + i]; lo[8 + i] = v2[i]; hi[8 + i] = v2[8 + i]; }
+            }
             tc_ld_wait();
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
