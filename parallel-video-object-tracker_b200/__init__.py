@@ -204,6 +204,20 @@ def device_frame(ptr: int, step: int, fmt=FMT_BGR8, stream=0) -> Frame:
     return Frame(stream, fmt, MEM_DEVICE, 0, ptr, step)
 
 
+class RingArray:
+    """A frame ring as the contiguous pvt_frame array pvt_submit_sequence takes (ring_len x n_frames), built once."""
+
+    def __init__(self, ring):
+        self.n_frames = len(ring[0])
+        self.ring_len = len(ring)
+        flat = [f for st in ring for f in st]
+        self.arr = (Frame * len(flat))(*flat)
+        self._keep = flat
+
+    def __len__(self):
+        return self.ring_len
+
+
 class PinnedBuffer:
     """cudaHostAlloc'ed bytes exposed as a numpy array (for frames streamed from the host)."""
 
@@ -296,10 +310,14 @@ class Tracker:
         return arr  # keep host buffers alive until collect()
 
     def submit_sequence(self, n_steps, ring, collect_every=0, want_results=False):
-        """main.cpp:93-169 as one call: n_steps steps cycling over `ring`, a list of per-step frame lists."""
-        n_frames = len(ring[0])
-        flat = [f for st in ring for f in st]
-        arr = (Frame * len(flat))(*flat)
+        """main.cpp:93-169 as one call: n_steps steps cycling over `ring`, a list of per-step frame lists -- or a RingArray built
+        once from such a list (a C caller passes the same pvt_frame array every time; building it is not part of the call)."""
+        if isinstance(ring, RingArray):
+            arr, n_frames, ring = ring.arr, ring.n_frames, ring
+        else:
+            n_frames = len(ring[0])
+            flat = [f for st in ring for f in st]
+            arr = (Frame * len(flat))(*flat)
         out = np.zeros((n_steps, self.max_tracks), RESULT_DTYPE) if (want_results and collect_every > 0) else None
         _ck(lib().pvt_submit_sequence(self._h, n_steps, n_frames, arr, len(ring), collect_every,
                                       out.ctypes.data if out is not None else None))
