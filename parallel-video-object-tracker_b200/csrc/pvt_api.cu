@@ -37,6 +37,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 constexpr int kMultiStep = 4;   // steps per launch of graph_multi: a graph-to-graph boundary costs ~4 us on the device, an edge inside a graph ~1.5 us
+constexpr int kMaxGraphSteps = 64; // largest exact-length step graph (latency shape): the results ring holds 64 steps
 constexpr int kLongStep = 16;   // ... and of graph_long (latency shape only: there 4 us per four 27 us steps is still 4 %)
 constexpr int kStageDepth = 3;  // host frames in flight per stream (H2D overlaps the previous step's kernels)
 constexpr size_t kSmemBudget = 227u * 1024u;
@@ -105,6 +106,10 @@ struct pvt_ctx {
     cudaGraphExec_t graph_multi = nullptr;   // kMultiStep consecutive time steps in one launch (resident frame rings)
     cudaGraphExec_t graph_pf = nullptr, graph_multi_pf = nullptr;   // the same with k_prefetch_roi (pinned host rings)
     cudaGraphExec_t graph_long = nullptr, graph_long_pf = nullptr;  // kLongStep steps per launch (K-split shape)
+    // latency shape: graphs of exactly n consecutive steps, built on first use ([0]: device-resident ring, [1]: pinned host ring with
+    // the prefetch branch).  A 20-step sequence is then ONE launch: the host is out of the loop for the whole sequence (two launches
+    // left a window in which a busy host -- eight ranks, their NCCL threads -- stalls the device between them).
+    cudaGraphExec_t graph_n[2][kMaxGraphSteps + 1] = {};
     cudaEvent_t pev[5][2]{};           // profiling: event-record NODES inside graph_prof, one pair per kernel class (+ k_ncc_search alone)
     bool graph_valid = false;
     std::vector<void*> allocs;
@@ -903,6 +908,36 @@ int add_global_tail(pvt_ctx* c, cudaGraph_t g, const cudaGraphNode_t* deps, size
     return PVT_OK;
 }
 
+// every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
+int capture_steps_graph(pvt_ctx* c, const Pass& p, int n, cudaGraphExec_t* out)
+{
+    cudaGraph_t gs = nullptr;
+    CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
+    int rr = PVT_OK;
+    for (int k = 0; k < n && !rr; ++k) rr = launch_step_kernels(c, p, false, true);
+    cudaError_t ee = cudaStreamEndCapture(c->compute, &gs);
+    if (rr) return rr;
+    CK(ee);
+    CK(cudaGraphInstantiate(out, gs, 0));
+    CK(cudaGraphDestroy(gs));
+    CK(cudaGraphUpload(*out, c->compute));   // the first launch must not pay the upload inside a caller's timed loop
+    return PVT_OK;
+}
+
+// latency shape: the graph of exactly n steps (built on first use)
+int steps_graph(pvt_ctx* c, int n, bool pf, cudaGraphExec_t* out)
+{
+    cudaGraphExec_t& g = c->graph_n[pf ? 1 : 0][n];
+    if (!g) {
+        Pass p = local_pass(c);
+        p.prefetch = pf;
+        int r = capture_steps_graph(c, p, n, &g);
+        if (r) return r;
+    }
+    *out = g;
+    return PVT_OK;
+}
+
 int build_graphs(pvt_ctx* c)
 {
     if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -944,20 +979,10 @@ int build_graphs(pvt_ctx* c)
     CK(cudaGraphUpload(c->graph, c->compute));
     for (cudaGraphExec_t* ge : {&c->graph_multi, &c->graph_long, &c->graph_pf, &c->graph_multi_pf, &c->graph_long_pf})
         if (*ge) { cudaGraphExecDestroy(*ge); *ge = nullptr; }
-    // every kernel finds its frame through the device-side step counter, so consecutive steps can share one launch
-    auto capture_steps = [&](const Pass& p, int n, cudaGraphExec_t* out) -> int {
-        cudaGraph_t gs = nullptr;
-        CK(cudaStreamBeginCapture(c->compute, cudaStreamCaptureModeThreadLocal));
-        int rr = PVT_OK;
-        for (int k = 0; k < n && !rr; ++k) rr = launch_step_kernels(c, p, false, true);
-        cudaError_t ee = cudaStreamEndCapture(c->compute, &gs);
-        if (rr) return rr;
-        CK(ee);
-        CK(cudaGraphInstantiate(out, gs, 0));
-        CK(cudaGraphDestroy(gs));
-        CK(cudaGraphUpload(*out, c->compute));   // the first launch must not pay the upload inside a caller's timed loop
-        return PVT_OK;
-    };
+    for (int a = 0; a < 2; ++a)
+        for (int n = 0; n <= kMaxGraphSteps; ++n)
+            if (c->graph_n[a][n]) { cudaGraphExecDestroy(c->graph_n[a][n]); c->graph_n[a][n] = nullptr; }
+    auto capture_steps = [&](const Pass& p, int n, cudaGraphExec_t* out) -> int { return capture_steps_graph(c, p, n, out); };
     const bool latency_shape = c->params.kernel != PVT_KERNEL_DIRECT && lp.tile.pj * lp.tile.pd > 1;
     if (!c->lost_mode) {
         if ((r = capture_steps(lp, kMultiStep, &c->graph_multi))) return r;
@@ -1261,6 +1286,9 @@ int pvt_destroy(pvt_ctx* c)
     for (int k = 0; k < 5; ++k) { if (c->pev[k][0]) cudaEventDestroy(c->pev[k][0]); if (c->pev[k][1]) cudaEventDestroy(c->pev[k][1]); }
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_table) cudaFreeHost(c->h_table);
+    for (int a = 0; a < 2; ++a)
+        for (int n = 0; n <= kMaxGraphSteps; ++n)
+            if (c->graph_n[a][n]) cudaGraphExecDestroy(c->graph_n[a][n]);
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_fault) cudaFreeHost(c->h_fault);
     for (int i = 0; i < kRing; ++i) if (c->table_ev[i]) cudaEventDestroy(c->table_ev[i]);
@@ -1702,9 +1730,21 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             auto fits = [&](cudaGraphExec_t ge, int n) {
                 return !batch && ge && s + n <= n_steps && (collect_every <= 0 || (s % collect_every) + n <= collect_every);
             };
-            const int group = fits(g_long, kLongStep) ? kLongStep : fits(g_multi, kMultiStep) ? kMultiStep : 1;
+            int group = fits(g_long, kLongStep) ? kLongStep : fits(g_multi, kMultiStep) ? kMultiStep : 1;
+            cudaGraphExec_t ge = group == kLongStep ? g_long : g_multi;
+            if (g_long && !batch) {
+                // latency shape: everything up to the next result read-back (at most 64 steps) in ONE launch
+                int n = n_steps - s;
+                if (collect_every > 0) n = std::min(n, collect_every - (s % collect_every));
+                n = std::min(n, kMaxGraphSteps);
+                if (n > 1) {
+                    int r3 = steps_graph(c, n, pf, &ge);
+                    if (r3) return r3;
+                    group = n;
+                }
+            }
             if (group > 1) {
-                CK(cudaGraphLaunch(group == kLongStep ? g_long : g_multi, c->compute));
+                CK(cudaGraphLaunch(ge, c->compute));
                 c->launches += (int64_t)group * (c->kps + (pf ? 1 : 0));
                 c->submitted += group;
                 s += group - 1;
