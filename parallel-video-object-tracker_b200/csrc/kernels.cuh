@@ -1137,6 +1137,7 @@ struct LocalCfg {
                          //    (TrackState.stats_done counts its CTAs); 0: computed here from the tile, before the loop
     int sNX, sNY;        // k_winstats' tile (StatCfg) -> how many of its CTAs store normalisers for a (clamped) window
     int update;          // 1: the track's last CTA (ticket) runs track_update; 0: k_update follows as its own launch
+    int late_trigger;    // 1: griddepcontrol.launch_dependents behind the FMA loop (k_update launched with a programmatic dependency)
 };
 constexpr int kLocalRed = 8 * kCY + 4;   // floats per thread in the reduction buffer (44: conflict-free float4 stores)
 
@@ -1144,7 +1145,7 @@ template <int CY>
 __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
 {
     extern __shared__ __align__(16) unsigned char sm_loc[];
-    pdl_trigger();
+    if (!g.late_trigger) pdl_trigger();
     const int per_track = g.bx * g.by;
     const int track = blockIdx.x / per_track, b = blockIdx.x - track * per_track;
     const int byi = b / g.bx, bxi = b - byi * g.bx;
@@ -1346,6 +1347,10 @@ __global__ void __launch_bounds__(256, 1) k_ncc_local(Ctx c, LocalCfg g)
         }
     }
     if (trc && tid == 0) trc[TR_FRINGE * 2 + 1] = gtime();
+    // k_update is launched behind this kernel with a programmatic dependency: released HERE (when every CTA is past its loop), its CTA
+    // becomes resident during the reduction -- not during the loop, where an early CTA was measured to slow the search -- reads the
+    // step, the track and the old template, and blocks in griddepcontrol.wait until this grid has completed
+    if (g.late_trigger) pdl_trigger();
     __syncthreads();                                               // (A) statistics done: the scratch becomes the reduction buffer
     if (tid < g.nfma) {
         float4* po = reinterpret_cast<float4*>(s_red + (size_t)tid * kLocalRed);

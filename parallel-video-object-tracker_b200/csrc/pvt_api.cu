@@ -479,6 +479,8 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
                 // update inside the kernel (last CTA of the track): measured 22.2 us per C2 step against 21.6 us with k_update as
                 // its own launch (one-shot code behind a ticket runs slower than the boundary it saves): opt-in, PVT_LOCAL_UPDATE=1
                 { const char* lu = getenv("PVT_LOCAL_UPDATE"); g.update = (lu && *lu == '1') ? 1 : 0; }
+                // k_update behind the search with a programmatic dependency released late (behind the FMA loop): 21.9 -> 20.2 us per C2 step
+                { const char* lt = getenv("PVT_LATE_TRIGGER"); g.late_trigger = (lt && *lt == '0') ? 0 : 1; }
                 g.P = 8 + d.mtp;
                 while (g.P % 8 != 4) ++g.P;
                 g.tileH = kCY * TR + d.mth - 1;
@@ -700,6 +702,8 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
     if (p.roi_ingest) {
         const int roi_groups = ((d.VW + 4 + 3) / 4 + 1) * (d.Hmax + d.mth);
+        // (a programmatic edge update(k) ~> ingest(k+1) was measured again in round 2, with the trigger late in the update: the gap
+        //  stays 1.8 us -- it is the update grid's completion + flush, not the ingest's launch)
         k_ingest_roi<<<dim3((roi_groups + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
     } else {
         k_ingest<<<ingest_grid(d), kIngestThreads, 0, c->compute>>>(d);
@@ -754,9 +758,11 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
             return PVT_OK;
         }
         if (profile) { int r = pnode(c, CLS_UPDATE, 0, c->compute); if (r) return r; }
-        // (a programmatic edge search ~> update -- the update's CTA starts early, prefetches the old template and blocks in
-        //  griddepcontrol.wait -- was measured: the step went 21.6 -> 23.4 us, the early CTA slows the search it shares the GPU with)
-        k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
+        // Programmatic edge search ~> update: the update's CTA becomes resident when every search CTA is past its FMA loop
+        // (LocalCfg.late_trigger), reads the step, the track and the old template, and blocks in griddepcontrol.wait until the peak
+        // exists: 21.9 -> 20.2 us per step.  (Released at the START of the search the early CTA slowed the search: 23.4 us.)
+        if (p.local.late_trigger) { int r = launch_pdl(k_update, dim3((unsigned)d.max_tracks), dim3(256), c->templ_smem, c->compute, pdl_l, d); if (r) return r; }
+        else k_update<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_UPDATE, 1, c->compute); if (r) return r; }
         { int r = dbg(c, "k_update"); if (r) return r; }
         if (forkl) CK(cudaStreamWaitEvent(c->compute, c->ev_join, 0));   // the statistics branch ends inside this step
