@@ -12,7 +12,8 @@ namespace pvt {
 
 // defined in section (5), used earlier
 __device__ void write_digits(const Ctx& c, int track, TrackState& t, const float* s_t, double mean, int tw, int th);
-__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th);
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th, bool have_sums = false,
+                                double ps = 0.0, double pq = 0.0);
 __device__ void track_update(const Ctx& c, int track, unsigned long long step, bool stepped, float* s_t, double* red);
 
 // =============================================================================================
@@ -1887,14 +1888,19 @@ __device__ void write_digits(const Ctx& c, int track, TrackState& t, const float
 
 // statistics + centred chunk-major template from the template held in shared memory (s_t, th*tw floats)
 // (tw, th) = (t.w, t.h), passed in registers: callers sit behind a barrier, where re-reading them costs an L2 round trip
-__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th)
+// have_sums: the caller accumulated this thread's partial sums (ps, pq) over its elements i = tid, tid + blockDim, ... in that order
+// while it produced them (the EMA loop): the same numbers as the loop below, without the pass over shared memory
+__device__ void finish_template(const Ctx& c, int track, TrackState& t, const float* s_t, double* red, int tw, int th, bool have_sums, double ps, double pq)
 {
     const int n = tw * th, tid = threadIdx.x;
-    double s = 0.0, q = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
-        const double v = (double)s_t[i];
-        s += v;
-        q += v * v;
+    double s = ps, q = pq;
+    if (!have_sums) {
+        s = 0.0; q = 0.0;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const double v = (double)s_t[i];
+            s += v;
+            q += v * v;
+        }
     }
     block_sum2(s, q, red);
     const double scale = 1.0 / (double)n;
@@ -1975,6 +1981,7 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
             // (row, column) of pixel i advance incrementally: no division per element
             const int stride = blockDim.x, dq = stride / tw, dr = stride - dq * tw;
             int r = threadIdx.x / tw, col = threadIdx.x - r * tw;
+            double es = 0.0, eq = 0.0;
             for (int i0 = threadIdx.x; i0 < n; i0 += 16 * stride) {
                 float pv[16], tv[16];
 #pragma unroll
@@ -1993,11 +2000,13 @@ __device__ void track_update(const Ctx& c, int track, unsigned long long step, b
                         const float v = (float)fma((double)tv[k], alpha, pb);
                         tp_[i] = v;
                         s_t[i] = v;
+                        es += (double)v;                         // the new template's sums, in finish_template's own order
+                        eq += (double)v * (double)v;
                     }
                 }
             }
-            __syncthreads();
-            finish_template(c, track, t, s_t, red, tw, th);
+            // (no barrier here: finish_template's block reduction has two before anybody reads another thread's s_t)
+            finish_template(c, track, t, s_t, red, tw, th, true, es, eq);
         }
         if (threadIdx.x == 0) {
             t.x = nx; t.y = ny; t.peak = 0ull;
