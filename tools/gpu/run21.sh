@@ -1,4 +1,5 @@
 set -x; mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/gputest21.log 2>&1; tail -4 gpurun_out/gputest21.log
 timeout 900 python bench.py > gpurun_out/bench21.json 2> gpurun_out/bench21.err; tail -c 300 gpurun_out/bench21.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench21_ref.json 2> gpurun_out/bench21_ref.err
