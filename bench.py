@@ -528,6 +528,17 @@ def run_ours(args):
             "tracks_total": TOTAL, "tracks_rank0": len(ids), "frames_per_s": e["value"], "ms_per_step": e["ms_per_step"],
             "regions_ms": e["regions_ms"], "e2e": e.get("e2e"), "ncc_gmacs_per_s": world * e["macs_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9,
             "roofline": e["roofline"], "kernel_ms_per_step": e["kernel_ms_per_step"], "ingest": e["ingest_mode"], "gathered": e["gathered"]}
+    if args.extra:
+        # the same 512-track job on the tensor-core search (PVT_KERNEL_TC, opt-in: csrc/ncc_tc.cuh), resident leg only
+        try:
+            e = measure(pvt, torch, "C5_sharded_tc", rank, world, 20, 4, barrier, maxr, full=False, wl=wl5, stream_ids=ids, total_streams=TOTAL,
+                        gather=gather, e2e_leg=False, tracker_kw={"kernel": pvt.KERNEL_TC})
+            out["extra"]["C5_sharded_tc"] = {
+                "workload": out["extra"]["C5_sharded"]["workload"] + " -- PVT_KERNEL_TC", "tracks_total": TOTAL, "frames_per_s": e["value"],
+                "ms_per_step": e["ms_per_step"], "regions_ms": e["regions_ms"], "speedup_vs_fp32": e["value"] / out["extra"]["C5_sharded"]["frames_per_s"],
+                "kernel_ms_per_step": e["kernel_ms_per_step"], "gathered": e["gathered"]}
+        except Exception as ex:   # an optional variant never takes the bench down (all ranks fail alike: geometry / device limits)
+            out["extra"]["C5_sharded_tc"] = {"unavailable": repr(ex)}
     if rank == 0 and world == 1 and args.extra:
         # the search kernel with the GPU filled: SURVEY.md 8(d) configs C3 (one 4K stream), C4 (256 ROIs) and C5's per-GPU share (64 streams)
         for w2 in ("C3", "C4", "C5"):
