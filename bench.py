@@ -439,11 +439,21 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
     tri.submit_sequence(20, ring_i[5 % L:] + ring_i[:5 % L])
     pf = tri.profile_get(reset=True)
     tri.profile_enable(False)
+    # the same kernel inside the production multi-step graphs, warm: device globaltimer, first CTA start .. last CTA end
+    # (the event-record nodes of the profiling pass add ~5 us per bracket: 12 % of a 40 us launch)
+    tri.trace_enable(True)
+    tri.submit_sequence(24, ring_i[25 % L:] + ring_i[:25 % L])
+    Ti = tri.trace_get(16).astype(np.int64)
+    tri.trace_enable(False)
     tri.close()
-    ing_s = pf["ingest_ms"] * 1e-3 / max(pf["ingest_launches"], 1)
+    ing_s_nodes = pf["ingest_ms"] * 1e-3 / max(pf["ingest_launches"], 1)
+    ing_s = float(np.median(Ti[:, 0, 1] - Ti[:, 0, 0])) * 1e-9
     ing_bytes = pf["ingest_bytes"] / max(pf["ingest_launches"], 1)
     out["ingest"] = {"kernel": "k_ingest (full frames)", "bound": "hbm", "achieved": ing_bytes / ing_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ing_bytes / ing_s / 1e9 / hbm_peak, "peak_source": hbm_src, "us_per_launch": ing_s * 1e6,
+                     "us_per_launch_event_nodes": ing_s_nodes * 1e6, "frac_event_nodes": ing_bytes / ing_s_nodes / 1e9 / hbm_peak,
+                     "how": "device globaltimer stamps of the kernel (first CTA start .. last CTA end) inside the production multi-step graphs; "
+                            "*_event_nodes: CUDA event-record nodes around the kernel, steps launched one by one (round 1's figure)",
                      "bytes_per_launch": ing_bytes, "frames_per_launch": NS,
                      "note": "BGR8 -> f32: 3 B read + 4 B written per pixel; the timed legs use ingest mode '%s'" % ingest_mode}
 

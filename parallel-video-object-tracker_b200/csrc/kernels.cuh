@@ -70,6 +70,7 @@ __device__ __forceinline__ float4 ingest_group(const FrameDesc& d, const unsigne
 // (3735 B + 19235 G + 16384, then + 9798 R: the 15-bit fixed point of cv::cvtColor, weights fit 16 bits) + shift + I2F +
 // FMUL, and two 32-byte stores (st.global.v8.f32: one full sector each).  Anything else takes the 4-pixel generic path.
 constexpr int kIngestThreads = 128;
+constexpr int kIngestRows = 4;       // rows per CTA of k_ingest
 // the gray level behind a toGrayF32 value of a u8-sourced frame: f = fl32(g * fl32(1/255)) -> rint(f * 255) == g for g = 0..255
 __device__ __forceinline__ unsigned int gray8_of(float f) { return (unsigned int)__float2int_rn(f * 255.0f) & 255u; }
 __device__ __forceinline__ void store_gray8(const Ctx& c, int stream, int x, int y, const float4& o)
@@ -93,55 +94,72 @@ __global__ void __launch_bounds__(kIngestThreads) k_ingest(Ctx c)
 {
     pdl_trigger();
     const unsigned long long step = *c.step;
-    const int stream = blockIdx.z, y = blockIdx.y;
+    const int stream = blockIdx.z, y0 = blockIdx.y * kIngestRows;
     if (c.global_pass && !c.stream_need[stream]) return;   // whole-frame pass: only streams with a lost track
     const FrameDesc d = c.table[table_row(c, step) + stream];
     if (!d.valid) return;
     trace_begin(c, step, TR_INGEST);
-    float* orow = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch;
-    const unsigned char* irow = (const unsigned char*)d.data + (size_t)y * d.step;
     const bool fast = d.format == PVT_FMT_BGR8 && (c.W & 15) == 0 && ((((size_t)d.data) | d.step) & 15) == 0;
     if (fast) {
+        // a CTA converts kIngestRows consecutive rows: the preamble above (three dependent loads) is paid once per 4 x 2048 pixels,
+        // and a thread has its 12 loads (192 bytes) in flight before the first conversion
         const int x = (blockIdx.x * kIngestThreads + threadIdx.x) * 16;
         if (x < c.W) {
-            const uint4* p = reinterpret_cast<const uint4*>(irow + 3 * x);
-            const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-            const unsigned int w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-            float o[16];
+            uint4 q[kIngestRows][3];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {   // 4 pixels = 3 words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
-                const unsigned int a = w[3 * g], b = w[3 * g + 1], e = w[3 * g + 2];
-                o[4 * g] = gray_px(a);                                   // bytes 0 1 2 of a
-                o[4 * g + 1] = gray_px(__byte_perm(a, b, 0x0543));       // a3 b0 b1
-                o[4 * g + 2] = gray_px(__byte_perm(b, e, 0x0432));       // b2 b3 e0
-                o[4 * g + 3] = gray_px(e >> 8);                          // e1 e2 e3
+            for (int r = 0; r < kIngestRows; ++r) {
+                const int y = min(y0 + r, c.H - 1);              // (clamped duplicates are not stored)
+                const uint4* p = reinterpret_cast<const uint4*>((const unsigned char*)d.data + (size_t)y * d.step + 3 * x);
+                q[r][0] = __ldg(p); q[r][1] = __ldg(p + 1); q[r][2] = __ldg(p + 2);
             }
-            if (c.gray8) {   // tensor-core search: keep the gray levels themselves (exactly rint(f * 255))
-                unsigned int b[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    b[g] = gray8_of(o[4 * g]) | (gray8_of(o[4 * g + 1]) << 8) | (gray8_of(o[4 * g + 2]) << 16) | (gray8_of(o[4 * g + 3]) << 24);
-                *reinterpret_cast<uint4*>(c.gray8 + (size_t)stream * c.plane8 + (size_t)y * c.pitch8 + x) = make_uint4(b[0], b[1], b[2], b[3]);
-            }
-            if ((c.pitch & 7) == 0) {
-                st_v8(orow + x, *reinterpret_cast<const float(*)[8]>(o));
-                st_v8(orow + x + 8, *reinterpret_cast<const float(*)[8]>(o + 8));
-            } else {
+            for (int r = 0; r < kIngestRows; ++r) {
+                const int y = y0 + r;
+                if (y < c.H) {
+                    float* orow = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch;
+                    const unsigned int w[12] = {q[r][0].x, q[r][0].y, q[r][0].z, q[r][0].w, q[r][1].x, q[r][1].y, q[r][1].z, q[r][1].w,
+                                                q[r][2].x, q[r][2].y, q[r][2].z, q[r][2].w};
+                    float o[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(orow + x + 4 * g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                    for (int g = 0; g < 4; ++g) {   // 4 pixels = 3 words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                        const unsigned int a = w[3 * g], b = w[3 * g + 1], e = w[3 * g + 2];
+                        o[4 * g] = gray_px(a);                                   // bytes 0 1 2 of a
+                        o[4 * g + 1] = gray_px(__byte_perm(a, b, 0x0543));       // a3 b0 b1
+                        o[4 * g + 2] = gray_px(__byte_perm(b, e, 0x0432));       // b2 b3 e0
+                        o[4 * g + 3] = gray_px(e >> 8);                          // e1 e2 e3
+                    }
+                    if (c.gray8) {   // tensor-core search: keep the gray levels themselves (exactly rint(f * 255))
+                        unsigned int b[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            b[g] = gray8_of(o[4 * g]) | (gray8_of(o[4 * g + 1]) << 8) | (gray8_of(o[4 * g + 2]) << 16) | (gray8_of(o[4 * g + 3]) << 24);
+                        *reinterpret_cast<uint4*>(c.gray8 + (size_t)stream * c.plane8 + (size_t)y * c.pitch8 + x) = make_uint4(b[0], b[1], b[2], b[3]);
+                    }
+                    if ((c.pitch & 7) == 0) {
+                        st_v8(orow + x, *reinterpret_cast<const float(*)[8]>(o));
+                        st_v8(orow + x + 8, *reinterpret_cast<const float(*)[8]>(o + 8));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(orow + x + 4 * g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                    }
+                }
             }
         }
     } else {
         // generic: 4-pixel groups, 4 per thread (strided by the block so that a warp's accesses stay contiguous)
         const int gpr = (c.W + 3) >> 2;
+        for (int y = y0; y < min(y0 + kIngestRows, c.H); ++y) {
+            float* orow = c.gray + (size_t)stream * c.plane + (size_t)y * c.pitch;
+            const unsigned char* irow = (const unsigned char*)d.data + (size_t)y * d.step;
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const int g = (blockIdx.x * 4 + k) * kIngestThreads + threadIdx.x;
-            if (g >= gpr) break;
-            const int x = g << 2;
-            const float4 o4 = ingest_group(d, irow, x, min(4, c.W - x));
-            *reinterpret_cast<float4*>(orow + x) = o4;  // pitch % 4 == 0
-            if (c.gray8) store_gray8(c, stream, x, y, o4);
+            for (int k = 0; k < 4; ++k) {
+                const int g = (blockIdx.x * 4 + k) * kIngestThreads + threadIdx.x;
+                if (g >= gpr) break;
+                const int x = g << 2;
+                const float4 o4 = ingest_group(d, irow, x, min(4, c.W - x));
+                *reinterpret_cast<float4*>(orow + x) = o4;  // pitch % 4 == 0
+                if (c.gray8) store_gray8(c, stream, x, y, o4);
+            }
         }
     }
     trace_end(c, step, TR_INGEST);

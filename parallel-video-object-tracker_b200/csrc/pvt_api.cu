@@ -688,7 +688,7 @@ int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaS
 // k_ingest: (column blocks, rows, streams); a block covers 16 * 128 = 2048 pixels of a row on either path
 dim3 ingest_grid(const Ctx& d)
 {
-    return dim3((unsigned)((d.W + 16 * kIngestThreads - 1) / (16 * kIngestThreads)), (unsigned)d.H, (unsigned)d.max_streams);
+    return dim3((unsigned)((d.W + 16 * kIngestThreads - 1) / (16 * kIngestThreads)), (unsigned)((d.H + kIngestRows - 1) / kIngestRows), (unsigned)d.max_streams);
 }
 
 // The kernels of one searched time step.  capturing: being recorded into a CUDA graph on c->compute (fork/join allowed).
