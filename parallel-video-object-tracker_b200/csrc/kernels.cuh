@@ -220,6 +220,11 @@ __global__ void __launch_bounds__(256) k_ingest_roi(Ctx c)
 // it works from the window k_ingest_roi recorded, not from the box, which the step's update moves.
 __global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c, int debug_delay_ns)
 {
+    // k_ncc_local shape: launched behind k_winstats with a programmatic dependency and NO griddepcontrol.wait: it only has to start
+    // after the search CTAs have their SMs (k_winstats' CTAs start with them), not after the statistics (behind their end it
+    // finished after the update and held up the next step's ingest: 21.7 instead of 19.9 us per step on pinned host rings).
+    // Starting before the ingest has stored this step's header is harmless: the tile is then staged under the previous step's
+    // tag, which no ingest accepts (the staging is an accelerator, never a correctness dependency).
     const SeqDesc q = *c.seq;
     if (!q.prefetch) return;
     if (debug_delay_ns > 0) {   // test hook (PVT_DEBUG_PREFETCH_DELAY_US): start late, as if the SMs had been busy
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c, int debug_delay_ns)
     // frame step+2 under the tag of step+1.
     const unsigned long long step = hdr->cur_step;
     if (step == ~0ull) return;                           // no ingest has run for this track in this sequence yet
+    if (c.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2] = gtime();   // (spare slot)
     const size_t nrow = (size_t)(q.row0 + (int)((step + 1ull - q.step0 + (unsigned long long)q.phase) % (unsigned long long)q.ring_len)) * c.max_streams;
     const FrameDesc d = c.table[nrow + t.stream];
     if (!d.valid) {
@@ -295,6 +301,7 @@ __global__ void __launch_bounds__(256) k_prefetch_roi(Ctx c, int debug_delay_ns)
             }
         }
     }
+    if (c.trace && threadIdx.x == 0) atomicMax(&c.trace[((step % kRing) * 8 + TR_ROWSUM) * 2 + 1], gtime());
 }
 
 // =============================================================================================

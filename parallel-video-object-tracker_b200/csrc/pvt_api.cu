@@ -744,7 +744,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         // (profiling graph: no event nodes on the statistics branch -- they delay k_winstats, and the search would be timed waiting for it)
         if (profile) { int r = pnode(c, CLS_STATS, 0, c->compute); if (r) return r; r = pnode(c, CLS_STATS, 1, c->compute); if (r) return r; }
         if (p.local.gstats) { int r = launch_pdl(k_winstats, dim3((unsigned)(p.stat.xtiles * p.stat.ybands), d.max_tracks), dim3(kStatThreads), 0, sst, pdl_l, d, p.stat); if (r) return r; }
-        if (pf_on_stats_branch) k_prefetch_roi<<<dim3(24, (unsigned)d.max_tracks), 256, 0, c->aux>>>(d, c->prefetch_delay_ns);
+        if (pf_on_stats_branch) { int r = launch_pdl(k_prefetch_roi, dim3(24, (unsigned)d.max_tracks), dim3(256), 0, c->aux, pdl_l, d, c->prefetch_delay_ns); if (r) return r; }
         if (forkl) CK(cudaEventRecord(c->ev_join, c->aux));
         if (profile) { int r = pnode(c, CLS_NCC, 0, c->compute); if (r) return r; r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
         { int r = launch_pdl(k_ncc_local<kCY>, dim3((unsigned)(d.max_tracks * p.local.bx * p.local.by)), dim3(threads), p.local_smem, c->compute, pdl_l, d, p.local); if (r) return r; }

@@ -27,7 +27,7 @@ print("%s: %.2f us/step (events); step-to-step %.2f us (trace)" % (wname, 1e3 * 
 prev_end = None
 local = T[:, 7, 0].any() and T[:, 6, 0].any() and not T[:, 4, 0].any()
 for k, nm in enumerate(names):
-    if not T[:, k, 0].any() or (local and k in (1, 6, 7)): continue
+    if not T[:, k, 0].any() or (local and k in (1, 2, 6, 7)): continue
     st = np.median(T[:, k, 0] - T[:, 0, 0]) / 1e3; en = np.median(T[:, k, 1] - T[:, 0, 0]) / 1e3
     print("  %-13s start %7.2f  end %7.2f  dur %6.2f us  gap-before %6.2f" % (nm, st, en, en - st, st - prev_end if prev_end is not None else 0.0))
     prev_end = en
@@ -39,5 +39,7 @@ elif T[:, 7, 0].any() and T[:, 6, 0].any():
     b = T[:, 3, 0]
     print("  K-split search, CTA 0 (from the kernel's first CTA start): tile requested +%.2f | landed +%.2f | loop done +%.2f | partial sums stored +%.2f us" %
           tuple(np.median(x - b) / 1e3 for x in (T[:, 6, 0], T[:, 6, 1], T[:, 7, 0], T[:, 7, 1])))
+if T[:, 2, 0].any() and local:
+    print("  k_prefetch_roi (statistics branch): start +%.2f  end +%.2f us from the step's start" % (np.median(T[:, 2, 0] - T[:, 0, 0]) / 1e3, np.median(T[:, 2, 1] - T[:, 0, 0]) / 1e3))
 nxt = np.median(T[1:, 0, 0] - T[:-1, 5, 1]) / 1e3
 print("  gap to next step's ingest: %.2f us" % nxt)
