@@ -255,7 +255,11 @@ PVT_API int pvt_profile_enable(pvt_ctx* ctx, int on); /* on: per-kernel CUDA eve
 PVT_API int pvt_profile_get(pvt_ctx* ctx, pvt_profile* out, int reset);
 /* device-side timeline: with tracing on, every kernel stamps %globaltimer (ns) at its first CTA's start and last
  * CTA's end; pvt_trace_get copies the stamps of the last <= 64 steps: out[step][8 kernel slots][2], slots =
- * ingest, colprefix, rowsum, ncc_search, ncc_finalize, update, ncc_fringe, ncc_tail_finalize.  Returns the number of steps written. */
+ * ingest, statistics (k_winstats; k_colprefix of the two-kernel statistics), rowsum, search (k_ncc_search / k_ncc_local / k_ncc_tc),
+ * ncc_finalize, update, ncc_fringe, ncc_tail_finalize.  Slots a plan does not launch carry phase stamps of CTA 0 instead:
+ * k_ncc_local and the K-split k_ncc_search use the last two (staged | loop done, statistics / loop done | reduced), k_ncc_tc
+ * slots 4, 6, 7, k_prefetch_roi slot 2 in the k_ncc_local shape (tools/timeline.py, tools/tc_timeline.py decode them).
+ * Returns the number of steps written. */
 PVT_API int pvt_trace_enable(pvt_ctx* ctx, int on);
 PVT_API int pvt_trace_get(pvt_ctx* ctx, uint64_t* out, int max_steps);
 PVT_API int64_t pvt_launch_count(pvt_ctx* ctx); /* kernels launched by this context so far (graph nodes counted per launch) */

@@ -1,6 +1,8 @@
 // Hand-written sm_100a kernels of the NCC tracking hot path.  One time step = the launch sequence
-//   k_ingest -> k_colprefix -> k_rowsum -> k_ncc_search [-> k_ncc_finalize] (or k_ncc_direct) -> k_update
-// captured once as a CUDA graph; every kernel finds "which frame / which step" through the
+//   many tracks:   k_ingest[_roi] -> k_winstats -> k_ncc_search ~> k_ncc_fringe [-> k_ncc_tail_finalize] -> k_update      (or k_ncc_tc: ncc_tc.cuh)
+//   one stream:    k_ingest_roi ~> { k_ncc_local || k_winstats } ~> k_update
+//   in between:    k_ingest_roi ~> k_ncc_search (K-split) || k_winstats -> k_ncc_finalize (its last CTA runs the update)
+// (~> = programmatic dependent launch) captured once as a CUDA graph; every kernel finds "which frame / which step" through the
 // device-side step counter and frame table, so the graph is launched unchanged for every frame and
 // nothing returns to the host between frames.
 #pragma once
