@@ -578,6 +578,12 @@ def run_ours(args):
             except Exception as ex:   # an optional variant never takes the bench down
                 out["extra"][w2 + "_tc"] = {"unavailable": repr(ex)}
         out["extra"]["whole_frame_search"] = whole_frame_leg(pvt, torch, m)
+        try:
+            wtc = whole_frame_leg(pvt, torch, m, tc=True)
+            wtc["speedup_step_vs_fp32"] = out["extra"]["whole_frame_search"]["ms_per_step"] / wtc["ms_per_step"]
+            out["extra"]["whole_frame_search_tc"] = wtc
+        except Exception as ex:   # an optional variant never takes the bench down
+            out["extra"]["whole_frame_search_tc"] = {"unavailable": repr(ex)}
         out["extra"]["map_operator"] = map_operator_leg(pvt, m)
         out["ref_gpu_baseline"] = ref_gpu_leg(m, out["extra"]["map_operator"])
         # the search kernel's roofline fraction where the GPU is full (the headline workload is a single latency-bound stream)
@@ -664,7 +670,7 @@ def map_operator_leg(pvt, m, n=6):
             "reference_cpu_ms": None}
 
 
-def whole_frame_leg(pvt, torch, m, steps=40):
+def whole_frame_leg(pvt, torch, m, steps=40, tc=False):
     """the lost-object mode's whole-frame search (tracker_ghc/src/main.cpp:186-193), one 1080p stream,
     64x64 template, the track held in the lost state (acceptance threshold 2.0 is never met), so every step computes the
     full 1857 x 1017 NCC map's arg-max: 7.74 GMAC per frame.  Step time by CUDA events; TFLOP/s from the step time (a lower
@@ -676,7 +682,8 @@ def whole_frame_leg(pvt, torch, m, steps=40):
     ring = ring_descs(pvt, wl, dev, True)
     res = {}
     for lost in (False, True):
-        tr = pvt.Tracker(W, H, tw, th, search_radius_x=wl["R"], search_radius_y=wl["R"], lost_frame_threshold=50, ncc_global_confidence=2.0)
+        tr = pvt.Tracker(W, H, tw, th, search_radius_x=wl["R"], search_radius_y=wl["R"], lost_frame_threshold=50, ncc_global_confidence=2.0,
+                         **({"kernel": pvt.KERNEL_TC} if tc else {}))
         tr.init_track(0, pvt.device_frame(dev[0, 0].data_ptr(), W * 3, stream=0), rois_for(wl, scenes[0])[0], stream=0)
         if lost:
             tr.set_lost_state(0, 1000, 1)
@@ -691,7 +698,8 @@ def whole_frame_leg(pvt, torch, m, steps=40):
         tr.close()
     macs = float((W - tw + 1) * (H - th + 1) * tw * th)
     peak = info["sm_count"] * 128 * 2 * info["sm_clock_khz"] * 1e-6 * 1e-3
-    return {"workload": "one 1920x1080 stream, 64x64 template, track lost: arg-max of the full 1857x1017 NCC map every frame",
+    return {"workload": "one 1920x1080 stream, 64x64 template, track lost: arg-max of the full 1857x1017 NCC map every frame"
+                        + (" -- PVT_KERNEL_TC (k_ncc_tc over column tiles of the map; TFLOP/s = useful MACs only)" if tc else ""),
             "frames_per_s": 1e3 / res[True], "ms_per_step": res[True], "macs_per_step": macs,
             "tflops_from_step_time": 2 * macs / (res[True] * 1e-3) / 1e12, "frac_of_fp32_peak_from_step_time": 2 * macs / (res[True] * 1e-3) / 1e12 / peak,
             "local_step_ms_with_lost_mode_on": res[False], "local_step_ms_headline": m["ms_per_step"],

@@ -43,8 +43,8 @@ constexpr int kTcEpiBytes = 8 * 2 * 32 * 17 * 8;   // epilogue staging: per warp
 constexpr int kTcPadL = 16, kTcPadR = 48;   // zero bytes left / right of a digit row in shared memory
 
 struct TcCfg {
-    int AG;          // candidate groups of 8 in an accumulator: NWpad / 8, NWpad = Wmax rounded up to 16
-    int KS;          // K-steps: ceil((Wmax + mtw - 1 + 15) / 32)
+    int AG;          // candidate groups of 8 in an accumulator: XW / 8
+    int KS;          // K-steps: ceil((XW + mtw - 1 + 15) / 32)
     int rows;        // image-tile rows = 128 + mth - 1 (TMA box)
     int nblk;        // Toeplitz blocks per (stage, digit): 4 KS + AG (band blocks inside a run of zero blocks)
     int stages;      // depth of the block ring
@@ -52,6 +52,9 @@ struct TcCfg {
     int mtiles;      // ceil(Hmax / 128)
     int tmem_cols;   // power of two >= 2 * 8 * AG
     int spin;        // 1: the ring's waits poll (mbarrier.test_wait) instead of suspending in try_wait
+    int XW;          // candidate columns per accumulator (multiple of 16, <= 256): Wmax rounded up to 16 when one accumulator covers the
+                     // window, else the window is cut into xtiles column tiles of XW candidates (4K windows, the whole-frame pass)
+    int xtiles;      // ceil(Wmax / XW); a CTA = (track, 128-row tile, column tile)
 };
 
 // ring waits: polling variant (the suspending try_wait of pvt_device.cuh wakes late when the producer / consumer chain is short)
@@ -162,15 +165,21 @@ __device__ __forceinline__ void tc_band(int kc, int o, int tw, int ww, int AG, i
 __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const __grid_constant__ CUtensorMap tmap8)
 {
     extern __shared__ __align__(1024) unsigned char sm_tc[];
-    const int track = blockIdx.x / g.mtiles, mt = blockIdx.x - track * g.mtiles;
+    const int per_track = g.mtiles * g.xtiles;
+    const int track = blockIdx.x / per_track, bt = blockIdx.x - track * per_track;
+    const int mt = bt / g.xtiles, xt = bt - mt * g.xtiles;
     TrackState& t = c.tracks[track];
     const unsigned long long step = *c.step;
     if (!track_stepped(c, t, step)) return;
-    const int ww = t.win[2], wh = t.win[3], row0 = mt * 128;
-    if (row0 >= wh) return;                                   // clamped window: no second row tile (CTA-uniform)
+    const int wfull = t.win[2], wh = t.win[3], row0 = mt * 128;
+    const int jx0 = xt * g.XW;                                // first candidate column of this column tile
+    if (row0 >= wh || jx0 >= wfull) return;                   // clamped window: no such row / column tile (CTA-uniform)
+    // from here on the CTA sees its column tile as a window of its own: origin win[0] + jx0, ww candidates wide; only the
+    // epilogue's indices into the window's maps (statistics, scores, peak key) use the full row length wfull
+    const int ww = min(g.XW, wfull - jx0);
     trace_begin(c, step, TR_NCC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int th = t.h, tw = t.w, o = t.win[0] & 15;
+    const int th = t.h, tw = t.w, ox = t.win[0] + jx0, o = ox & 15;
     const int CH = g.rows * 16;                               // bytes per 16-pixel chunk of the image tile
     const int blk_bytes = g.nblk * 128;                       // one (stage, digit) run of Toeplitz blocks
     const int drow = kTcPadL + g.tpp + kTcPadR;               // digit row pitch in shared memory
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
             for (int s = 0; s < g.stages; ++s) { mbar_init(&full[s], (kTcThreads - 32) / 32); mbar_init(&empty[s], 1); }
             fence_mbar_init();
             mbar_arrive_expect_tx(bar_tile, (uint32_t)(CH * 2 * g.KS));
-            tma_load_4d(sA, &tmap8, bar_tile, 0, t.win[1] + row0, t.win[0] >> 4, t.stream);
+            tma_load_4d(sA, &tmap8, bar_tile, 0, t.win[1] + row0, ox >> 4, t.stream);
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
@@ -331,10 +340,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
         const int y = row0 + q4 * 32 + lane;
         const bool rowok = y < wh;
         double* stg = reinterpret_cast<double*>(sm_tc) + (size_t)e * (2 * 32 * 17);   // [denom | wsum][row of the warp][17]
-        const size_t woff = (size_t)track * c.Hmax * c.Wmax;
+        const size_t woff = (size_t)track * c.Hmax * c.Wmax + (size_t)jx0;
         const double* dnb = c.denom + woff;
         const double* wsb = c.wsum + woff;
-        float* mp = (c.params->keep_maps && rowok) ? c.maps + woff + (size_t)y * ww : nullptr;
+        float* mp = (c.params->keep_maps && rowok) ? c.maps + woff + (size_t)y * wfull : nullptr;
         const int flat = t.flat;
         const double sc = (double)(1.0f / 255.0f) * t.tc_inv, dc = t.tc_dc;     // fl32(1/255): the ingest's own constant (utils.hpp:12)
         const int NW = g.AG * 8;
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {                      // a warp instruction covers two rows x 16 candidates (128 B each)
                     const int r = 2 * i + (lane >> 4);
-                    const size_t o = (size_t)min(row0 + q4 * 32 + r, wh - 1) * ww + jc;
+                    const size_t o = (size_t)min(row0 + q4 * 32 + r, wh - 1) * wfull + jc;
                     cp_async8(stg + r * 17 + (lane & 15), dnb + o);
                     cp_async8(stg + (32 + r) * 17 + (lane & 15), wsb + o);
                 }
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_ncc_tc(Ctx c, TcCfg g, const 
                     const int j = jb + (i < 8 ? 8 + i : i - 8);
                     if (j < ww) {
                         if (mp) mp[j] = v[i];
-                        const unsigned long long k2 = peak_key(v[i], (unsigned int)(y * ww + j));
+                        const unsigned long long k2 = peak_key(v[i], (unsigned int)(y * wfull + jx0 + j));
                         key = k2 > key ? k2 : key;
                     }
                 }

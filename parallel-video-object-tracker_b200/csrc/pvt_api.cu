@@ -71,6 +71,9 @@ struct Pass {
     bool roi_ingest = false;   // k_ingest_roi instead of k_ingest
     bool pdl = true;           // k_ncc_fringe behind the search with a programmatic dependency (plain stream order otherwise)
     bool prefetch = false;     // k_prefetch_roi beside the step (graphs for pinned host rings)
+    TcCfg tc{};                // PVT_KERNEL_TC: geometry of k_ncc_tc for this pass's windows (XW == 0: the pass keeps the FP32 search)
+    size_t tc_smem = 0;
+    CUtensorMap tmap8{};
 };
 
 }  // namespace
@@ -308,6 +311,7 @@ int raise_smem(const void* fn, size_t bytes)
 }
 
 int encode_tmap(const Ctx& d, const TileCfg& tile, CUtensorMap* out);
+int tc_geometry(pvt_ctx* c, const Ctx& d, int sm_count, TcCfg& g, size_t* smem, CUtensorMap* tmap8);
 
 // kernels one pass launches per searched step: ingest, 2 statistics, search, [fringe], [tail reduction] + update | finalize
 int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool fused = false, bool local = false, int extra_local = 0)
@@ -517,7 +521,7 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     d.Wmax = d.W; d.Hmax = d.H;                         // upper bounds of the map (W - tw + 1) x (H - th + 1)
     d.VW = (d.Wmax + d.mtw - 1 + 7) & ~7;
     d.maps = nullptr; d.partial = nullptr; d.fringe_acc = nullptr; d.trace = nullptr;
-    d.wsum = nullptr;                                   // the whole-frame pass keeps the FP32 search (its window sums would not fit the local buffer)
+    d.wsum = nullptr;                                   // (its window sums do not fit the local buffer: own array below)
     const size_t win = (size_t)d.Wmax * d.Hmax;
     d.vsum = nullptr; d.vsq = nullptr;
     if (stats_legacy(d.mtw)) {
@@ -529,27 +533,65 @@ int build_global_pass(pvt_ctx* c, int sm_count)
     { int r = dev_alloc(c, &d.stream_need, (size_t)d.max_streams); if (r) return r; }
     int r = build_plan(c, g, sm_count, PVT_INGEST_FULL, false);
     if (r) return r;
+    if (c->tc_ready) {
+        // PVT_KERNEL_TC: the whole-frame search on the tensor cores too, the map cut into column tiles (TcCfg.xtiles).
+        // PVT_TC_GLOBAL=0 keeps the FP32 K-split search for this pass (the round-2 state; A/B measurements)
+        const char* e = getenv("PVT_TC_GLOBAL");
+        if (!(e && *e == '0')) {
+            { int r2 = dev_alloc(c, &d.wsum, (size_t)d.max_tracks * win, false); if (r2) return r2; }
+            { int r2 = tc_geometry(c, d, sm_count, g.tc, &g.tc_smem, &g.tmap8); if (r2) return r2; }
+        }
+    }
     c->kps_global = 2;   // k_global_mark + k_step_advance; the conditional body's kernels (they only run while a track is lost) are not counted
     return PVT_OK;
 }
 
-// PVT_KERNEL_TC: geometry of k_ncc_tc, its buffers (u8 gray plane, template digits, window sums) and the 4-D tensor map
-// (16 B, row, 16-pixel chunk, stream) whose box lands in shared memory chunk-major (ncc_tc.cuh)
-int setup_tc(pvt_ctx* c)
+// PVT_KERNEL_TC: candidate columns per accumulator.  One accumulator of Wmax columns where that fits (<= 256 columns, <= kTcKMax
+// K-steps: the 161-wide windows of C2/C4/C5); else the window is cut into column tiles: a CTA = (track, 128 rows, XW columns).
+// The width is chosen on a small cost model of one CTA (tools/tc_timeline.py: ~130 clk per MMA = per (template row, K-step),
+// ~900 clk of epilogue per 16 columns, ~6k clk of prologue) times the number of waves the pass's CTAs need on the GPU.
+int tc_pick_xw(const Ctx& d, int sm_count)
 {
-    Ctx& d = c->d;
-    TcCfg& g = c->tc;
+    auto ks_of = [&](int xw) { return (xw + d.mtw - 1 + 15 + 31) / 32; };
     const int NW = (d.Wmax + 15) & ~15;
-    g.AG = NW / 8;
-    g.KS = (d.Wmax + d.mtw - 1 + 15 + 31) / 32;
+    if (const char* e = getenv(d.global_pass ? "PVT_TC_XW_GLOBAL" : "PVT_TC_XW")) {   // experiments
+        const int xw = (atoi(e) + 15) & ~15;
+        if (xw >= 16 && xw <= 256 && ks_of(xw) <= kTcKMax) return std::min(xw, NW);
+    }
+    if (!d.global_pass && NW <= 256 && ks_of(NW) <= kTcKMax) return NW;
+    // the whole-frame pass is sized for ONE lost track and the map it really has, (W - tw + 1) x (H - th + 1)
+    const int wt = d.global_pass ? std::max(1, d.Wmax - d.mtw + 1) : d.Wmax, ht = d.global_pass ? std::max(1, d.Hmax - d.mth + 1) : d.Hmax;
+    const long long tracks = d.global_pass ? 1 : d.max_tracks;
+    int best_xw = 0;
+    double best = 1e300;
+    for (int xw = 16; xw <= 256 && xw <= NW; xw += 16) {
+        const int ks = ks_of(xw);
+        if (ks > kTcKMax) break;
+        const long long ctas = tracks * ((ht + 127) / 128) * ((wt + xw - 1) / xw);
+        const long long waves = (ctas + sm_count - 1) / sm_count;
+        const double cost = (double)waves * ((double)d.mth * ks * 130.0 + (xw / 16) * 900.0 + 6000.0);
+        if (cost < best) { best = cost; best_xw = xw; }
+    }
+    return best_xw;
+}
+
+// PVT_KERNEL_TC: geometry of k_ncc_tc for one pass (window bounds d.Wmax x d.Hmax), its shared memory and the 4-D tensor map
+// (16 B, row, 16-pixel chunk, stream) of the u8 gray plane whose box lands in shared memory chunk-major (ncc_tc.cuh)
+int tc_geometry(pvt_ctx* c, const Ctx& d, int sm_count, TcCfg& g, size_t* smem, CUtensorMap* tmap8)
+{
+    g = TcCfg{};
+    g.XW = tc_pick_xw(d, sm_count);
     g.rows = 128 + d.mth - 1;
+    if (g.XW <= 0 || g.rows > 256)
+        return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: template height <= 129 and template width <= 260 required");
+    g.xtiles = (d.Wmax + g.XW - 1) / g.XW;
+    g.AG = g.XW / 8;
+    g.KS = (g.XW + d.mtw - 1 + 15 + 31) / 32;
     g.nblk = 4 * g.KS + g.AG;
     g.tpp = (d.mtw + 15) & ~15;
     g.mtiles = (d.Hmax + 127) / 128;
     g.tmem_cols = 32;
-    while (g.tmem_cols < 2 * NW) g.tmem_cols <<= 1;
-    if (NW > 256 || g.KS > kTcKMax || g.rows > 256)
-        return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: window width <= 256, template height <= 129 and window + template width <= 306 required");
+    while (g.tmem_cols < 2 * g.XW) g.tmem_cols <<= 1;
     auto smem_of = [&](int stages) {
         const size_t main_bytes = (size_t)16 * g.rows * 2 * g.KS + (size_t)stages * 2 * g.nblk * 128 + ((((size_t)2 * d.mth * (kTcPadL + g.tpp + kTcPadR)) + 15) & ~(size_t)15);
         return std::max(main_bytes, (size_t)kTcEpiBytes) + sizeof(uint64_t) * (2 + 2 * stages) + 64;
@@ -558,15 +600,12 @@ int setup_tc(pvt_ctx* c)
     if (const char* e = getenv("PVT_TC_STAGES")) g.stages = std::max(2, std::min(16, atoi(e)));   // experiments
     if (const char* e = getenv("PVT_TC_SPIN")) g.spin = atoi(e);
     while (g.stages > 2 && smem_of(g.stages) > kSmemBudget - 1024) --g.stages;
-    c->tc_smem = smem_of(g.stages);
-    if (c->tc_smem > kSmemBudget - 1024) return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: tile does not fit shared memory");
-    { int r = raise_smem((const void*)k_ncc_tc, c->tc_smem); if (r) return r; }
-    d.pitch8 = (d.W + 15) & ~15;
-    d.plane8 = ((size_t)d.pitch8 * d.H + 255) & ~(size_t)255;
-    d.tpp = g.tpp;
-    { int r = dev_alloc(c, &d.gray8, d.plane8 * d.max_streams); if (r) return r; }
-    { int r = dev_alloc(c, &d.tdig, (size_t)d.max_tracks * 2 * d.mth * g.tpp); if (r) return r; }
-    { int r = dev_alloc(c, &d.wsum, (size_t)d.max_tracks * d.Wmax * d.Hmax, false); if (r) return r; }
+    *smem = smem_of(g.stages);
+    if (*smem > kSmemBudget - 1024) return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: tile does not fit shared memory");
+    { int r = raise_smem((const void*)k_ncc_tc, *smem); if (r) return r; }
+    if (getenv("PVT_DEBUG_PLAN"))
+        fprintf(stderr, "[pvt] tc plan (%s pass): XW=%d xtiles=%d mtiles=%d KS=%d stages=%d tmem=%d smem=%zu\n", d.global_pass ? "whole-frame" : "local", g.XW, g.xtiles,
+                g.mtiles, g.KS, g.stages, g.tmem_cols, *smem);
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -575,9 +614,23 @@ int setup_tc(pvt_ctx* c)
     cuuint64_t strides[3] = {(cuuint64_t)d.pitch8, 16, (cuuint64_t)d.plane8};
     cuuint32_t box[4] = {16, (cuuint32_t)g.rows, (cuuint32_t)(2 * g.KS), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = ((EncodeTiledFn)fn)(&c->tmap8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d.gray8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = ((EncodeTiledFn)fn)(tmap8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d.gray8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PVT_ERR_CUDA, "cuTensorMapEncodeTiled (u8 gray plane, 4-D) failed, CUresult " + std::to_string((int)r));
+    return PVT_OK;
+}
+
+// PVT_KERNEL_TC: the context's buffers (u8 gray plane, template digits, window sums) and the local pass's geometry
+int setup_tc(pvt_ctx* c, int sm_count)
+{
+    Ctx& d = c->d;
+    d.pitch8 = (d.W + 15) & ~15;
+    d.plane8 = ((size_t)d.pitch8 * d.H + 255) & ~(size_t)255;
+    d.tpp = (d.mtw + 15) & ~15;
+    { int r = dev_alloc(c, &d.gray8, d.plane8 * d.max_streams); if (r) return r; }
+    { int r = dev_alloc(c, &d.tdig, (size_t)d.max_tracks * 2 * d.mth * d.tpp); if (r) return r; }
+    { int r = dev_alloc(c, &d.wsum, (size_t)d.max_tracks * d.Wmax * d.Hmax, false); if (r) return r; }
+    { int r = tc_geometry(c, d, sm_count, c->tc, &c->tc_smem, &c->tmap8); if (r) return r; }
     c->tc_ready = true;
     return PVT_OK;
 }
@@ -657,6 +710,7 @@ Pass local_pass(const pvt_ctx* c)
 {
     Pass p;
     p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
+    p.tc = c->tc; p.tc_smem = c->tc_smem; p.tmap8 = c->tmap8;
     p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fused = c->fused; p.fused_smem = c->fused_smem; p.local = c->local; p.local_smem = c->local_smem; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
     return p;
 }
@@ -772,9 +826,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
-    const bool tc = c->params.kernel == PVT_KERNEL_TC && !d.global_pass;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
+    const bool tc = c->params.kernel == PVT_KERNEL_TC && p.tc.XW > 0;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
     const bool ksplit = c->params.kernel == PVT_KERNEL_AUTO ? p.tile.pj * p.tile.pd > 1
-                                                             : (c->params.kernel == PVT_KERNEL_TC && d.global_pass && p.tile.pj * p.tile.pd > 1);
+                                                             : (c->params.kernel == PVT_KERNEL_TC && !tc && p.tile.pj * p.tile.pd > 1);
     const bool fork = capturing && ksplit;
     cudaStream_t sstats = c->compute;
     if (fork) {
@@ -818,7 +872,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     if (tc) {
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
-        k_ncc_tc<<<(unsigned)(d.max_tracks * c->tc.mtiles), kTcThreads, c->tc_smem, c->compute>>>(d, c->tc, c->tmap8);
+        k_ncc_tc<<<(unsigned)(d.max_tracks * p.tc.mtiles * p.tc.xtiles), kTcThreads, p.tc_smem, c->compute>>>(d, p.tc, p.tmap8);
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else if (c->params.kernel == PVT_KERNEL_DIRECT) {
@@ -1117,7 +1171,8 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             if (r) return r;
             k_step_advance<<<1, 32, 0, c->compute>>>(gp.d);
             { int r2 = dbg(c, "k_step_advance"); if (r2) return r2; }
-            c->launches += c->kps_global + pass_kernels(gp.tile, gp.fringe, gp.stat);
+            const bool gtc = c->params.kernel == PVT_KERNEL_TC && gp.tc.XW > 0;   // ingest, statistics (1 or 2 kernels), k_ncc_tc, update
+            c->launches += c->kps_global + (gtc ? (gp.stat.NX > 0 ? 4 : 5) : pass_kernels(gp.tile, gp.fringe, gp.stat));
         }
     } else if (c->profiling) {
         // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
@@ -1464,7 +1519,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CR(dev_alloc(c, &d.stage, (size_t)d.max_tracks * d.stage_w * d.stage_h));
         CR(dev_alloc(c, &d.stage_hdr, (size_t)d.max_tracks));
     }
-    if (params->kernel == PVT_KERNEL_TC) CR(setup_tc(c));
+    if (params->kernel == PVT_KERNEL_TC) CR(setup_tc(c, prop.multiProcessorCount));
     c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
     if (c->templ_smem > 48u * 1024u) {
         CR(raise_smem((const void*)k_update, c->templ_smem));

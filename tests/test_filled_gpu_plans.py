@@ -174,9 +174,12 @@ def test_c4_256_rois_one_stream_tail_split_and_fringe(kernel):
 
 
 @pytest.mark.gpu
-def test_whole_frame_1080p_six_band_tail_split_plan():
+@pytest.mark.parametrize("kernel", ["auto", "tc"])
+def test_whole_frame_1080p_six_band_tail_split_plan(kernel):
     """(1) map operator on a 1080p frame: the 1857 x 1017 map under the 6-band tail-split plan against the oracle's;
-    (2) lost-object mode with the track forced lost: the same plan inside the conditional graph node, then back to local."""
+    (2) lost-object mode with the track forced lost: the same plan inside the conditional graph node, then back to local.
+    kernel "tc": (2) with the whole-frame pass on the tensor cores (k_ncc_tc over column tiles of the 1857-wide map; the whole
+    map of that shape is compared score by score in tests/test_tc_kernel.py::test_tc_whole_map_in_column_tiles_vs_oracle)."""
     sm = pvt.device_info(0)["sm_count"]
     plan = pvt.plan_query(1, FC.TW, FC.TH, FC.W, FC.H, FC.W, FC.H, sm_count=sm)
     assert plan["pj"] * plan["pd"] == 1 and plan["bands"] == 6 and plan["n_tail"] > 0 and plan["tail_parts"] >= 2, plan
@@ -196,7 +199,7 @@ def test_whole_frame_1080p_six_band_tail_split_plan():
     best, bx, by = O.max_loc(want)
 
     with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, search_radius_x=FC.R, search_radius_y=FC.R, lost_frame_threshold=50,
-                     ncc_global_confidence=0.60) as tr:
+                     ncc_global_confidence=0.60, kernel=pvt.KERNEL_TC if kernel == "tc" else pvt.KERNEL_AUTO) as tr:
         tr.init_track(0, wf.frames[0], roi)
         tr.set_state(0, wf.stale_box, None)
         tr.set_lost_state(0, 1000, 1)

@@ -138,13 +138,13 @@ def test_tc_contract_errors_and_gray_sources():
         with pytest.raises(pvt.PvtError) as e:
             tr.set_params(kernel=pvt.KERNEL_TC)
         assert e.value.code == pvt.ERR_INVALID
-    with pytest.raises(pvt.PvtError) as e:                        # 4K / 128x128 / R160: window wider than the two accumulators
-        pvt.Tracker(3840, 2160, 128, 128, search_radius_x=160, search_radius_y=160, kernel=pvt.KERNEL_TC)
+    with pytest.raises(pvt.PvtError) as e:                        # templates higher than 129 rows: 128 candidate rows + th - 1 exceed the 256-row TMA box
+        pvt.Tracker(3840, 2160, 160, 160, search_radius_x=160, search_radius_y=160, kernel=pvt.KERNEL_TC)
     assert e.value.code == pvt.ERR_UNSUPPORTED
 
 
 def test_tc_lost_object_mode_and_batch_hold():
-    """kernel TC + lost-object mode: local windows on the tensor cores, the whole-frame pass on the FP32 kernel; + batch hold."""
+    """kernel TC + lost-object mode: local windows AND the whole-frame pass (column tiles) on the tensor cores; + batch hold."""
     from tools import synth
     with open(os.path.join(Hp.GOLD, "meta_ghc.json")) as fh:
         m = json.load(fh)["clips"]["reacquire"]
@@ -163,3 +163,82 @@ def test_tc_lost_object_mode_and_batch_hold():
     rb, tb = pvt.track_clip(cb["frames"], cb["roi"], mode=pvt.MODE_BATCH, batch_size=4, kernel=pvt.KERNEL_TC)
     Hp.check_records(records_of(rb), g["records"], "batch4 (tc)")
     assert np.array_equal(tb, g["templ"])
+
+
+# ---- column tiles: windows wider than one accumulator (4K windows, whole-frame maps) are cut into tiles of TcCfg.XW candidate
+# ---- columns; a CTA = (track, 128 rows, XW columns) with its own origin alignment, partial last tile and band
+def _whole_map_case(W, H, tw, th, seed):
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(seed)
+    base = gaussian_filter(rng.random((H, W, 3)), (1.5, 1.5, 0))
+    f0 = np.clip((base - base.min()) / (base.max() - base.min()) * 255, 0, 255).astype(np.uint8)
+    f1 = np.clip(np.roll(f0, (2, -3), (0, 1)).astype(np.int16) + rng.integers(-3, 4, f0.shape), 0, 255).astype(np.uint8)
+    f1[: H // 5, : W // 4] = 77                                  # a flat corner: degenerate windows (G4) in the first tiles
+    return f0, f1
+
+
+@pytest.mark.parametrize("W,H,tw,th,xw", [(700, 300, 40, 36, None), (700, 300, 40, 36, 64), (700, 300, 40, 36, 240), (523, 417, 64, 64, 112),
+                                          (333, 130, 17, 129, None), (1920, 1080, 64, 64, None)])
+def test_tc_whole_map_in_column_tiles_vs_oracle(W, H, tw, th, xw, monkeypatch):
+    """Search radius = the frame: the local window is the whole (W - tw + 1) x (H - th + 1) map, wider than one accumulator.
+    Every score against the oracle's map (G3/G4), the arg-max and the record (G1/G2/G5); PVT_TC_XW forces tile widths."""
+    if xw is not None:
+        monkeypatch.setenv("PVT_TC_XW", str(xw))
+    else:
+        monkeypatch.delenv("PVT_TC_XW", raising=False)
+    f0, f1 = _whole_map_case(W, H, tw, th, 1000 + W + tw)
+    x, y = (W - tw) // 3, (H - th) // 2
+    g0, g1 = O.to_gray_f32(f0), O.to_gray_f32(f1)
+    templ = g0[y:y + th, x:x + tw].copy()
+    with pvt.Tracker(W, H, tw, th, keep_maps=1, search_radius_x=W, search_radius_y=H, kernel=pvt.KERNEL_TC) as tr:
+        tr.init_track(0, f0, (x, y, tw, th))
+        r = tr.step([f1])[0]
+        m, win = tr.window_map(0)
+        _, t_end = tr.get_state(0)
+    assert win == (0, 0, W - tw + 1, H - th + 1)
+    want = O.ncc_match_cpu(g1, templ)
+    assert m.shape == want.shape
+    sig = Hp.window_sigma(g1, tw, th, win)
+    d = np.abs(m - want)
+    assert d[sig >= 0.002].max(initial=0) <= Hp.TOL_SCORE and d.max() <= Hp.TOL_LOWVAR, float(d.max())
+    deg = (want == 0) | (np.abs(want) == 1)
+    assert np.array_equal(m[deg], want[deg])
+    assert np.argmax(m) == np.argmax(want)
+    rec, _, _ = O.track_step(g1, templ, x, y, rx=W, ry=H)       # templ updated in place
+    assert (r["x"], r["y"], r["moved"], r["updated"]) == (rec.x, rec.y, rec.moved, rec.updated)
+    assert abs(float(r["conf"]) - rec.conf) <= Hp.TOL_SCORE
+    assert np.array_equal(t_end, templ)
+
+
+def test_tc_c3_4k_windows_in_column_tiles_vs_cv2_golden():
+    """BASELINE.json configs[2] (4K, 128 x 128, R 160): the 321-wide window is cut into column tiles."""
+    (c, tk) = Hp.clip("c3_4k")
+    g = Hp.golden("clip_c3_4k.npz")
+    recs, templ = pvt.track_clip(c["frames"], c["roi"], search_radius_x=tk.get("rx", 160), search_radius_y=tk.get("ry", 160), kernel=pvt.KERNEL_TC)
+    Hp.check_records(records_of(recs), g["records"], "c3_4k (tc)")
+    assert np.array_equal(templ, g["templ"])
+
+
+@pytest.mark.parametrize("name", ["ghc_defaults", "reacquire", "reacquire_odd"])
+def test_tc_lost_object_clips_whole_frame_pass_on_tensor_cores(name):
+    """tracker_ghc/src/main.cpp:183-239 with kernel TC: the local windows and the whole-frame pass (column tiles) on the
+    tensor cores, against the cv2 4.13.0 goldens of the lost-object clips."""
+    from tools import synth
+    with open(os.path.join(Hp.GOLD, "meta_ghc.json")) as fh:
+        clips = json.load(fh)["clips"]
+    if name not in clips:
+        pytest.skip(f"no lost-object golden named {name}")
+    m = clips[name]
+    c = synth.make_clip(synth.ClipSpec(**m["spec"]))
+    assert zlib.crc32(np.ascontiguousarray(c["frames"]).tobytes()) & 0xFFFFFFFF == m["frames_crc"]
+    z = np.load(os.path.join(Hp.GOLD, f"ghc_{name}.npz"))
+    want = z["records"]
+    tk = m["track"]
+    recs, templ = pvt.track_clip(c["frames"], c["roi"], search_radius_x=tk["rx"], search_radius_y=tk["ry"], lost_frame_threshold=tk["lost_threshold"],
+                                 ncc_global_confidence=tk.get("global_conf", 0.60), kernel=pvt.KERNEL_TC)
+    got = records_of(recs)
+    assert np.array_equal(got[:, :4], want[:, :4]) and np.array_equal(got[:, 5:7], want[:, 5:7])
+    assert np.array_equal(recs["searched"], want[:, 7].astype(np.uint8))
+    assert np.abs(got[:, 4] - want[:, 4]).max() <= Hp.TOL_SCORE
+    if "templ" in z.files:
+        assert np.array_equal(templ, z["templ"])
