@@ -67,12 +67,15 @@ typedef enum pvt_mode {
 typedef enum pvt_kernel {
     PVT_KERNEL_AUTO = 0,   /* production kernel (TMA-staged tile, register-blocked FP32) */
     PVT_KERNEL_DIRECT = 1, /* one thread per candidate, global loads: verification twin of the reference's naive kernel */
-    PVT_KERNEL_TC = 2      /* tensor-core search (tcgen05.mma kind::i8, exact integer cross term of the 16-bit fixed-point centred
+    PVT_KERNEL_TC = 2,     /* tensor-core search (tcgen05.mma kind::i8, exact integer cross term of the 16-bit fixed-point centred
                             * template; scores within 1e-4 of the CPU path like the others, peaks identical).  For the throughput
-                            * shapes (many tracks / ROIs per GPU).  Must be chosen at pvt_create (it allocates an 8-bit gray plane);
-                            * needs 8-bit frames (BGR8 / GRAY8 -- a GRAYF32 frame is rejected), window width <= 256, template
-                            * height <= 129, window width + template width <= 306; the whole-frame pass of the lost-object mode
-                            * keeps the FP32 kernel. */
+                            * shapes (many tracks / ROIs per GPU) and for wide maps: windows wider than one accumulator (256
+                            * candidate columns: 4K windows, the whole-frame pass of the lost-object mode) are cut into column
+                            * tiles.  Must be chosen at pvt_create (it allocates an 8-bit gray plane); needs 8-bit frames (BGR8 /
+                            * GRAY8 -- a GRAYF32 frame is rejected), template height <= 129, template width <= 260. */
+    PVT_KERNEL_TC_GLOBAL = 3 /* lost-object mode: the planner's FP32 kernels for the local windows (the single-stream latency
+                            * shape is faster there), the tensor-core search for the whole-frame pass only
+                            * (tracker_ghc/src/main.cpp:186-193).  Same creation-time and frame-format rules as PVT_KERNEL_TC. */
 } pvt_kernel;
 
 /* frame ingest (utils.hpp:5-14 toGrayF32).  FULL converts whole frames, as the reference does.  ROI converts only each

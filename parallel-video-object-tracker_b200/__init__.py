@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libpvt.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MODE_NAIVE, MODE_CPU, MODE_SHARED, MODE_CONST, MODE_CONST_TILED, MODE_BATCH = range(6)
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TC = range(3)
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TC, KERNEL_TC_GLOBAL = range(4)
 FMT_BGR8, FMT_GRAY8, FMT_GRAYF32 = range(3)
 MEM_HOST, MEM_DEVICE, MEM_HOST_PINNED = range(3)
 INGEST_AUTO, INGEST_FULL, INGEST_ROI = range(3)

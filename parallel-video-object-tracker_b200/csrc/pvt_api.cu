@@ -153,6 +153,15 @@ struct pvt_ctx {
 
 namespace {
 
+// PVT_KERNEL_TC_GLOBAL: the planner's FP32 kernels for the local windows, the tensor cores for the whole-frame pass only
+inline int local_kernel(const pvt_ctx* c) { return c->params.kernel == PVT_KERNEL_TC_GLOBAL ? (int)PVT_KERNEL_AUTO : (int)c->params.kernel; }
+inline int pass_kernel(const pvt_ctx* c, const Ctx& d)
+{
+    if (c->params.kernel != PVT_KERNEL_TC_GLOBAL) return (int)c->params.kernel;
+    return d.global_pass ? (int)PVT_KERNEL_TC : (int)PVT_KERNEL_AUTO;
+}
+inline bool wants_tc(int kernel) { return kernel == PVT_KERNEL_TC || kernel == PVT_KERNEL_TC_GLOBAL; }
+
 template <typename T>
 int dev_alloc(pvt_ctx* c, T** p, size_t n, bool zero = true)
 {
@@ -325,7 +334,7 @@ int pass_kernels(const TileCfg& t, const FringeCfg& f, const StatCfg& st, bool f
 int kernels_per_step(const pvt_ctx* c)
 {
     // k_ncc_direct / k_ncc_tc: ingest, statistics (1 or 2 kernels), search, update
-    return c->params.kernel != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0, c->local.gstats + (c->local.update ? 0 : 1));
+    return local_kernel(c) != PVT_KERNEL_AUTO ? (c->stat.NX > 0 ? 4 : 5) : pass_kernels(c->tile, c->fringe, c->stat, c->fused, c->local.TR > 0, c->local.gstats + (c->local.update ? 0 : 1));
 }
 
 // item grid + tail splitting (see TileCfg)
@@ -446,7 +455,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
         // in which only ~54 threads per CTA have work (5.4 us instead of 3.1).  Kept behind PVT_FUSED=1, with its parity tests.
         const char* nf = getenv("PVT_FUSED");
         const long long search_ctas = (long long)d.max_tracks * p.tile.cpt * p.tile.pj * p.tile.pd;
-        if (allow_env && (nf && *nf == '1') && c->params.kernel == PVT_KERNEL_AUTO && !c->lost_mode && p.tile.pj * p.tile.pd > 1 &&
+        if (allow_env && (nf && *nf == '1') && local_kernel(c) == PVT_KERNEL_AUTO && !c->lost_mode && p.tile.pj * p.tile.pd > 1 &&
             p.fringe.colg + p.fringe.rowg == 0 && p.stat.NX > 0 && search_ctas <= sm_count && p.fused_smem + 1024 <= kSmemBudget) {
             p.fused = true;
             p.stat.signal = 1;
@@ -458,7 +467,7 @@ int build_plan(pvt_ctx* c, Pass& p, int sm_count, int ingest, bool allow_env)
     p.local = LocalCfg{};
     {
         const char* nl = getenv("PVT_NO_LOCAL");
-        const bool want = allow_env && !(nl && *nl == '1') && c->params.kernel == PVT_KERNEL_AUTO && !c->lost_mode && !d.global_pass &&
+        const bool want = allow_env && !(nl && *nl == '1') && local_kernel(c) == PVT_KERNEL_AUTO && !c->lost_mode && !d.global_pass &&
                           p.tile.pj * p.tile.pd > 1 && !getenv("PVT_PLAN");
         const int nch = d.mtp / 8, Gall = (d.Hmax + kCY - 1) / kCY, bx = (d.Wmax + 7) / 8;
         // statistics: from k_winstats running beside the search on SMs the plan leaves free (one per statistics CTA in the worst
@@ -671,7 +680,7 @@ int validate_params(const pvt_params* p)
     if (p->mode == PVT_MODE_CPU)
         return fail(PVT_ERR_UNSUPPORTED, "PVT_MODE_CPU: libpvt has no CPU path (the CPU oracle lives in oracle/, test-only)");
     if (p->mode < PVT_MODE_NAIVE || p->mode > PVT_MODE_BATCH) return fail(PVT_ERR_INVALID, "unknown mode");
-    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TC) return fail(PVT_ERR_INVALID, "unknown kernel variant");
+    if (p->kernel < PVT_KERNEL_AUTO || p->kernel > PVT_KERNEL_TC_GLOBAL) return fail(PVT_ERR_INVALID, "unknown kernel variant");
     if (p->ingest < PVT_INGEST_AUTO || p->ingest > PVT_INGEST_ROI) return fail(PVT_ERR_INVALID, "unknown ingest mode");
     if (p->search_radius_x < 0 || p->search_radius_y < 0) return fail(PVT_ERR_INVALID, "negative search radius");
     if (p->mode == PVT_MODE_BATCH && p->batch_size < 1) return fail(PVT_ERR_INVALID, "batch_size < 1");
@@ -752,6 +761,7 @@ dim3 ingest_grid(const Ctx& d)
 int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing = false)
 {
     const Ctx& d = p.d;
+    const int kern = pass_kernel(c, d);
     profile = profile && capturing;
     if (profile) { int r = pnode(c, CLS_INGEST, 0, c->compute); if (r) return r; }
     if (p.roi_ingest) {
@@ -769,7 +779,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     // (k_ncc_local with its statistics on a parallel branch fills all but a few SMs with one CTA each: a prefetch CTA that lands on
     //  an SM first keeps a search CTA out until it has finished its PCIe reads -- measured: e2e 37.3k -> 31.3k frames/s.  There the
     //  prefetch is launched BEHIND k_winstats on the statistics branch instead: by then every search CTA has its SM.)
-    const bool local_gs = p.local.TR > 0 && p.local.gstats && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass;
+    const bool local_gs = p.local.TR > 0 && p.local.gstats && kern == PVT_KERNEL_AUTO && !d.global_pass;
     const bool pf_on_stats_branch = local_gs && capturing && d.stage && p.roi_ingest && p.prefetch;
     if (d.stage && p.roi_ingest && !d.global_pass && p.prefetch && !pf_on_stats_branch) {
         const dim3 pgrid(24, (unsigned)d.max_tracks);   // small on purpose: see k_prefetch_roi
@@ -785,7 +795,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         }
     }
 
-    if (p.local.TR > 0 && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass) {
+    if (p.local.TR > 0 && kern == PVT_KERNEL_AUTO && !d.global_pass) {
         // latency shape, K-split and statistics inside the CTA: ingest ~> k_ncc_local -> k_update
         const bool pdl_l = capturing && !profile && p.pdl;
         const unsigned threads = 32u * (unsigned)((p.local.nfma + 31) / 32);
@@ -826,9 +836,9 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     // K-split mode inside a captured graph: the statistics kernels and the search only meet in k_ncc_finalize, so they
     // run as two concurrent branches (fork after ingest, join before finalize)
-    const bool tc = c->params.kernel == PVT_KERNEL_TC && p.tc.XW > 0;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
-    const bool ksplit = c->params.kernel == PVT_KERNEL_AUTO ? p.tile.pj * p.tile.pd > 1
-                                                             : (c->params.kernel == PVT_KERNEL_TC && !tc && p.tile.pj * p.tile.pd > 1);
+    const bool tc = kern == PVT_KERNEL_TC && p.tc.XW > 0;   // tensor-core search: ingest -> statistics -> k_ncc_tc -> update
+    const bool ksplit = kern == PVT_KERNEL_AUTO ? p.tile.pj * p.tile.pd > 1
+                                                             : (kern == PVT_KERNEL_TC && !tc && p.tile.pj * p.tile.pd > 1);
     const bool fork = capturing && ksplit;
     cudaStream_t sstats = c->compute;
     if (fork) {
@@ -849,7 +859,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     if (profile) { int r = pnode(c, CLS_STATS, 1, sstats); if (r) return r; }
     { int r = dbg(c, "k_rowsum"); if (r) return r; }
     // the candidates outside the thread-tile grid: after the statistics (they need the normaliser), beside the search
-    const bool fringe = !tc && c->params.kernel != PVT_KERNEL_DIRECT && p.fringe.colg + p.fringe.rowg > 0;
+    const bool fringe = !tc && kern != PVT_KERNEL_DIRECT && p.fringe.colg + p.fringe.rowg > 0;
     const dim3 fgrid((unsigned)(p.fringe.colg + p.fringe.rowg), (unsigned)d.max_tracks, (unsigned)(p.fringe.defer ? p.tile.pd : 1));
     if (fork) CK(cudaEventRecord(c->ev_join, c->aux));
 
@@ -875,7 +885,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         k_ncc_tc<<<(unsigned)(d.max_tracks * p.tc.mtiles * p.tc.xtiles), kTcThreads, p.tc_smem, c->compute>>>(d, p.tc, p.tmap8);
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
-    } else if (c->params.kernel == PVT_KERNEL_DIRECT) {
+    } else if (kern == PVT_KERNEL_DIRECT) {
         k_ncc_direct<<<dim3((d.Wmax * d.Hmax + 255) / 256, d.max_tracks), 256, 0, c->compute>>>(d);
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
     } else {
@@ -885,7 +895,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
         // (K-split shape: the search directly follows the ingest on this stream and waits for it before fetching its tile.
         //  Unsplit shape: a plain dependency on k_rowsum -- starting the search during the statistics' tail was measured and
         //  lost 4 % on C4: k_ncc_fringe then has to wait for the whole search grid before it may read the normalisers)
-        const bool fused = p.fused && c->params.kernel == PVT_KERNEL_AUTO && !d.global_pass;
+        const bool fused = p.fused && kern == PVT_KERNEL_AUTO && !d.global_pass;
         if (fused) {
             // search + second stage + update in one launch; it waits for k_winstats (the other branch) through TrackState.stats_done
             { int r = launch_pdl(k_step_fused<kCY>, dim3(nbx * (unsigned)parts), dim3(kTilesPerCta), p.fused_smem, c->compute, pdl && fork, d, p.tile, p.tmap, p.stat); if (r) return r; }
@@ -1094,7 +1104,7 @@ int check_frame(const pvt_ctx* c, const pvt_frame* f)
     if (f->memory != PVT_MEM_HOST && f->memory != PVT_MEM_DEVICE && f->memory != PVT_MEM_HOST_PINNED) return fail(PVT_ERR_INVALID, "unknown frame memory kind");
     if (f->step < frame_row_bytes(c, f->format)) return fail(PVT_ERR_INVALID, "frame.step smaller than one row");
     if (f->format == PVT_FMT_GRAYF32 && (f->step % 4 || ((size_t)f->data) % 4)) return fail(PVT_ERR_INVALID, "f32 frame not 4-byte aligned");
-    if (f->format == PVT_FMT_GRAYF32 && c->params.kernel == PVT_KERNEL_TC)
+    if (f->format == PVT_FMT_GRAYF32 && wants_tc(c->params.kernel))
         return fail(PVT_ERR_INVALID, "PVT_KERNEL_TC searches the 8-bit gray levels: GRAYF32 frames are not accepted by this context");
     return PVT_OK;
 }
@@ -1171,7 +1181,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             if (r) return r;
             k_step_advance<<<1, 32, 0, c->compute>>>(gp.d);
             { int r2 = dbg(c, "k_step_advance"); if (r2) return r2; }
-            const bool gtc = c->params.kernel == PVT_KERNEL_TC && gp.tc.XW > 0;   // ingest, statistics (1 or 2 kernels), k_ncc_tc, update
+            const bool gtc = wants_tc(c->params.kernel) && gp.tc.XW > 0;   // ingest, statistics (1 or 2 kernels), k_ncc_tc, update
             c->launches += c->kps_global + (gtc ? (gp.stat.NX > 0 ? 4 : 5) : pass_kernels(gp.tile, gp.fringe, gp.stat));
         }
     } else if (c->profiling) {
@@ -1519,7 +1529,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CR(dev_alloc(c, &d.stage, (size_t)d.max_tracks * d.stage_w * d.stage_h));
         CR(dev_alloc(c, &d.stage_hdr, (size_t)d.max_tracks));
     }
-    if (params->kernel == PVT_KERNEL_TC) CR(setup_tc(c, prop.multiProcessorCount));
+    if (wants_tc(params->kernel)) CR(setup_tc(c, prop.multiProcessorCount));
     c->templ_smem = (size_t)d.mth * d.mtw * sizeof(float);
     if (c->templ_smem > 48u * 1024u) {
         CR(raise_smem((const void*)k_update, c->templ_smem));
@@ -1547,7 +1557,7 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
     if (p->keep_maps && !c->d.maps) return fail(PVT_ERR_INVALID, "keep_maps must be set at pvt_create");
     if ((p->lost_frame_threshold > 0) != c->lost_mode) return fail(PVT_ERR_INVALID, "lost-object mode (lost_frame_threshold > 0) must be chosen at pvt_create");
     if (p->formula != c->params.formula) return fail(PVT_ERR_INVALID, "the score formula must be chosen at pvt_create (templates carry its statistics)");
-    if (p->kernel == PVT_KERNEL_TC && !c->tc_ready) return fail(PVT_ERR_INVALID, "PVT_KERNEL_TC must be chosen at pvt_create (it allocates the 8-bit gray plane and the template digits)");
+    if (wants_tc(p->kernel) && !c->tc_ready) return fail(PVT_ERR_INVALID, "PVT_KERNEL_TC must be chosen at pvt_create (it allocates the 8-bit gray plane and the template digits)");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->compute));
     const bool regraph = p->kernel != c->params.kernel || p->ingest != c->params.ingest;
@@ -2189,7 +2199,7 @@ int pvt_search_kind(pvt_ctx* c, char* name, int name_bytes)
     const char* k = "k_ncc_search";
     if (c->params.kernel == PVT_KERNEL_TC) k = "k_ncc_tc";
     else if (c->params.kernel == PVT_KERNEL_DIRECT) k = "k_ncc_direct";
-    else if (c->local.TR > 0) k = "k_ncc_local";
+    else if (c->local.TR > 0 && local_kernel(c) == PVT_KERNEL_AUTO) k = "k_ncc_local";
     else if (c->fused) k = "k_step_fused";
     else if (c->tile.pj * c->tile.pd > 1) k = "k_ncc_search+k_ncc_finalize";
     if (name && name_bytes > 0) { std::strncpy(name, k, (size_t)name_bytes - 1); name[name_bytes - 1] = 0; }

@@ -174,7 +174,7 @@ def test_c4_256_rois_one_stream_tail_split_and_fringe(kernel):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", ["auto", "tc"])
+@pytest.mark.parametrize("kernel", ["auto", "tc", "tc_global"])
 def test_whole_frame_1080p_six_band_tail_split_plan(kernel):
     """(1) map operator on a 1080p frame: the 1857 x 1017 map under the 6-band tail-split plan against the oracle's;
     (2) lost-object mode with the track forced lost: the same plan inside the conditional graph node, then back to local.
@@ -199,7 +199,7 @@ def test_whole_frame_1080p_six_band_tail_split_plan(kernel):
     best, bx, by = O.max_loc(want)
 
     with pvt.Tracker(FC.W, FC.H, FC.TW, FC.TH, search_radius_x=FC.R, search_radius_y=FC.R, lost_frame_threshold=50,
-                     ncc_global_confidence=0.60, kernel=pvt.KERNEL_TC if kernel == "tc" else pvt.KERNEL_AUTO) as tr:
+                     ncc_global_confidence=0.60, kernel={"auto": pvt.KERNEL_AUTO, "tc": pvt.KERNEL_TC, "tc_global": pvt.KERNEL_TC_GLOBAL}[kernel]) as tr:
         tr.init_track(0, wf.frames[0], roi)
         tr.set_state(0, wf.stale_box, None)
         tr.set_lost_state(0, 1000, 1)

@@ -219,10 +219,12 @@ def test_tc_c3_4k_windows_in_column_tiles_vs_cv2_golden():
     assert np.array_equal(templ, g["templ"])
 
 
+@pytest.mark.parametrize("kernel", ["tc", "tc_global"])
 @pytest.mark.parametrize("name", ["ghc_defaults", "reacquire", "reacquire_odd"])
-def test_tc_lost_object_clips_whole_frame_pass_on_tensor_cores(name):
+def test_tc_lost_object_clips_whole_frame_pass_on_tensor_cores(name, kernel):
     """tracker_ghc/src/main.cpp:183-239 with kernel TC: the local windows and the whole-frame pass (column tiles) on the
-    tensor cores, against the cv2 4.13.0 goldens of the lost-object clips."""
+    tensor cores, against the cv2 4.13.0 goldens of the lost-object clips.  kernel "tc_global" (PVT_KERNEL_TC_GLOBAL): FP32
+    kernels for the local windows, k_ncc_tc for the whole-frame pass only."""
     from tools import synth
     with open(os.path.join(Hp.GOLD, "meta_ghc.json")) as fh:
         clips = json.load(fh)["clips"]
@@ -235,10 +237,28 @@ def test_tc_lost_object_clips_whole_frame_pass_on_tensor_cores(name):
     want = z["records"]
     tk = m["track"]
     recs, templ = pvt.track_clip(c["frames"], c["roi"], search_radius_x=tk["rx"], search_radius_y=tk["ry"], lost_frame_threshold=tk["lost_threshold"],
-                                 ncc_global_confidence=tk.get("global_conf", 0.60), kernel=pvt.KERNEL_TC)
+                                 ncc_global_confidence=tk.get("global_conf", 0.60), kernel=pvt.KERNEL_TC if kernel == "tc" else pvt.KERNEL_TC_GLOBAL)
     got = records_of(recs)
     assert np.array_equal(got[:, :4], want[:, :4]) and np.array_equal(got[:, 5:7], want[:, 5:7])
     assert np.array_equal(recs["searched"], want[:, 7].astype(np.uint8))
     assert np.abs(got[:, 4] - want[:, 4]).max() <= Hp.TOL_SCORE
     if "templ" in z.files:
         assert np.array_equal(templ, z["templ"])
+
+
+def test_tc_global_runs_the_fp32_plan_on_local_windows():
+    """PVT_KERNEL_TC_GLOBAL without a lost track is the planner's FP32 path bit for bit (records, final template), and reports
+    the FP32 search kernel; GRAYF32 frames are rejected like with PVT_KERNEL_TC (the whole-frame pass reads the gray levels)."""
+    (c, tk) = Hp.clip("small")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    ra, ta = pvt.track_clip(frames[:8], roi, lost_frame_threshold=50)
+    rg, tg = pvt.track_clip(frames[:8], roi, lost_frame_threshold=50, kernel=pvt.KERNEL_TC_GLOBAL)
+    assert np.array_equal(records_of(ra), records_of(rg)) and np.array_equal(ta, tg)
+    with pvt.Tracker(W, H, roi[2], roi[3], lost_frame_threshold=50, kernel=pvt.KERNEL_TC_GLOBAL) as tr, \
+         pvt.Tracker(W, H, roi[2], roi[3], lost_frame_threshold=50) as ta_:
+        assert tr.search_kind()[0] == ta_.search_kind()[0] != "k_ncc_tc"
+        tr.init_track(0, frames[0], roi)
+        with pytest.raises(pvt.PvtError) as e:
+            tr.step([O.to_gray_f32(frames[1])])
+        assert e.value.code == pvt.ERR_INVALID
