@@ -24,6 +24,10 @@
 //     blocks per (template row, digit) that alias each other, inside a zero-filled run of blocks.
 //   * band-aware issue: a 32-column K-step only meets the candidates whose taps it holds; the MMA is issued for that
 //     sub-range (N' = 16..96 of 176 columns) through a column offset into D and a block offset into B.
+//   * column tiles: a window wider than one accumulator (TcCfg.XW candidate columns, <= 256) -- 4K windows, the whole-frame pass of
+//     the lost-object mode (tracker_ghc/src/main.cpp:186-193) -- is cut into TcCfg.xtiles tiles; a CTA = (track, 128 rows, XW
+//     columns) treats its tile as a window of its own (origin win[0] + xt * XW: own alignment o, own band, partial last tile) and
+//     only the epilogue's indices into the window's maps use the full row length.
 // Roles in the CTA (9 warps): warp 0 = TMA + MMA issue (one elected lane; every operand warp-uniform, see tc_probe.cu for
 // what a divergent issue loop costs), warps 1-8 build the Toeplitz blocks of the coming template rows into a ring of stages
 // (full / empty mbarriers; empty is signalled by tcgen05.commit) and afterwards run the epilogue: TMEM -> registers (a warp
