@@ -62,12 +62,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(wname):
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_ncc_search per launch, from the committed `ncu --set full` capture of
-    this workload and the summary file it comes from (profiles/traffic_r1.json); (None, None) when there is no capture."""
-    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
+def ncu_traffic(wname, kernel=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel per launch, from the committed `ncu --set full` capture of
+    this workload and kernel, and the summary file it comes from (profiles/traffic_r2.json keyed "workload:kernel", else the round-1
+    k_ncc_search captures in profiles/traffic_r1.json); (None, None) when there is no capture."""
     try:
-        with open(p) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic_r2.json")) as fh:
+            e = json.load(fh).get("%s:%s" % (wname, kernel))
+        if e:
+            return float(e["dram_bytes"]), e["source"]
+        if kernel is not None and not str(kernel).startswith("k_ncc_search"):
+            return None, None
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
             e = json.load(fh).get(wname)
         return (float(e["dram_bytes"]), e["source"]) if e else (None, None)
     except Exception:
@@ -356,10 +362,10 @@ def measure(pvt, torch, wname, rank, world, K, Wm, barrier, maxr, full=True, wl=
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": 2.0 * kmacs_per_launch / (k_us * 1e-6) / 1e12 / fp32_peak,
                      "us_per_launch": k_us, "share_of_step": k_share,
                      "us_per_launch_event_nodes": ncc_s * 1e6, "frac_event_nodes": ncc_tf / fp32_peak,
-                     "traffic": ncu_traffic(wname)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
-                     "traffic_source": ncu_traffic(wname)[1],
+                     "traffic": ncu_traffic(wname, search_kernel)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
+                     "traffic_source": ncu_traffic(wname, search_kernel)[1],
                      "peak_source": "SMs*128*2*max SM clock (%d SMs, %.3f GHz); SURVEY.md 8(d)" % (info["sm_count"], fmax_ghz),
-                     "peak_measured": 0.985 * fp32_peak, "frac_of_measured": ncc_tf / (0.985 * fp32_peak),
+                     "peak_measured": 0.985 * fp32_peak, "frac_of_measured": 2.0 * kmacs_per_launch / (k_us * 1e-6) / 1e12 / (0.985 * fp32_peak),
                      "peak_measured_source": "tools/microbench.cu on B200: dependent-free FFMA stream sustains 98.5 % of nominal "
                                              "(profiles/microbench_r1.log); MEASURED_PEAKS.json has no FP32 entry",
                      "macs_per_launch": kmacs_per_launch,
@@ -690,9 +696,10 @@ def whole_frame_leg(pvt, torch, m, steps=40, tc=False, tc_kernel=None):
         if lost:
             tr.set_lost_state(0, 1000, 1)
         tr.submit_sequence(6, ring[1:] + ring[:1])
+        tr.submit_sequence(steps, ring[7 % L:] + ring[:7 % L])    # same length as the timed sequence: its step graphs are built here (first use)
         tr.sync()
         tr.timer_start()
-        tr.submit_sequence(steps, ring[7 % L:] + ring[:7 % L])
+        tr.submit_sequence(steps, ring[(7 + steps) % L:] + ring[:(7 + steps) % L])
         ms = tr.timer_stop() / steps
         last = tr.collect(1)[0][0]
         assert int(last["searched"]) == (2 if lost else 1)

@@ -953,7 +953,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
 
 // Lost-object mode: append  k_global_mark -> IF (any track lost) { the whole-frame pass } -> k_step_advance  to graph g behind
 // `deps`.  The condition is set on the device by k_global_mark, so nothing returns to the host between the passes.
-int add_global_tail(pvt_ctx* c, cudaGraph_t g, const cudaGraphNode_t* deps, size_t n_deps)
+int add_global_tail(pvt_ctx* c, cudaGraph_t g, const cudaGraphNode_t* deps, size_t n_deps, cudaGraphNode_t* last = nullptr)
 {
     const Pass gp = global_pass(c);
     Ctx gd = gp.d;
@@ -979,6 +979,41 @@ int add_global_tail(pvt_ctx* c, cudaGraph_t g, const cudaGraphNode_t* deps, size
     cudaKernelNodeParams ka{};
     ka.func = (void*)k_step_advance; ka.gridDim = dim3(1); ka.blockDim = dim3(32); ka.sharedMemBytes = 0; ka.kernelParams = aargs;
     CK(cudaGraphAddKernelNode(&n_adv, g, &n_if, 1, &ka));
+    if (last) *last = n_adv;
+    return PVT_OK;
+}
+
+// Lost-object mode: n consecutive time steps in one graph.  Per step: the local pass captured behind the previous step's
+// k_step_advance, then (behind the local pass's leaves) k_global_mark -> IF { whole-frame pass } -> k_step_advance with a
+// conditional handle of its own.
+int capture_lost_steps_graph(pvt_ctx* c, const Pass& lp, int n, cudaGraphExec_t* out)
+{
+    cudaGraph_t g = nullptr;
+    CK(cudaGraphCreate(&g, 0));
+    cudaGraphNode_t prev{};
+    for (int k = 0; k < n; ++k) {
+        CK(cudaStreamBeginCaptureToGraph(c->compute, g, k ? &prev : nullptr, nullptr, k ? 1 : 0, cudaStreamCaptureModeThreadLocal));
+        int r = launch_step_kernels(c, lp, false, true);
+        cudaError_t e = cudaStreamEndCapture(c->compute, nullptr);
+        if (r) { cudaGraphDestroy(g); return r; }
+        CK(e);
+        size_t nn = 0, ne = 0;
+        CK(cudaGraphGetNodes(g, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        CK(cudaGraphGetNodes(g, nodes.data(), &nn));
+        CK(cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &ne));   // _v2: the graph has programmatic edges
+        std::vector<cudaGraphNode_t> from(ne), to(ne);
+        std::vector<cudaGraphEdgeData> ed(ne);
+        if (ne) CK(cudaGraphGetEdges_v2(g, from.data(), to.data(), ed.data(), &ne));
+        std::vector<cudaGraphNode_t> leaves;   // earlier steps end in their k_step_advance, which this step's roots depend on
+        for (cudaGraphNode_t nd : nodes)
+            if (std::find(from.begin(), from.end(), nd) == from.end()) leaves.push_back(nd);
+        r = add_global_tail(c, g, leaves.data(), leaves.size(), &prev);
+        if (r) { cudaGraphDestroy(g); return r; }
+    }
+    CK(cudaGraphInstantiate(out, g, 0));
+    CK(cudaGraphDestroy(g));
+    CK(cudaGraphUpload(*out, c->compute));
     return PVT_OK;
 }
 
@@ -1005,7 +1040,7 @@ int steps_graph(pvt_ctx* c, int n, bool pf, cudaGraphExec_t* out)
     if (!g) {
         Pass p = local_pass(c);
         p.prefetch = pf;
-        int r = capture_steps_graph(c, p, n, &g);
+        int r = c->lost_mode ? capture_lost_steps_graph(c, p, n, &g) : capture_steps_graph(c, p, n, &g);
         if (r) return r;
     }
     *out = g;
@@ -1026,31 +1061,13 @@ int build_graphs(pvt_ctx* c)
         e = cudaStreamEndCapture(c->compute, &g);
         if (r) return r;
         CK(e);
+        CK(cudaGraphInstantiate(&c->graph, g, 0));
+        CK(cudaGraphDestroy(g));
+        CK(cudaGraphUpload(c->graph, c->compute));
     } else {
-        // one graph per step: the local pass, then (behind its leaves) the conditional whole-frame pass
-        CK(cudaGraphCreate(&g, 0));
-        CK(cudaStreamBeginCaptureToGraph(c->compute, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-        r = launch_step_kernels(c, lp, false, true);
-        e = cudaStreamEndCapture(c->compute, nullptr);
-        if (r) return r;
-        CK(e);
-        size_t nn = 0, ne = 0;
-        CK(cudaGraphGetNodes(g, nullptr, &nn));
-        std::vector<cudaGraphNode_t> nodes(nn);
-        CK(cudaGraphGetNodes(g, nodes.data(), &nn));
-        CK(cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &ne));   // _v2: the graph has programmatic edges
-        std::vector<cudaGraphNode_t> from(ne), to(ne);
-        std::vector<cudaGraphEdgeData> ed(ne);
-        if (ne) CK(cudaGraphGetEdges_v2(g, from.data(), to.data(), ed.data(), &ne));
-        std::vector<cudaGraphNode_t> leaves;
-        for (cudaGraphNode_t n : nodes)
-            if (std::find(from.begin(), from.end(), n) == from.end()) leaves.push_back(n);
-        r = add_global_tail(c, g, leaves.data(), leaves.size());
-        if (r) return r;
+        // the local pass, then (behind its leaves) the conditional whole-frame pass
+        if ((r = capture_lost_steps_graph(c, lp, 1, &c->graph))) return r;
     }
-    CK(cudaGraphInstantiate(&c->graph, g, 0));
-    CK(cudaGraphDestroy(g));
-    CK(cudaGraphUpload(c->graph, c->compute));
     for (cudaGraphExec_t* ge : {&c->graph_multi, &c->graph_long, &c->graph_pf, &c->graph_multi_pf, &c->graph_long_pf})
         if (*ge) { cudaGraphExecDestroy(*ge); *ge = nullptr; }
     for (int a = 0; a < 2; ++a)
@@ -1807,11 +1824,12 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             };
             int group = fits(g_long, kLongStep) ? kLongStep : fits(g_multi, kMultiStep) ? kMultiStep : 1;
             cudaGraphExec_t ge = group == kLongStep ? g_long : g_multi;
-            if (g_long && !batch) {
+            static const bool lost_multi = [] { const char* e = getenv("PVT_LOST_MULTI"); return !(e && *e == '0'); }();
+            if ((g_long || (c->lost_mode && lost_multi)) && !batch) {
                 // latency shape: everything up to the next result read-back (at most 64 steps) in ONE launch
                 int n = n_steps - s;
                 if (collect_every > 0) n = std::min(n, collect_every - (s % collect_every));
-                n = std::min(n, kMaxGraphSteps);
+                n = std::min(n, c->lost_mode ? 16 : kMaxGraphSteps);   // (every step of a lost-mode graph carries a whole-frame pass as the body of its IF node)
                 if (n > 1) {
                     int r3 = steps_graph(c, n, pf, &ge);
                     if (r3) return r3;
@@ -1820,7 +1838,7 @@ int pvt_submit_sequence(pvt_ctx* c, int n_steps, int n_frames, const pvt_frame* 
             }
             if (group > 1) {
                 CK(cudaGraphLaunch(ge, c->compute));
-                c->launches += (int64_t)group * (c->kps + (pf ? 1 : 0));
+                c->launches += (int64_t)group * (c->kps + (pf ? 1 : 0) + (c->lost_mode ? c->kps_global : 0));
                 c->submitted += group;
                 s += group - 1;
                 if (collect_every <= 0 || (s + 1) % collect_every != 0) continue;

@@ -114,6 +114,32 @@ def test_gpu_ghc_async_sequence_and_two_tracks():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["auto", "tc_global", "tc"])
+@pytest.mark.parametrize("name", ["reacquire", "reacquire_odd"])
+def test_gpu_ghc_async_sequence_single_track_n_step_graphs(name, kernel):
+    """One track, the whole clip enqueued at once: sequences of up to 16 steps are ONE graph launch in this mode too (a conditional
+    node per step), the local pass in the latency shape; the track gets lost and is re-acquired INSIDE such a graph.  Same cv2
+    golden; kernel "tc_global" / "tc": the whole-frame pass on the tensor cores."""
+    import torch
+    c, tk, g = load(name)
+    frames, roi = c["frames"], c["roi"]
+    n, H, W, _ = frames.shape
+    dev = torch.from_numpy(frames).cuda()
+    kern = {"auto": pvt.KERNEL_AUTO, "tc_global": pvt.KERNEL_TC_GLOBAL, "tc": pvt.KERNEL_TC}[kernel]
+    with pvt.Tracker(W, H, roi[2], roi[3], search_radius_x=tk["rx"], search_radius_y=tk["ry"], lost_frame_threshold=tk["lost_threshold"],
+                     ncc_global_confidence=tk.get("global_conf", 0.60), kernel=kern) as tr:
+        tr.init_track(0, pvt.device_frame(dev[0].data_ptr(), W * 3, stream=0), roi, stream=0)
+        ring = [[pvt.Frame(0, pvt.FMT_BGR8, pvt.MEM_DEVICE, 0, dev[k].data_ptr(), W * 3)] for k in range(1, n)]
+        tr.submit_sequence(n - 1, ring)
+        res = tr.collect(n - 1)
+        _, templ = tr.get_state(0)
+    got = np.array([(r["x"], r["y"], r["w"], r["h"], float(r["conf"]), r["moved"], r["updated"], r["searched"], 0, 0) for r in res[:, 0]], np.float64)
+    check(got, g["records"], f"async single track ({kernel})")
+    assert (got[:, 7] == 2).sum() == META[name]["global_frames"] > 0
+    assert np.array_equal(templ, g["templ"])
+
+
+@pytest.mark.gpu
 def test_gpu_ghc_checkpoint_resume_in_lost_state():
     name = "reacquire"
     c, tk, g = load(name)
