@@ -1829,6 +1829,23 @@ __global__ void __launch_bounds__(256) k_track_refresh(Ctx c, int track)
     finish_template(c, track, t, sm_f, red, w, h);
 }
 
+// PVT_KERNEL_TC_GLOBAL: the local pass runs the FP32 kernels and its update does not maintain the template's 8-bit digits (4 us of
+// a 38 us step); the whole-frame pass derives them here, right before k_ncc_tc, for the tracks it owns in this step.
+__global__ void __launch_bounds__(256) k_track_digits(Ctx c)
+{
+    extern __shared__ float sm_f[];
+    const int track = blockIdx.x;
+    TrackState& t = c.tracks[track];
+    unsigned long long step;
+    if (!track_stepped_ld(c, t, step)) return;
+    const float* tp_ = c.templ + (size_t)track * c.mth * c.mtw;
+    const int w = t.w, h = t.h;
+    const double mean = t.mean;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) sm_f[i] = tp_[i];
+    __syncthreads();
+    write_digits(c, track, t, sm_f, mean, w, h);
+}
+
 // =============================================================================================
 // (5) track_update: peak -> gates -> bbox -> EMA -> next frame's template statistics, by ONE CTA per track.
 //     main.cpp:150-161.  bestVal is the float peak widened to double and compared in double

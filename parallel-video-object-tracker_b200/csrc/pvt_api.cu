@@ -724,6 +724,7 @@ Pass local_pass(const pvt_ctx* c)
     Pass p;
     p.d = c->d; p.tile = c->tile; p.tmap = c->tmap; p.ncc_smem = c->ncc_smem; p.rowsum_warps = c->rowsum_warps; p.rowsum_pw = c->rowsum_pw;
     p.tc = c->tc; p.tc_smem = c->tc_smem; p.tmap8 = c->tmap8;
+    if (c->params.kernel == PVT_KERNEL_TC_GLOBAL) p.d.tdig = nullptr;   // the FP32 local pass keeps no template digits: k_track_digits (whole-frame pass)
     p.colprefix_chunks = c->colprefix_chunks; p.stat = c->stat; p.fused = c->fused; p.fused_smem = c->fused_smem; p.local = c->local; p.local_smem = c->local_smem; p.fringe = c->fringe; p.fringe_smem = c->fringe_smem; p.roi_ingest = c->roi_ingest;
     return p;
 }
@@ -844,6 +845,20 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     const bool ksplit = kern == PVT_KERNEL_AUTO ? p.tile.pj * p.tile.pd > 1
                                                              : (kern == PVT_KERNEL_TC && !tc && p.tile.pj * p.tile.pd > 1);
     const bool fork = capturing && ksplit;
+    // PVT_KERNEL_TC_GLOBAL: the template digits of the tracks this whole-frame pass owns (k_track_digits), beside the statistics
+    bool join_dig = false;
+    if (tc && d.global_pass && c->params.kernel == PVT_KERNEL_TC_GLOBAL) {
+        if (capturing) {
+            CK(cudaEventRecord(c->ev_fork, c->compute));
+            CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
+            k_track_digits<<<d.max_tracks, 256, c->templ_smem, c->aux2>>>(d);
+            CK(cudaEventRecord(c->ev_join2, c->aux2));
+            join_dig = true;
+        } else {
+            k_track_digits<<<d.max_tracks, 256, c->templ_smem, c->compute>>>(d);
+            { int r = dbg(c, "k_track_digits"); if (r) return r; }
+        }
+    }
     cudaStream_t sstats = c->compute;
     if (fork) {
         CK(cudaEventRecord(c->ev_fork, c->compute));
@@ -886,6 +901,7 @@ int launch_step_kernels(pvt_ctx* c, const Pass& p, bool profile, bool capturing 
     }
     if (tc) {
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 0, c->compute); if (r) return r; }
+        if (join_dig) CK(cudaStreamWaitEvent(c->compute, c->ev_join2, 0));
         k_ncc_tc<<<(unsigned)(d.max_tracks * p.tc.mtiles * p.tc.xtiles), kTcThreads, p.tc_smem, c->compute>>>(d, p.tc, p.tmap8);
         if (profile) { int r = pnode(c, CLS_SEARCH_KERNEL, 1, c->compute); if (r) return r; }
         if (profile) { int r = pnode(c, CLS_NCC, 1, c->compute); if (r) return r; }
@@ -1203,7 +1219,7 @@ int enqueue_step(pvt_ctx* c, int n_frames, const pvt_frame* frames, bool hold)
             k_step_advance<<<1, 32, 0, c->compute>>>(gp.d);
             { int r2 = dbg(c, "k_step_advance"); if (r2) return r2; }
             const bool gtc = wants_tc(c->params.kernel) && gp.tc.XW > 0;   // ingest, statistics (1 or 2 kernels), k_ncc_tc, update
-            c->launches += c->kps_global + (gtc ? (gp.stat.NX > 0 ? 4 : 5) : pass_kernels(gp.tile, gp.fringe, gp.stat));
+            c->launches += c->kps_global + (gtc ? (gp.stat.NX > 0 ? 4 : 5) + (c->params.kernel == PVT_KERNEL_TC_GLOBAL ? 1 : 0) : pass_kernels(gp.tile, gp.fringe, gp.stat));
         }
     } else if (c->profiling) {
         // measurement pass: the same graph with event-record nodes around every kernel class, one step at a time
@@ -1557,6 +1573,7 @@ int pvt_create(pvt_ctx** out, const pvt_params* params, const pvt_config* cfg)
         CR(raise_smem((const void*)k_ncc_finalize, c->templ_smem));
         CR(raise_smem((const void*)k_track_init, c->templ_smem));
         CR(raise_smem((const void*)k_track_refresh, c->templ_smem));
+        CR(raise_smem((const void*)k_track_digits, c->templ_smem));
     }
     if (c->lost_mode) CR(build_global_pass(c, prop.multiProcessorCount));
     CR(upload_params(c));
