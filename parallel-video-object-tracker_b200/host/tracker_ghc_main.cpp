@@ -9,7 +9,7 @@
 // Differences forced by this image (no OpenCV C++, no video codecs, no display):
 //   * input is a raw BGR clip:   magic "PVTBGR1\n", int32 W, H, N, then N*H*W*3 bytes (first frame = template frame)
 //   * the ROI comes from --roi x,y,w,h instead of cv::selectROI (:116); constants may be overridden for tests with
-//     --radius R, --lost N, --global C (the reference hard-codes them)
+//     --radius R, --lost N, --global C (the reference hard-codes them); --tc-global selects PVT_KERNEL_TC_GLOBAL
 //   * the per-frame box goes to --out FILE as CSV instead of being drawn (:241)
 //   * --cpu is rejected: the library has no CPU path (the CPU mode is restated in oracle/, test-only)
 #include <chrono>
@@ -45,6 +45,7 @@ int main(int argc, char** argv)
         else if (arg == "--lost" && i + 1 < argc) p.lost_frame_threshold = std::atoi(argv[++i]);
         else if (arg == "--global" && i + 1 < argc) p.ncc_global_confidence = std::atof(argv[++i]);
         else if (arg == "--gpu-formula") p.formula = PVT_FORMULA_EPS;   // score like the reference's CUDA kernels, not like --cpu
+        else if (arg == "--tc-global") p.kernel = PVT_KERNEL_TC_GLOBAL; // whole-frame re-acquisition search (:186-193) on the tensor cores (8-bit sources)
     }
     if (mode == "cpu") { std::cerr << "--cpu is not available: libpvt has no CPU path (see oracle/ for the CPU restatement)\n"; return -1; }
     std::ifstream f(video_path, std::ios::binary);

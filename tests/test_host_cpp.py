@@ -87,8 +87,10 @@ def test_ghc_cli_builds_and_rejects(built, tmp_path):
 
 
 @pytest.mark.gpu
-def test_ghc_cli_reacquires_like_the_golden(built, tmp_path):
-    """tracker_ghc twin: local search -> lost -> whole-frame search -> re-acquired, as cv2 4.13.0 does it."""
+@pytest.mark.parametrize("extra", [[], ["--tc-global"]])
+def test_ghc_cli_reacquires_like_the_golden(built, tmp_path, extra):
+    """tracker_ghc twin: local search -> lost -> whole-frame search -> re-acquired, as cv2 4.13.0 does it.
+    --tc-global: the whole-frame search on the tensor cores (PVT_KERNEL_TC_GLOBAL), same golden."""
     import json
     import zlib
     from tools import synth
@@ -101,7 +103,7 @@ def test_ghc_cli_reacquires_like_the_golden(built, tmp_path):
     roi = ",".join(str(v) for v in c["roi"])
     tk = m["track"]
     r = subprocess.run([os.path.join(built, "tracker_ghc"), str(tmp_path / "c.bgr"), "--first", "--roi", roi, "--out", str(tmp_path / "o.csv"),
-                        "--radius", str(tk["rx"]), "--lost", str(tk["lost_threshold"])], capture_output=True, text=True)
+                        "--radius", str(tk["rx"]), "--lost", str(tk["lost_threshold"])] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "Tracking mode: cuda" in r.stdout and f"Interactive tracking summary: frames={len(c['frames']) - 1}," in r.stdout
     rows = np.genfromtxt(tmp_path / "o.csv", delimiter=",", skip_header=1)
