@@ -247,6 +247,14 @@ PVT_API int pvt_ncc_match_batched_f(int device, int formula, int n, const float*
 PVT_API int pvt_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y,
                            int32_t out[16]);
 
+/* The geometry of the tensor-core search (PVT_KERNEL_TC, k_ncc_tc) for the local windows (whole_frame_pass = 0) or for the
+ * whole-frame pass of the lost-object mode (1: tracker_ghc/src/main.cpp:186-193, the radii are ignored); pure host logic.
+ * out = {candidate columns per accumulator XW, column tiles per window, 128-row tiles per window, K-steps of 32 image columns,
+ * candidate groups of 8 per accumulator, TMEM columns, depth of the Toeplitz block ring, shared bytes per CTA}.
+ * PVT_ERR_UNSUPPORTED: template higher than 129 rows / wider than 260 columns. */
+PVT_API int pvt_tc_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y,
+                              int whole_frame_pass, int32_t out[8]);
+
 /* The sink side of the reference loop (tracker/src/main.cpp:166  cv::rectangle(frame, bbox, {0,255,0}, 2)): paint the boxes
  * (n x {x, y, w, h}) onto a BGR8 frame, in place, with cv::rectangle's thickness-2 pixel coverage (bit-identical to OpenCV 4.13).
  * frame->memory says where the pixels live: device frames are painted where they are; host frames make the round trip through

@@ -39,7 +39,7 @@ SYMBOLS = [
     "pvt_step", "pvt_submit", "pvt_collect", "pvt_submit_sequence", "pvt_sync", "pvt_get_state", "pvt_set_state", "pvt_get_window_map",
     "pvt_to_gray_f32", "pvt_ncc_match", "pvt_ncc_match_batched", "pvt_profile_enable", "pvt_profile_get",
     "pvt_launch_count", "pvt_timer_start", "pvt_timer_stop", "pvt_trace_enable", "pvt_trace_get",
-    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query", "pvt_ncc_match_batched_f",
+    "pvt_default_params_ghc", "pvt_get_lost_state", "pvt_set_lost_state", "pvt_plan_query", "pvt_tc_plan_query", "pvt_ncc_match_batched_f",
     "pvt_search_kind", "pvt_draw_boxes",
 ]
 
@@ -167,6 +167,16 @@ def plan_query(n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x=80, radius
     out = (C.c_int32 * 16)()
     _ck(lib().pvt_plan_query(sm_count, n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x, radius_y, out))
     return dict(zip(PLAN_FIELDS, out))
+
+
+TC_PLAN_FIELDS = ("xw", "xtiles", "mtiles", "ksteps", "groups", "tmem_cols", "stages", "smem")
+
+
+def tc_plan_query(n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x=80, radius_y=80, whole_frame_pass=False, sm_count=148) -> dict:
+    """The k_ncc_tc geometry pvt_create would derive for the local windows / the whole-frame pass (host logic only)."""
+    out = (C.c_int32 * 8)()
+    _ck(lib().pvt_tc_plan_query(sm_count, n_tracks, templ_w, templ_h, frame_w, frame_h, radius_x, radius_y, 1 if whole_frame_pass else 0, out))
+    return dict(zip(TC_PLAN_FIELDS, out))
 
 
 def device_count() -> int:

@@ -590,7 +590,8 @@ int tc_pick_xw(const Ctx& d, int sm_count)
 
 // PVT_KERNEL_TC: geometry of k_ncc_tc for one pass (window bounds d.Wmax x d.Hmax), its shared memory and the 4-D tensor map
 // (16 B, row, 16-pixel chunk, stream) of the u8 gray plane whose box lands in shared memory chunk-major (ncc_tc.cuh)
-int tc_geometry(pvt_ctx* c, const Ctx& d, int sm_count, TcCfg& g, size_t* smem, CUtensorMap* tmap8)
+// host arithmetic only (pvt_tc_plan_query calls it without a device)
+int tc_shape(const Ctx& d, int sm_count, TcCfg& g, size_t* smem)
 {
     g = TcCfg{};
     g.XW = tc_pick_xw(d, sm_count);
@@ -615,6 +616,13 @@ int tc_geometry(pvt_ctx* c, const Ctx& d, int sm_count, TcCfg& g, size_t* smem, 
     while (g.stages > 2 && smem_of(g.stages) > kSmemBudget - 1024) --g.stages;
     *smem = smem_of(g.stages);
     if (*smem > kSmemBudget - 1024) return fail(PVT_ERR_UNSUPPORTED, "PVT_KERNEL_TC: tile does not fit shared memory");
+    return PVT_OK;
+}
+
+int tc_geometry(pvt_ctx* c, const Ctx& d, int sm_count, TcCfg& g, size_t* smem, CUtensorMap* tmap8)
+{
+    (void)c;
+    { int r = tc_shape(d, sm_count, g, smem); if (r) return r; }
     { int r = raise_smem((const void*)k_ncc_tc, *smem); if (r) return r; }
     if (getenv("PVT_DEBUG_PLAN"))
         fprintf(stderr, "[pvt] tc plan (%s pass): XW=%d xtiles=%d mtiles=%d KS=%d stages=%d tmem=%d smem=%zu\n", d.global_pass ? "whole-frame" : "local", g.XW, g.xtiles,
@@ -1307,6 +1315,23 @@ int pvt_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int fra
     plan_items(g, n_tracks, mtp, sm_count);
     const int32_t v[16] = {g.G, g.C, g.GB, g.bands, g.ctas_band, g.span, g.boxW, g.boxH, g.pj, g.pd, g.cpt, g.n_full, g.n_tail, g.tail_ps,
                            (int32_t)smem, (int32_t)((Wmax > 8 * g.C ? 1 : 0) | (Hmax > kCY * g.G ? 2 : 0))};
+    std::memcpy(out, v, sizeof(v));
+    return PVT_OK;
+}
+int pvt_tc_plan_query(int sm_count, int n_tracks, int templ_w, int templ_h, int frame_w, int frame_h, int radius_x, int radius_y, int whole_frame_pass,
+                      int32_t out[8])
+{
+    if (!out || sm_count <= 0 || n_tracks <= 0 || templ_w <= 0 || templ_h <= 0 || templ_w > frame_w || templ_h > frame_h || radius_x < 0 || radius_y < 0)
+        return fail(PVT_ERR_INVALID, "bad plan query");
+    Ctx d{};
+    d.W = frame_w; d.H = frame_h; d.mtw = templ_w; d.mth = templ_h; d.max_tracks = n_tracks;
+    d.global_pass = whole_frame_pass ? 1 : 0;
+    d.Wmax = whole_frame_pass ? frame_w : std::min(2 * radius_x + 1, frame_w);     // as pvt_create / build_global_pass size the passes
+    d.Hmax = whole_frame_pass ? frame_h : std::min(2 * radius_y + 1, frame_h);
+    TcCfg g{};
+    size_t smem = 0;
+    { int r = tc_shape(d, sm_count, g, &smem); if (r) return r; }
+    const int32_t v[8] = {g.XW, g.xtiles, g.mtiles, g.KS, g.AG, g.tmem_cols, g.stages, (int32_t)smem};
     std::memcpy(out, v, sizeof(v));
     return PVT_OK;
 }

@@ -77,3 +77,23 @@ def test_plan_query_rejects_bad_geometry():
         q(1, 64, 64, 32, 32, 80)
     with pytest.raises(pvt.PvtError):
         q(0, 8, 8, 64, 64, 8)
+
+
+def test_tc_plan_column_tiles_host_logic():
+    """k_ncc_tc geometry (pvt_tc_plan_query, no device): one accumulator where the window fits (the round-2 plans of C2/C4/C5 are
+    unchanged), column tiles for 4K windows and for the whole-frame pass; the limits the kernel's issue code is unrolled for hold."""
+    c5 = pvt.tc_plan_query(64, 64, 64, 1920, 1080, 80, 80)
+    assert (c5["xw"], c5["xtiles"], c5["mtiles"], c5["ksteps"], c5["tmem_cols"]) == (176, 1, 2, 8, 512)
+    small = pvt.tc_plan_query(1, 32, 32, 320, 240, 12, 12)
+    assert (small["xw"], small["xtiles"], small["mtiles"]) == (32, 1, 1)
+    wf = pvt.tc_plan_query(1, 64, 64, 1920, 1080, whole_frame_pass=True)
+    assert wf["xw"] == 112 and wf["xtiles"] == 18 and wf["mtiles"] == 9 and wf["tmem_cols"] == 256   # 17 x 8 of them meet the 1857 x 1017 map: 136 CTAs, one wave
+    assert -(-(1920 - 64 + 1) // wf["xw"]) * -(-(1080 - 64 + 1) // 128) <= 148
+    c3 = pvt.tc_plan_query(1, 128, 128, 3840, 2160, 160, 160)
+    assert c3["xtiles"] >= 2 and c3["xw"] * c3["xtiles"] >= 321 and c3["mtiles"] == 3
+    for p in (c5, small, wf, c3, pvt.tc_plan_query(8, 17, 129, 333, 130, 333, 130), pvt.tc_plan_query(1, 260, 40, 1920, 1080, whole_frame_pass=True)):
+        assert p["xw"] % 16 == 0 and 16 <= p["xw"] <= 256 and p["ksteps"] <= 10 and p["tmem_cols"] >= 2 * p["xw"] and p["smem"] <= 227 * 1024
+        assert p["groups"] == p["xw"] // 8 and p["stages"] >= 2
+    with pytest.raises(pvt.PvtError) as e:                      # 128 candidate rows + th - 1 exceed the 256-row TMA box
+        pvt.tc_plan_query(1, 160, 160, 3840, 2160, 160, 160)
+    assert e.value.code == pvt.ERR_UNSUPPORTED
