@@ -183,6 +183,9 @@ def test_whole_frame_1080p_six_band_tail_split_plan(kernel):
     sm = pvt.device_info(0)["sm_count"]
     plan = pvt.plan_query(1, FC.TW, FC.TH, FC.W, FC.H, FC.W, FC.H, sm_count=sm)
     assert plan["pj"] * plan["pd"] == 1 and plan["bands"] == 6 and plan["n_tail"] > 0 and plan["tail_parts"] >= 2, plan
+    if kernel != "auto":   # the whole-frame pass on the tensor cores: 17 x 8 column / row tiles meet the map
+        tcp = pvt.tc_plan_query(1, FC.TW, FC.TH, FC.W, FC.H, whole_frame_pass=True, sm_count=sm)
+        assert tcp["xtiles"] >= 2 and tcp["xw"] <= 256, tcp
     wf = FC.WF()
     assert wf.crc() == _meta()["wf"]["frames_crc"]
     gold = Hp.golden("filled_wf_1080p.npz")

@@ -186,6 +186,8 @@ def test_tc_whole_map_in_column_tiles_vs_oracle(W, H, tw, th, xw, monkeypatch):
         monkeypatch.setenv("PVT_TC_XW", str(xw))
     else:
         monkeypatch.delenv("PVT_TC_XW", raising=False)
+    plan = pvt.tc_plan_query(1, tw, th, W, H, W, H)             # reads PVT_TC_XW like pvt_create does
+    assert plan["xtiles"] >= 2 and (xw is None or plan["xw"] == xw), plan   # the test cannot silently stop covering the column tiles
     f0, f1 = _whole_map_case(W, H, tw, th, 1000 + W + tw)
     x, y = (W - tw) // 3, (H - th) // 2
     g0, g1 = O.to_gray_f32(f0), O.to_gray_f32(f1)
@@ -214,6 +216,8 @@ def test_tc_c3_4k_windows_in_column_tiles_vs_cv2_golden():
     """BASELINE.json configs[2] (4K, 128 x 128, R 160): the 321-wide window is cut into column tiles."""
     (c, tk) = Hp.clip("c3_4k")
     g = Hp.golden("clip_c3_4k.npz")
+    H, W = c["frames"].shape[1:3]
+    assert pvt.tc_plan_query(1, c["roi"][2], c["roi"][3], W, H, tk.get("rx", 160), tk.get("ry", 160))["xtiles"] >= 2
     recs, templ = pvt.track_clip(c["frames"], c["roi"], search_radius_x=tk.get("rx", 160), search_radius_y=tk.get("ry", 160), kernel=pvt.KERNEL_TC)
     Hp.check_records(records_of(recs), g["records"], "c3_4k (tc)")
     assert np.array_equal(templ, g["templ"])
