@@ -75,7 +75,8 @@ typedef enum pvt_kernel {
                             * GRAY8 -- a GRAYF32 frame is rejected), template height <= 129, template width <= 260. */
     PVT_KERNEL_TC_GLOBAL = 3 /* lost-object mode: the planner's FP32 kernels for the local windows (the single-stream latency
                             * shape is faster there), the tensor-core search for the whole-frame pass only
-                            * (tracker_ghc/src/main.cpp:186-193).  Same creation-time and frame-format rules as PVT_KERNEL_TC. */
+                            * (tracker_ghc/src/main.cpp:186-193).  Same creation-time and frame-format rules as PVT_KERNEL_TC;
+                            * pvt_set_params may switch such a context between AUTO, TC and TC_GLOBAL at any time. */
 } pvt_kernel;
 
 /* frame ingest (utils.hpp:5-14 toGrayF32).  FULL converts whole frames, as the reference does.  ROI converts only each

@@ -1630,6 +1630,13 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
         c->roi_ingest = p->ingest == PVT_INGEST_ROI || (p->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
     }
     if (p->mode != c->params.mode || p->batch_size != c->params.batch_size) c->hold_pending = 0;   // a new cadence starts from a full batch
+    if (c->params.kernel == PVT_KERNEL_TC_GLOBAL && p->kernel == PVT_KERNEL_TC) {
+        // the FP32 local pass of PVT_KERNEL_TC_GLOBAL kept no template digits (k_track_digits derives them per whole-frame pass):
+        // the local tensor-core search needs them for every track from its first step
+        for (int t = 0; t < c->d.max_tracks; ++t)
+            if (c->track_stream[t] >= 0) k_track_refresh<<<1, 256, c->templ_smem, c->compute>>>(c->d, t);
+        CK(cudaGetLastError());
+    }
     c->params = *p;
     c->kps = kernels_per_step(c);
     if (regraph) c->graph_valid = false;

@@ -266,3 +266,24 @@ def test_tc_global_runs_the_fp32_plan_on_local_windows():
         with pytest.raises(pvt.PvtError) as e:
             tr.step([O.to_gray_f32(frames[1])])
         assert e.value.code == pvt.ERR_INVALID
+
+
+def test_tc_global_to_tc_switch_rebuilds_the_template_digits():
+    """A PVT_KERNEL_TC_GLOBAL context keeps no template digits in its FP32 local pass; switching it to PVT_KERNEL_TC
+    (pvt_set_params) must derive them for the templates as they are NOW (after EMA updates), not as they were at init."""
+    (c, tk) = Hp.clip("small")
+    g = Hp.golden("clip_small.npz")
+    frames, roi = c["frames"], c["roi"]
+    H, W = frames.shape[1:3]
+    n = len(frames)
+    cut = n // 2
+    with pvt.Tracker(W, H, roi[2], roi[3], search_radius_x=tk.get("rx", 80), search_radius_y=tk.get("ry", 80), kernel=pvt.KERNEL_TC_GLOBAL) as tr:
+        tr.init_track(0, frames[0], roi)
+        got = [tr.step([frames[k]])[0] for k in range(1, cut)]
+        assert any(int(r["updated"]) for r in got)              # the template has moved on since init
+        tr.set_params(kernel=pvt.KERNEL_TC)
+        assert tr.search_kind()[0] == "k_ncc_tc"
+        got += [tr.step([frames[k]])[0] for k in range(cut, n)]
+        _, templ = tr.get_state(0)
+    Hp.check_records(records_of(np.array(got)), g["records"], "small (tc_global -> tc)")
+    assert np.array_equal(templ, g["templ"])
