@@ -48,8 +48,8 @@ GEOMS = [(320, 240, 32, 32, 80), (400, 300, 37, 29, 40), (640, 360, 200, 40, 60)
 @pytest.mark.parametrize("W,H,tw,th,R", GEOMS)
 @pytest.mark.parametrize("kernel", ["auto", "tc"])
 def test_winstats_equals_two_kernel_statistics(W, H, tw, th, R, kernel):
-    if kernel == "tc" and (2 * R + 1 > 256 or 2 * R + 1 + tw > 306 or th > 129):
-        pytest.skip("outside PVT_KERNEL_TC's geometry")
+    if kernel == "tc" and (tw > 260 or th > 129):
+        pytest.skip("outside PVT_KERNEL_TC's geometry")      # (wide windows / templates run in column tiles: the 200-wide template here)
     c = synth.make_clip(synth.ClipSpec(seed=7 + tw, W=W, H=H, tw=tw, th=th, n_frames=3, R=R))
     frames, roi = c["frames"], c["roi"]
     kw = {"kernel": pvt.KERNEL_TC} if kernel == "tc" else {}
