@@ -1630,9 +1630,10 @@ int pvt_set_params(pvt_ctx* c, const pvt_params* p)
         c->roi_ingest = p->ingest == PVT_INGEST_ROI || (p->ingest == PVT_INGEST_AUTO && tiles <= 0.5 * frames_px);
     }
     if (p->mode != c->params.mode || p->batch_size != c->params.batch_size) c->hold_pending = 0;   // a new cadence starts from a full batch
-    if (c->params.kernel == PVT_KERNEL_TC_GLOBAL && p->kernel == PVT_KERNEL_TC) {
+    if (c->params.kernel == PVT_KERNEL_TC_GLOBAL && p->kernel != PVT_KERNEL_TC_GLOBAL) {
         // the FP32 local pass of PVT_KERNEL_TC_GLOBAL kept no template digits (k_track_digits derives them per whole-frame pass):
-        // the local tensor-core search needs them for every track from its first step
+        // a local tensor-core search needs them for every track from its first step -- re-derived whenever the context leaves this
+        // kernel choice (also towards AUTO: a later switch to PVT_KERNEL_TC must not meet digits of an older template)
         for (int t = 0; t < c->d.max_tracks; ++t)
             if (c->track_stream[t] >= 0) k_track_refresh<<<1, 256, c->templ_smem, c->compute>>>(c->d, t);
         CK(cudaGetLastError());
